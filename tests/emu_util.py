@@ -1,0 +1,73 @@
+"""ctypes driver for tests/emu/libemu_conv.so (CPU emulation of the CUDA conv tile code)."""
+import ctypes
+import os
+import subprocess
+
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "emu", "libemu_conv.so")
+SRC = os.path.join(HERE, "emu", "emu_conv.cpp")
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int32) for k in
+                ("B", "Cin", "Cout", "Tin", "Tout", "K", "stride", "dil", "pad", "refl", "groups")]
+
+
+class Epilogue(ctypes.Structure):
+    _fields_ = [("bias", ctypes.c_void_p), ("res", ctypes.c_void_p), ("mask", ctypes.c_void_p),
+                ("slope", ctypes.c_float), ("beta", ctypes.c_float)]
+
+
+def build():
+    deps = [SRC] + [os.path.join(HERE, "..", "vibravox_b200", "csrc", f)
+                    for f in ("gemm_conv.cuh", "conv_plan.h")]
+    if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", SO, SRC])
+    return ctypes.CDLL(SO)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = build()
+    return _lib
+
+
+def tout(Tin, K, s, d, pad):
+    return (Tin + 2 * pad - d * (K - 1) - 1) // s + 1
+
+
+def transpose_weight(w, groups):
+    """W[co][ci_g][k] -> Wt[g][ci_g][co_g][k]"""
+    Cout, Cin_g, K = w.shape
+    return w.view(groups, Cout // groups, Cin_g, K).permute(0, 2, 1, 3).contiguous()
+
+
+def scatter_weight(w, groups):
+    """W[co][ci_g][k] -> Wk[g][(ci,k)][co_g]"""
+    Cout, Cin_g, K = w.shape
+    return w.view(groups, Cout // groups, Cin_g * K).permute(0, 2, 1).contiguous()
+
+
+def ref_padded(x, pad, refl):
+    if refl:
+        x = F.pad(x, (refl, refl), mode="reflect")
+    if pad - refl:
+        x = F.pad(x, (pad - refl, pad - refl))
+    return x
+
+
+def emu(mode, desc, a, b, out, bias=None, res=None, mask=None, slope=1.0, beta=0.0):
+    e = Epilogue(bias.data_ptr() if bias is not None else None,
+                 res.data_ptr() if res is not None else None,
+                 mask.data_ptr() if mask is not None else None, slope, beta)
+    r = lib().emu_conv(mode, ctypes.byref(desc), ctypes.c_void_p(a.data_ptr()),
+                       ctypes.c_void_p(b.data_ptr()), ctypes.byref(e), ctypes.c_void_p(out.data_ptr()))
+    assert r == 0, r
+    return out

@@ -1,0 +1,113 @@
+// Launch planning for the Conv1d family: tile-config choice, grid shape, GemmP fill.
+// Plain C++ (no CUDA) so tests/emu can drive the identical plan on the CPU.
+#pragma once
+#include "../../include/vbx.h"
+#include "gemm_conv.cuh"
+
+namespace vbx {
+
+inline int plan_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+inline int pick_tm(int M) {
+  if (M > 64) return 128;
+  if (M > 32) return 64;
+  if (M > 16) return 32;
+  if (M > 8) return 16;
+  if (M > 4) return 8;
+  return 4;
+}
+inline int tn_of(int tm) { return tm >= 32 ? 128 : 256; }
+
+// returns NULL when the descriptor is valid, else the complaint
+inline const char* check_desc_msg(const vbx_conv_desc* d, int* code) {
+  *code = VBX_BAD_POINTER;
+  if (!d) return "conv: null descriptor";
+  *code = VBX_BAD_SHAPE;
+  if (!(d->B > 0 && d->Cin > 0 && d->Cout > 0 && d->Tin > 0 && d->Tout > 0 && d->K > 0 &&
+        d->stride > 0 && d->dil > 0 && d->pad >= 0 && d->refl >= 0 && d->groups > 0))
+    return "conv: non-positive dimension";
+  if (!(d->Cin % d->groups == 0 && d->Cout % d->groups == 0))
+    return "conv: channels not divisible by groups";
+  if (!(d->refl <= d->pad && d->refl <= d->Tin - 1))
+    return "conv: reflect halo larger than pad or than the signal";
+  long long span = (long long)d->Tin + 2LL * d->pad - (long long)d->dil * (d->K - 1) - 1;
+  if (!(span >= 0 && span / d->stride + 1 == d->Tout))
+    return "conv: Tout inconsistent with Tin/pad/K/stride/dil";
+  *code = VBX_UNSUPPORTED;
+  if (!((long long)d->B * d->Cin * d->Tin < (1LL << 31) &&
+        (long long)d->B * d->Cout * d->Tout < (1LL << 31)))
+    return "conv: tensor too large for 32-bit tile indexing";
+  if (d->stride > 65535) return "conv: stride too large";
+  *code = 0;
+  return nullptr;
+}
+
+inline void fill(GemmP& P, const vbx_conv_desc* d) {
+  P.B = d->B; P.Cin = d->Cin; P.Cout = d->Cout; P.Tin = d->Tin; P.Tout = d->Tout; P.K = d->K;
+  P.stride = d->stride; P.dil = d->dil; P.pad = d->pad; P.refl = d->refl; P.groups = d->groups;
+  P.Cin_g = d->Cin / d->groups; P.Cout_g = d->Cout / d->groups;
+  P.mtiles = 1; P.split = 0;
+  P.W = nullptr; P.X = nullptr; P.DY = nullptr; P.Y = nullptr;
+  P.bias = nullptr; P.res = nullptr; P.mask = nullptr; P.slope = 1.f; P.beta = 0.f;
+}
+inline void fill_epi(GemmP& P, const vbx_epilogue* e) {
+  if (!e) return;
+  P.bias = e->bias; P.res = e->res; P.mask = e->mask; P.slope = e->slope; P.beta = e->beta;
+}
+
+struct Plan { int tm; bool bk; int grid[3]; };
+
+inline Plan plan_conv(int mode, GemmP& P) {
+  Plan pl;
+  pl.bk = false;
+  if (mode == FWD) {
+    const int M = P.Cout_g;
+    pl.tm = pick_tm(M);
+    P.mtiles = plan_cdiv(M, pl.tm);
+    pl.grid[0] = plan_cdiv((long long)P.B * P.Tout, tn_of(pl.tm));
+    pl.grid[1] = P.mtiles * P.groups; pl.grid[2] = 1;
+    pl.bk = P.stride >= 16;
+  } else if (mode == DGRAD) {
+    const int M = P.Cin_g;
+    pl.tm = pick_tm(M);
+    P.mtiles = plan_cdiv(M, pl.tm);
+    const long long Up = plan_cdiv(P.Tin, P.stride);
+    pl.grid[0] = plan_cdiv((long long)P.B * Up, tn_of(pl.tm));
+    pl.grid[1] = P.mtiles * P.groups; pl.grid[2] = P.stride;
+  } else if (mode == WGRAD) {
+    const int M = P.Cout_g;
+    pl.tm = pick_tm(M);
+    const int tn = tn_of(pl.tm);
+    P.mtiles = plan_cdiv(M, pl.tm);
+    const int ntiles = plan_cdiv((long long)P.Cin_g * P.K, tn);
+    const long long red = (long long)P.B * P.Tout;
+    // split the (b,t) reduction so that the grid covers the 148 SMs a few times over
+    long long tiles = (long long)ntiles * P.mtiles * P.groups;
+    long long want = (148 * 4 + tiles - 1) / tiles;
+    long long max_split = (red + 16 * 8 - 1) / (16 * 8);   // >= 8 chunks per slice
+    if (want > max_split) want = max_split;
+    if (want < 1) want = 1;
+    if (want > 65535) want = 65535;
+    long long split = (red + want - 1) / want;
+    split = (split + 15) / 16 * 16;
+    P.split = (int)split;
+    pl.grid[0] = ntiles; pl.grid[1] = P.mtiles * P.groups; pl.grid[2] = plan_cdiv(red, split);
+    pl.bk = true;
+  } else {  // SCATTER
+    const int M = P.Cin_g * P.K;
+    pl.tm = pick_tm(M);
+    P.mtiles = plan_cdiv(M, pl.tm);
+    pl.grid[0] = plan_cdiv((long long)P.B * P.Tout, tn_of(pl.tm));
+    pl.grid[1] = P.mtiles * P.groups; pl.grid[2] = 1;
+  }
+  return pl;
+}
+
+using C128 = Cfg<128, 128, 8, 8>;
+using C64 = Cfg<64, 128, 8, 4>;
+using C32 = Cfg<32, 128, 4, 4>;
+using C16 = Cfg<16, 256, 4, 4>;
+using C8 = Cfg<8, 256, 2, 4>;
+using C4 = Cfg<4, 256, 1, 4>;
+
+}  // namespace vbx
