@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""EBEN BWE train-step throughput (audio-seconds per second @16 kHz) - BASELINE.json metric.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference ...                      # the CPU port of the reference path (oracle/)
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the definition of every key.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR = 16000
+METRIC = "EBEN BWE train-step audio-sec/sec @16kHz"
+
+
+def synthetic_pairs(batch: int, samples: int, seed: int):
+    """0.1*randn clamped to +-1, (B,1,samples) x2, host generator (seed 42 + rank)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    air = (0.1 * torch.randn(batch, 1, samples, generator=g)).clamp(-1, 1)
+    body = (0.1 * torch.randn(batch, 1, samples, generator=g)).clamp(-1, 1)
+    return body, air
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, val in zip(names, r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def layer_microbench(device, B, L):
+    """Per-kernel roofline evidence, measured live with CUDA events on the launching stream:
+    (a) the dominant kernel of the step = the dense MelGAN stage 4 implicit-GEMM conv,
+    (b) the HBM-bound generator residual-unit convs (north_star's 60 % target)."""
+    import torch
+    from vibravox_b200 import ops
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    tens = peaks.get("bf16_tflops_sustained", 1400.0)
+    src = "measured" if peaks else "fallback"
+
+    def timeit(fn, reps=10, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e-3
+
+    out = []
+    # (a) MelGAN stage 4: 1024 -> 1024, k41, s4, groups 4 on (B,1024,748)
+    T3 = ((L - 41 + 40) // 4 + 1 - 41 + 40) // 4 + 1
+    T3 = (T3 - 41 + 40) // 4 + 1
+    g = ops.ConvGeom(1024, 1024, 41, 4, 1, 20, 0, 4)
+    x = torch.randn(B, 1024, T3, device=device)
+    w = torch.randn(1024, 256, 41, device=device) * 0.01
+    bias = torch.zeros(1024, device=device)
+    To = g.tout(T3)
+    flops = 2.0 * B * To * 1024 * 256 * 41
+    byt = 4.0 * (B * 1024 * T3 + B * 1024 * To + w.numel())
+    t = timeit(lambda: ops.conv1d_fwd(x, w, g, bias=bias, slope=0.2), reps=5, warm=2)
+    out.append({"kernel": "gemm_conv_kernel<FWD> melgan.4 (1024->1024,k41,s4,g4)", "bound": "tensor",
+                "achieved": flops / t / 1e12, "peak": tens, "unit": "TFLOP/s", "frac": flops / t / 1e12 / tens,
+                "ms": t * 1e3, "algorithmic_bytes": byt, "peak_source": src + " bf16 sustained", "traffic": None})
+    # (b) generator residual unit convs at C=32, T=11968
+    Tb = (L + 32) // 4
+    for C, T in ((32, Tb), (64, Tb // 2), (128, Tb // 8)):
+        xg = torch.randn(B, C, T, device=device)
+        w1 = torch.randn(C, C, 3, device=device) * 0.1
+        w2 = torch.randn(C, C, 1, device=device) * 0.1
+        g1 = ops.ConvGeom(C, C, 3, 1, 3, 3, 3, 1)
+        g2 = ops.ConvGeom(C, C, 1, 1, 1, 0, 0, 1)
+        byt = 4.0 * 2 * B * C * T
+        t1 = timeit(lambda: ops.conv1d_fwd(xg, w1, g1))
+        t2 = timeit(lambda: ops.conv1d_fwd(xg, w2, g2, res=xg, slope=0.01))
+        for nm, tt, bb in (("dilated k3 d3", t1, byt), ("pointwise+lrelu+res", t2, byt * 1.5)):
+            out.append({"kernel": f"gemm_conv_kernel<FWD> residual {nm} C={C} T={T}", "bound": "hbm",
+                        "achieved": bb / tt / 1e9, "peak": hbm, "unit": "GB/s", "frac": bb / tt / 1e9 / hbm,
+                        "ms": tt * 1e3, "algorithmic_bytes": bb, "peak_source": src + " copy", "traffic": None})
+    return out
+
+
+def run_ours(args):
+    import torch
+    from vibravox_b200 import _lib, parallel
+    import vibravox_b200
+
+    rank, local_rank, world = parallel.init_from_env("nccl")
+    if world != args.gpus:
+        assert world == 1 and args.gpus == 1, f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B, S = args.batch, int(args.seconds * SR)
+    lm = vibravox_b200.build_model(seed=42, device=dev)
+    L = S - (S + 32) % lm.generator.multiple
+    body_h, air_h = synthetic_pairs(B, S, parallel.rank_seed(42, rank))
+    body_h, air_h = body_h.pin_memory(), air_h.pin_memory()
+    body_d, air_d = body_h.to(dev), air_h.to(dev)
+    batch = {"audio_body_conducted": body_d, "audio_airborne": air_d}
+
+    def step():
+        lm.training_step(batch)
+
+    def timed(fn, k):
+        parallel.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        parallel.barrier()
+        wall = time.perf_counter() - t0
+        return parallel.max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev), wall
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    n0 = _lib.launch_count()
+    t_dev, _ = timed(step, args.steps)
+    launches = _lib.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    audio_s = world * B * L / SR
+    value = audio_s * args.steps / t_dev
+
+    # e2e: the public call with HOST buffers; H2D of the step's inputs and D2H of its losses inside the timed region
+    stage_body, stage_air = torch.empty_like(body_d), torch.empty_like(air_d)
+    loss_h = torch.empty(2, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        stage_body.copy_(body_h, non_blocking=True)
+        stage_air.copy_(air_h, non_blocking=True)
+        lm.training_step({"audio_body_conducted": stage_body, "audio_airborne": stage_air})
+        loss_h[0:1].copy_(lm.logged["train/generator/backprop_loss"].view(1), non_blocking=True)
+        loss_h[1:2].copy_(lm.logged["train/discriminator/backprop_loss"].view(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_step()
+    _, wall = timed(e2e_step, args.steps)
+    wall = parallel.max_over_ranks(wall, dev)
+    e2e = {"value": audio_s * args.steps / wall, "unit": "audio-s/s",
+           "h2d_bytes_per_step": int(2 * body_h.numel() * 4), "d2h_bytes_per_step": 8,
+           "losses": [float(loss_h[0]), float(loss_h[1])]}
+
+    if rank != 0:
+        return
+    kernels = layer_microbench(dev, B, L) if not args.no_micro else []
+    roof = dict(kernels[0]) if kernels else None
+    line = {
+        "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": f"EBEN BWE full train step (gen+disc+MR-STFT/FM/hinge, EMA balancing, 2x Adam) "
+                               f"bs={B}x{args.seconds:g}s@16kHz per GPU (L={L} after cut_to_valid_length), "
+                               f"m=4 n=32 p=2 q=4 min_channels=24, reference schedule",
+                   "batch_per_gpu": B, "samples": L, "parallelism": f"dp{world}",
+                   "l2": "per-step working set (activations ~ GBs) >> 126 MB L2; no explicit flush"},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": roof, "kernel_rooflines": kernels,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args, bounded=True)
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(args, bounded: bool):
+    """The oracle port of the reference path on the host cores (kind 'port'), bounded sample."""
+    import torch
+    from oracle import eben_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = args.cpu_batch
+    S = int(args.seconds * SR)
+    body, air = synthetic_pairs(B, S, 42)
+    step = O.OracleEBENStep(seed=42)
+    step.step(body, air)                                  # warm-up (allocator, oneDNN primitives)
+    k = args.cpu_steps
+    t0 = time.perf_counter()
+    for _ in range(k):
+        step.step(body, air)
+    dt = (time.perf_counter() - t0) / k
+    L = S - (S + 32) % 256
+    return {"value": B * L / SR / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
+            "s_per_step": dt, "sample": f"{k} timed steps (+1 warm-up) of the same train step at bs={B}x{args.seconds:g}s, "
+                                        f"fp32, torch CPU ({cores} threads)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_baseline(args, bounded=True)
+    S = int(args.seconds * SR)
+    L = S - (S + 32) % 256
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "audio-s/s",
+            "n_gpus": args.gpus, "steps": args.cpu_steps, "warmup": 1, "ms_per_step": cb["s_per_step"] * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": f"EBEN BWE full train step, CPU port of the reference path, bounded sample "
+                                   f"bs={args.cpu_batch}x{args.seconds:g}s@16kHz (L={L})",
+                       "batch_per_gpu": args.cpu_batch, "samples": L, "parallelism": "host-cpu"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--seconds", type=float, default=3.0)
+    ap.add_argument("--cpu-batch", type=int, default=4)
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--no-micro", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

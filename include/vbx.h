@@ -22,6 +22,11 @@ extern "C" {
 #endif
 
 #define VBX_ABI_VERSION 1
+#if defined(__GNUC__)
+#define VBX_API __attribute__((visibility("default")))
+#else
+#define VBX_API
+#endif
 
 enum vbx_status { VBX_OK = 0, VBX_BAD_SHAPE = -1, VBX_BAD_POINTER = -2, VBX_UNSUPPORTED = -3 };
 
@@ -44,43 +49,43 @@ typedef struct {
   float beta;
 } vbx_epilogue;
 
-int vbx_abi_version(void);
-const char* vbx_last_error(void);
+VBX_API int vbx_abi_version(void);
+VBX_API const char* vbx_last_error(void);
 /* number of kernels this library has launched since load (for bench.py's gpu_launches) */
-uint64_t vbx_launch_count(void);
+VBX_API uint64_t vbx_launch_count(void);
 /* opt-in tensor-core path for dense layers (0 = fp32 FMA everywhere) */
-int vbx_set_tensor_core_mode(int mode);
+VBX_API int vbx_set_tensor_core_mode(int mode);
 
 /* ---- Conv1d family ------------------------------------------------------------------
  * replaces aten::conv1d / aten::reflection_pad1d / aten::leaky_relu / aten::add issued by
  * eben_generator.py:112-166,241-249,272-280,295-316, eben_discriminator.py:66-157,
  * melgan_discriminator.py:89-156, and (STFT-as-conv) auraloss STFTLoss.stft. */
-int vbx_conv1d_fwd(const vbx_conv_desc* d, const float* x, const float* w, const vbx_epilogue* e,
+VBX_API int vbx_conv1d_fwd(const vbx_conv_desc* d, const float* x, const float* w, const vbx_epilogue* e,
                    float* y, void* stream);
 /* dx = epi(conv_transpose(dy)).  wt is the group-transposed weight Wt[g][ci][co_g][k]
  * (vbx_weight_norm_fwd / vbx_transpose_weight produce it).  Replaces aten::convolution_backward
  * (input gradient) AND the forward of nn.ConvTranspose1d (eben_generator.py:241-249). */
-int vbx_conv1d_dgrad(const vbx_conv_desc* d, const float* dy, const float* wt, const vbx_epilogue* e,
+VBX_API int vbx_conv1d_dgrad(const vbx_conv_desc* d, const float* dy, const float* wt, const vbx_epilogue* e,
                      float* dx, void* stream);
 /* dw[co][ci][k] += sum_{b,t} dy*x  (accumulates: the caller zeroes its flat gradient bucket once).
  * Replaces aten::convolution_backward (weight gradient). */
-int vbx_conv1d_wgrad(const vbx_conv_desc* d, const float* x, const float* dy, float* dw, void* stream);
+VBX_API int vbx_conv1d_wgrad(const vbx_conv_desc* d, const float* x, const float* dy, float* dw, void* stream);
 /* col2im form of dgrad: dx += scatter(Wk^T dy), wk = Wk[g][(ci,k)][co_g]; dx must be pre-zeroed
  * (or hold the value to accumulate onto).  Used for the STFT-as-conv backward. */
-int vbx_conv1d_dgrad_scatter(const vbx_conv_desc* d, const float* dy, const float* wk, float* dx,
+VBX_API int vbx_conv1d_dgrad_scatter(const vbx_conv_desc* d, const float* dy, const float* wk, float* dx,
                              void* stream);
 /* W[co][ci_g][k] -> Wt[g][ci_g][co_g][k]  (layout for vbx_conv1d_dgrad) */
-int vbx_transpose_weight(const float* w, float* wt, int32_t Cout, int32_t Cin_g, int32_t K,
+VBX_API int vbx_transpose_weight(const float* w, float* wt, int32_t Cout, int32_t Cin_g, int32_t K,
                          int32_t groups, void* stream);
 
 /* ---- weight norm (torch_modules/utils.py:4-9; aten::_weight_norm_interface, dim=0) -----
  * w[r,:] = g[r] * v[r,:] / ||v[r,:]||  for R rows of length `row` (= C1*K).
  * inv_norm[r] = 1/||v[r,:]|| is saved for the backward.  When wt != NULL the group-transposed
  * copy is written as well (Cout=R, Cin_g, K, groups describe the conv the weight belongs to). */
-int vbx_weight_norm_fwd(const float* g, const float* v, float* w, float* wt, float* inv_norm,
+VBX_API int vbx_weight_norm_fwd(const float* g, const float* v, float* w, float* wt, float* inv_norm,
                         int32_t R, int32_t Cin_g, int32_t K, int32_t groups, void* stream);
 /* dg[r] (+)= <dw,v>/||v|| ;  dv (+)= g/||v|| * dw - g*<dw,v>/||v||^3 * v   (accumulate when beta=1) */
-int vbx_weight_norm_bwd(const float* g, const float* v, const float* inv_norm, const float* dw,
+VBX_API int vbx_weight_norm_bwd(const float* g, const float* v, const float* inv_norm, const float* dw,
                         float* dg, float* dv, int32_t R, int32_t row, float beta, void* stream);
 
 /* ---- PQMF (dsp/pqmf.py:194-213), one polyphase kernel each way ---------------------------
@@ -89,83 +94,92 @@ int vbx_weight_norm_bwd(const float* g, const float* v, const float* inv_norm, c
  * synthesis: per band z[b,c,u] = sum_{k: (u+n-1-k) % m == 0} w[c,k] * x[b,c,(u+n-1-k)/m];
  *   sum_bands=1 writes y[b,0,u] = sum_c z (the generator's `.sum(1)`, eben_generator.py:209-211),
  *   sum_bands=0 writes the (B,m,L) tensor F.conv_transpose1d returns (pqmf.py:204-213).
- * T = band-rate length, L = full-rate length; requires L + n == m*T + ... as in the reference
- * (T == (L + n - 2)/m + 1 and L == m*T - n + ... are checked). */
-int vbx_pqmf_analysis(const float* x, const float* w, float* y, int32_t B, int32_t L, int32_t T,
-                      int32_t m, int32_t n, int32_t bands, void* stream);
-int vbx_pqmf_synthesis(const float* x, const float* w, float* y, int32_t B, int32_t T, int32_t L,
-                       int32_t m, int32_t n, int32_t sum_bands, void* stream);
+ * T = band-rate length, L = full-rate length (the reference has T = (L+n-2)/m + 1 and
+ * L = m*T - n; any T, L are accepted and out-of-range taps read zero, which also makes each
+ * kernel the other's backward: x_per_band=1 lets analysis read a (B,bands,L) input, `bands`
+ * in synthesis is the number of input channels (<= m) that are filtered/summed). */
+VBX_API int vbx_pqmf_analysis(const float* x, const float* w, float* y, int32_t B, int32_t L, int32_t T,
+                      int32_t m, int32_t n, int32_t bands, int32_t x_per_band, void* stream);
+VBX_API int vbx_pqmf_synthesis(const float* x, const float* w, float* y, int32_t B, int32_t T, int32_t L,
+                       int32_t m, int32_t n, int32_t bands, int32_t sum_bands, void* stream);
 
 /* ---- element-wise -------------------------------------------------------------------- */
 /* y = x > 0 ? x : slope*x                       (nn.LeakyReLU, eben_generator.py:110,187-189) */
-int vbx_leaky_relu_fwd(const float* x, float* y, int64_t n, float slope, void* stream);
+VBX_API int vbx_leaky_relu_fwd(const float* x, float* y, int64_t n, float slope, void* stream);
 /* dx = dy * (ref > 0 ? 1 : slope) (+ beta*dx); ref = input or output of the activation.
  * If dbias != NULL also dbias[c] += sum_{b,t} dx[b,c,t]  (C, T give the layout; bias gradient
  * of the discriminator convs).  mask != NULL replaces the sign test on ref. */
-int vbx_leaky_relu_bwd(const float* dy, const float* ref, const uint8_t* mask, float* dx, float* dbias,
+VBX_API int vbx_leaky_relu_bwd(const float* dy, const float* ref, const uint8_t* mask, float* dx, float* dbias,
                        int32_t B, int32_t C, int32_t T, float slope, float beta, void* stream);
 /* y[b,c,t] = tanh(x[b,c,t] + (c < p ? first[b,c,t] : 0))      (eben_generator.py:203-208) */
-int vbx_tanh_recompose_fwd(const float* x, const float* first, float* y, int32_t B, int32_t m,
+VBX_API int vbx_tanh_recompose_fwd(const float* x, const float* first, float* y, int32_t B, int32_t m,
                            int32_t p, int32_t T, void* stream);
 /* dx = dy * (1 - y^2) */
-int vbx_tanh_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream);
+VBX_API int vbx_tanh_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream);
 /* y = a + b */
-int vbx_add(const float* a, const float* b, float* y, int64_t n, void* stream);
+VBX_API int vbx_add(const float* a, const float* b, float* y, int64_t n, void* stream);
 /* y = alpha * x (+ beta*y) */
-int vbx_axpby(const float* x, float* y, int64_t n, float alpha, float beta, void* stream);
+VBX_API int vbx_axpby(const float* x, float* y, int64_t n, float alpha, float beta, void* stream);
 
 /* ---- losses -------------------------------------------------------------------------- */
 /* Feature matching (losses/feature_loss.py:37-50).  For one embedding pair accumulate
  * sums[0] += sum|a-b|, sums[1] += sum|a| (double). */
-int vbx_l1_pair_sums(const float* a, const float* b, int64_t n, double* sums, void* stream);
+VBX_API int vbx_l1_pair_sums(const float* a, const float* b, int64_t n, double* sums, void* stream);
 /* loss = scale * sum_i sums[2i]/sums[2i+1] over npairs   (scale = 1/(scales*layers)) */
-int vbx_fm_finalize(const double* sums, int32_t npairs, float scale, float* loss, void* stream);
+VBX_API int vbx_fm_finalize(const double* sums, int32_t npairs, float scale, float* loss, void* stream);
 /* da = go*scale*( sign(a-b)/S_a - S_ab/S_a^2 * sign(a) ), db = -go*scale*sign(a-b)/S_a
  * (either may be NULL); go is a device scalar. */
-int vbx_l1_pair_bwd(const float* a, const float* b, int64_t n, const double* sums, const float* go,
+VBX_API int vbx_l1_pair_bwd(const float* a, const float* b, int64_t n, const double* sums, const float* go,
                     float scale, float* da, float* db, void* stream);
 /* Hinge (losses/hinge_loss.py:35-43): acc[0] += scale * sum relu(1 - target*c) ; acc is a double. */
-int vbx_hinge_fwd(const float* c, int64_t n, float target, float scale, double* acc, void* stream);
+VBX_API int vbx_hinge_fwd(const float* c, int64_t n, float target, float scale, double* acc, void* stream);
 /* dc = go * scale * (1 - target*c > 0 ? -target : 0) */
-int vbx_hinge_bwd(const float* c, int64_t n, float target, float scale, const float* go, float* dc,
+VBX_API int vbx_hinge_bwd(const float* c, int64_t n, float target, float scale, const float* go, float* dc,
                   void* stream);
 /* double -> float scalar copy(s) with optional scaling */
-int vbx_d2f(const double* src, float* dst, int32_t n, float scale, void* stream);
+VBX_API int vbx_d2f(const double* src, float* dst, int32_t n, float scale, void* stream);
 /* STFT loss statistics (auraloss.freq.STFTLoss as configured by multi_stft.yaml:1-18).
  * X, Y: (B, 2*bins, F) outputs of the STFT-as-conv (rows [0,bins) real, [bins,2bins) imaginary).
  * stats[0] += sum (ym-xm)^2, stats[1] += sum ym^2, stats[2] += sum |log xm - log ym| (double),
  * with xm = sqrt(max(re^2+im^2, eps)). */
-int vbx_stft_stats(const float* X, const float* Y, int32_t B, int32_t bins, int32_t F, float eps,
+VBX_API int vbx_stft_stats(const float* X, const float* Y, int32_t B, int32_t bins, int32_t F, float eps,
                    double* stats, void* stream);
 /* loss += w * ( sqrt(s0)/sqrt(s1) + s2/count ) for each of nres statistic triples */
-int vbx_stft_finalize(const double* stats, const double* counts, int32_t nres, float w, float* loss,
+VBX_API int vbx_stft_finalize(const double* stats, const double* counts, int32_t nres, float w, float* loss,
                       void* stream);
 /* dX = d loss / d X for one resolution (go: device scalar, w: 1/nres) */
-int vbx_stft_bwd(const float* X, const float* Y, int32_t B, int32_t bins, int32_t F, float eps,
+VBX_API int vbx_stft_bwd(const float* X, const float* Y, int32_t B, int32_t bins, int32_t F, float eps,
                  const double* stats, double count, const float* go, float w, float* dX, void* stream);
+
+/* total[0] = sum_i lam[i]*x_i[0], terms[i] = lam[i]*x_i[0] for up to 4 device scalars x_i
+ * (lam == NULL -> 1).  The `sum(atomic_losses.values())` of lightning_modules/eben.py:106,239. */
+VBX_API int vbx_weighted_sum(const float* x0, const float* x1, const float* x2, const float* x3, int32_t n,
+                     const float* lam, float* terms, float* total, void* stream);
+/* out[i] = go[0] * (lam ? lam[i] : 1) */
+VBX_API int vbx_scalar_mul(const float* go, const float* lam, float* out, int32_t n, void* stream);
 
 /* ---- reductions / optimiser ------------------------------------------------------------ */
 /* out[0] = sqrt(sum x^2) (float); scratch is a double the kernel zeroes itself is NOT assumed:
  * pass a zeroed double. */
-int vbx_sumsq(const float* x, int64_t n, double* acc, void* stream);
+VBX_API int vbx_sumsq(const float* x, int64_t n, double* acc, void* stream);
 /* dynamically_balance_losses (lightning_modules/eben.py:222-240) on device scalars:
  * norm_i = sqrt(sumsq[i]); ema: old = first ? norm : old; old = beta*old + (1-beta)*norm;
  * lambda_i = clamp(1/(old_i + 1e-4), 0, 1e4).  mode 0 = "simple", 1 = "ema". */
-int vbx_balance(const double* sumsq, float* norms_old, int32_t* initialised, float* lambdas,
+VBX_API int vbx_balance(const double* sumsq, float* norms_old, int32_t* initialised, float* lambdas,
                 float* norms_out, int32_t n, float beta_ema, int32_t mode, void* stream);
 /* torch.optim.Adam (optimizer/adam.yaml:1-9), single flat bucket:
  * g = grad_scale*grad; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
  * p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps);  t = ++step[0] (device int, bumped by
  * the kernel's first block AFTER all reads: launch vbx_adam_tick first). */
-int vbx_adam_tick(int32_t* step, void* stream);
-int vbx_adam_step(float* p, const float* grad, float* m, float* v, int64_t n, const int32_t* step,
+VBX_API int vbx_adam_tick(int32_t* step, void* stream);
+VBX_API int vbx_adam_step(float* p, const float* grad, float* m, float* v, int64_t n, const int32_t* step,
                   float lr, float b1, float b2, float eps, float grad_scale, void* stream);
-int vbx_fill(float* p, int64_t n, float value, void* stream);
+VBX_API int vbx_fill(float* p, int64_t n, float value, void* stream);
 
 /* ---- noisy-BWE collate arithmetic (vibravox/utils.py:195-254, 50-81) ------------------- */
 /* out_body[b,:] = speech_body[b, off[b] : off[b]+len] + noise[b, start[b] + off[b] : ...];
  * out_air[b,:] = speech_air[b, off[b] : off[b]+len].  start/off are device int arrays. */
-int vbx_noise_mix_crop(const float* body, const float* air, const float* noise, const int32_t* start,
+VBX_API int vbx_noise_mix_crop(const float* body, const float* air, const float* noise, const int32_t* start,
                        const int32_t* off, float* out_body, float* out_air, int32_t B, int32_t Ls,
                        int32_t Ln, int32_t len, void* stream);
 

@@ -1,0 +1,259 @@
+"""-m gpu: every kernel family of libvbx_b200.so, called through the C ABI (vibravox_b200.ops),
+against plain PyTorch fp64 references of the same op on the host."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from emu_util import ref_padded, scatter_weight, tout, transpose_weight
+from test_emu_conv import CASES
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def cuda(*ts):
+    return [t.to(DEV) for t in ts]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(c) for c in CASES])
+def test_conv_family_matches_torch(case):
+    from vibravox_b200 import ops
+    B, Cin, Cout, Tin, K, s, d, pad, refl, groups = case
+    geom = ops.ConvGeom(Cin, Cout, K, s, d, pad, refl, groups)
+    torch.manual_seed(sum(case))
+    To = tout(Tin, K, s, d, pad)
+    x = torch.randn(B, Cin, Tin)
+    w = torch.randn(Cout, Cin // groups, K) / (Cin // groups * K) ** 0.5
+    bias, res = torch.randn(Cout), torch.randn(B, Cout, To)
+    x64, w64 = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    pre = F.conv1d(ref_padded(x64, pad, refl), w64, bias.double(), s, 0, d, groups)
+    want = F.leaky_relu(pre, 0.2) + res.double()
+    xc, wc, bc, rc = cuda(x, w, bias, res)
+    y, mask = ops.conv1d_fwd(xc, wc, geom, bias=bc, res=rc, slope=0.2, want_mask=True)
+    assert (y.cpu().double() - want).abs().max() < 2e-5
+    assert (mask.cpu().bool() != (pre > 0)).sum() <= 2
+    dy = torch.randn(B, Cout, To)
+    plain = F.conv1d(ref_padded(x64, pad, refl), w64, None, s, 0, d, groups)
+    gx, gw = torch.autograd.grad(plain, (x64, w64), dy.double())
+    dyc = dy.to(DEV)
+    wt = ops.transpose_weight(wc, groups)
+    assert torch.equal(wt.cpu().view(-1), transpose_weight(w, groups).view(-1))
+    r2 = torch.randn(B, Cin, Tin)
+    dx = ops.conv1d_dgrad(dyc, wt, geom, Tin, res=r2.to(DEV))
+    assert (dx.cpu().double() - (gx + r2.double())).abs().max() < 2e-5
+    dw = ops.conv1d_wgrad(xc, dyc, geom)
+    assert (dw.cpu().double() - gw).abs().max() / gw.abs().max() < 5e-6
+    dx2 = ops.conv1d_dgrad_scatter(dyc, scatter_weight(w, groups).to(DEV), geom, Tin)
+    assert (dx2.cpu().double() - gx).abs().max() < 2e-5
+
+
+def test_weight_norm_fwd_bwd():
+    from vibravox_b200 import ops
+    torch.manual_seed(1)
+    for shape, groups in (((64, 32, 4), 1), ((48, 6, 7), 4), ((256, 128, 16), 1), ((1, 768, 3), 1)):
+        v = torch.randn(shape)
+        g = torch.rand(shape[0], 1, 1) + 0.5
+        v64, g64 = v.double().requires_grad_(True), g.double().requires_grad_(True)
+        w64 = torch._weight_norm(v64, g64, 0)
+        dw = torch.randn(shape)
+        dv64, dg64 = torch.autograd.grad(w64, (v64, g64), dw.double())
+        gc, vc, dwc = cuda(g, v, dw)
+        w, wt, inv = ops.weight_norm_fwd(gc, vc, groups)
+        assert (w.cpu().double() - w64).abs().max() < 1e-6
+        assert torch.equal(wt.cpu().view(-1), transpose_weight(w.cpu(), groups).view(-1))
+        dg, dv = ops.weight_norm_bwd(gc, vc, inv, dwc)
+        assert (dg.cpu().double() - dg64).abs().max() < 2e-5 * max(1.0, float(dg64.abs().max()))
+        assert (dv.cpu().double() - dv64).abs().max() < 1e-5
+        dg2, dv2 = ops.weight_norm_bwd(gc, vc, inv, dwc, dg=dg.clone(), dv=dv.clone(), beta=1.0)
+        assert torch.allclose(dv2, 2 * dv, atol=1e-6) and torch.allclose(dg2, 2 * dg, atol=1e-5)
+
+
+def test_pqmf_elementwise_and_reconstruction():
+    """north_star: 'PQMF reconstruction ... checked element-wise'."""
+    from oracle import eben_oracle as O
+    from vibravox_b200 import ops
+    wa, ws, _ = O.pqmf_design(4, 32)
+    wac, wsc = cuda(wa, ws)
+    torch.manual_seed(2)
+    for B, L in ((1, 15840), (3, 47840), (2, 4000)):
+        x = torch.randn(B, 1, L)
+        for bands in (2, 4):
+            want = O.pqmf_analysis(x, wa, bands)
+            got = ops.pqmf_analysis(x.to(DEV), wac, bands)
+            assert got.shape == want.shape and (got.cpu() - want).abs().max() < 2e-6
+        dec = O.pqmf_analysis(x, wa)
+        want_full = O.pqmf_synthesis(dec, ws)
+        got_full = ops.pqmf_synthesis(dec.to(DEV), wsc, sum_bands=False)
+        assert got_full.shape == want_full.shape and (got_full.cpu() - want_full).abs().max() < 5e-6
+        got_sum = ops.pqmf_synthesis(dec.to(DEV), wsc, sum_bands=True)
+        assert (got_sum.cpu() - want_full.sum(1, keepdim=True)).abs().max() < 1e-5
+        rec = ops.pqmf_synthesis(ops.pqmf_analysis(x.to(DEV), wac, 4), wsc, sum_bands=True).cpu()
+        ref = want_full.sum(1, keepdim=True)
+        snr_ref = 10 * torch.log10((ref ** 2).mean() / ((x - ref) ** 2).mean())
+        snr = 10 * torch.log10((rec ** 2).mean() / ((x - rec) ** 2).mean())
+        assert abs(float(snr - snr_ref)) < 0.01 and snr > 45
+    # other filter banks
+    for m, n in ((8, 64), (2, 16)):
+        wa2, ws2, _ = O.pqmf_design(m, n)
+        x = torch.randn(2, 1, 1000 * m - n)
+        want = O.pqmf_analysis(x, wa2)
+        got = ops.pqmf_analysis(x.to(DEV), wa2.to(DEV), m)
+        assert (got.cpu() - want).abs().max() < 5e-6
+        got_s = ops.pqmf_synthesis(want.to(DEV), ws2.to(DEV), sum_bands=False)
+        assert (got_s.cpu() - O.pqmf_synthesis(want, ws2)).abs().max() < 1e-5
+
+
+def test_pqmf_autograd():
+    from oracle import eben_oracle as O
+    from vibravox_b200.functional import PQMFAnalysisFn, PQMFSynthesisFn
+    wa, ws, _ = O.pqmf_design(4, 32)
+    x = torch.randn(2, 1, 4064, dtype=torch.float64, requires_grad=True)
+    ya = O.pqmf_analysis(x, wa.double(), 2)
+    ga = torch.randn_like(ya)
+    (gx,) = torch.autograd.grad(ya, x, ga)
+    xc = x.detach().float().to(DEV).requires_grad_(True)
+    yc = PQMFAnalysisFn.apply(xc, wa.to(DEV), 2)
+    (gxc,) = torch.autograd.grad(yc, xc, ga.float().to(DEV))
+    assert (gxc.cpu().double() - gx).abs().max() < 1e-5
+    b = torch.randn(2, 4, 1024, dtype=torch.float64, requires_grad=True)
+    for summed in (True, False):
+        ys = O.pqmf_synthesis(b, ws.double())
+        if summed:
+            ys = ys.sum(1, keepdim=True)
+        gs = torch.randn_like(ys)
+        (gb,) = torch.autograd.grad(ys, b, gs)
+        bc = b.detach().float().to(DEV).requires_grad_(True)
+        yc = PQMFSynthesisFn.apply(bc, ws.to(DEV), summed)
+        (gbc,) = torch.autograd.grad(yc, bc, gs.float().to(DEV))
+        assert (gbc.cpu().double() - gb).abs().max() < 2e-5
+
+
+def test_elementwise_and_losses():
+    from oracle import eben_oracle as O
+    from vibravox_b200 import ops
+    from vibravox_b200.functional import FeatureMatchingFn, HingeFn, LeakyReluFn, TanhRecomposeFn, WeightedSumFn
+    torch.manual_seed(3)
+    x = torch.randn(3, 5, 1001, dtype=torch.float64, requires_grad=True)
+    xc = x.detach().float().to(DEV).requires_grad_(True)
+    g = torch.randn(3, 5, 1001)
+    y, yc = F.leaky_relu(x, 0.01), LeakyReluFn.apply(xc, 0.01)
+    assert (yc.cpu().double() - y).abs().max() < 1e-6
+    (gx,), (gxc,) = torch.autograd.grad(y, x, g.double()), torch.autograd.grad(yc, xc, g.to(DEV))
+    assert (gxc.cpu().double() - gx).abs().max() < 1e-6
+    first = torch.randn(3, 2, 1001)
+    y = torch.tanh(x + torch.cat((first.double(), torch.zeros(3, 3, 1001, dtype=torch.float64)), 1))
+    yc = TanhRecomposeFn.apply(xc, first.to(DEV), 2)
+    assert (yc.cpu().double() - y).abs().max() < 1e-6
+    (gx,), (gxc,) = torch.autograd.grad(y, x, g.double()), torch.autograd.grad(yc, xc, g.to(DEV))
+    assert (gxc.cpu().double() - gx).abs().max() < 2e-6
+    # bias-gradient reduction
+    dy, ref = torch.randn(4, 7, 333), torch.randn(4, 7, 333)
+    db = torch.zeros(7, device=DEV)
+    dxc = ops.leaky_relu_bwd(dy.to(DEV), ref.to(DEV), 0.2, dbias=db)
+    want = dy.double() * torch.where(ref > 0, 1.0, 0.2).double()
+    assert (dxc.cpu().double() - want).abs().max() < 1e-6
+    assert (db.cpu().double() - want.sum((0, 2))).abs().max() < 1e-4
+    # feature matching + hinge against the oracle (fp64)
+    shapes = [[(2, 1, 500), (2, 24, 502), (2, 48, 251), (2, 1, 251)], [(2, 1, 2000), (2, 16, 2000), (2, 1, 500)]]
+    a = [[torch.randn(s, dtype=torch.float64, requires_grad=True) for s in sc] for sc in shapes]
+    b = [[torch.randn(s, dtype=torch.float64) for s in sc] for sc in shapes]
+    fm = O.feature_matching_loss(a, b)
+    ac = [[t.detach().float().to(DEV).requires_grad_(True) for t in sc] for sc in a]
+    bc = [[t.float().to(DEV) for t in sc] for sc in b]
+    from vibravox_b200.torch_modules.losses.feature_loss import FeatureLossForDiscriminatorMelganMultiScales
+    from vibravox_b200.torch_modules.losses.hinge_loss import HingeLossForDiscriminatorMelganMultiScales
+    fmc = FeatureLossForDiscriminatorMelganMultiScales()(ac, bc)
+    assert float(fmc) == pytest.approx(float(fm), rel=1e-5)
+    inner = [a[0][1], a[0][2], a[1][1]]
+    innerc = [ac[0][1], ac[0][2], ac[1][1]]
+    for gw, gc in zip(torch.autograd.grad(fm, inner), torch.autograd.grad(fmc, innerc)):
+        assert (gc.cpu().double() - gw).abs().max() < 1e-6 * max(1.0, float(gw.abs().max()) * 1e3)
+    for target in (1.0, -1.0):
+        h = O.hinge_loss(a, target)
+        hc = HingeLossForDiscriminatorMelganMultiScales()(embeddings=ac, target=target)
+        assert float(hc) == pytest.approx(float(h), rel=1e-5)
+        gw = torch.autograd.grad(h, [a[0][-1], a[1][-1]])
+        gc = torch.autograd.grad(hc, [ac[0][-1], ac[1][-1]])
+        for u, v in zip(gw, gc):
+            assert (v.cpu().double() - u).abs().max() < 1e-8 + 1e-5 * float(u.abs().max())
+    # weighted sum
+    l1 = torch.tensor(2.0, device=DEV, requires_grad=True)
+    l2 = torch.tensor(3.0, device=DEV, requires_grad=True)
+    lam = torch.tensor([0.5, 4.0], device=DEV)
+    tot = WeightedSumFn.apply(lam, l1, l2)
+    assert float(tot) == 13.0
+    g1, g2 = torch.autograd.grad(tot, (l1, l2))
+    assert float(g1) == 0.5 and float(g2) == 4.0
+
+
+def test_mrstft_loss_and_per_bin_magnitudes():
+    """north_star: 'per-bin STFT checked element-wise'."""
+    from oracle import eben_oracle as O
+    from vibravox_b200 import ops
+    from vibravox_b200.torch_modules.losses.mrstft_loss import MultiResolutionSTFTLoss
+    torch.manual_seed(4)
+    B, L = 2, 15840
+    x = (0.3 * torch.randn(B, 1, L)).double().requires_grad_(True)
+    y = (0.3 * torch.randn(B, 1, L)).double()
+    taps = O.a_weighting_fir()
+    want = O.mrstft_loss(x, y, taps.double())
+    (gx,) = torch.autograd.grad(want, x)
+    mod = MultiResolutionSTFTLoss(fft_sizes=(512, 1024, 2048), hop_sizes=(50, 120, 240),
+                                  win_lengths=(240, 600, 1200), sample_rate=16000, perceptual_weighting=True).to(DEV)
+    assert torch.allclose(mod.fir_taps.cpu().view(-1), taps, atol=0, rtol=0)
+    xc = x.detach().float().to(DEV).requires_grad_(True)
+    got = mod(xc, y.float().to(DEV))
+    assert float(got) == pytest.approx(float(want), rel=2e-5)
+    (gxc,) = torch.autograd.grad(got, xc)
+    err = (gxc.cpu().double() - gx).norm() / gx.norm()
+    assert err < 2e-4, float(err)
+    # per-bin magnitudes
+    spec = mod._get_spec(torch.device(DEV, torch.cuda.current_device()))
+    sig = x.detach().float().view(B, 1, L).to(DEV)
+    for (geom, basis, _), (n_fft, hop, win) in zip(spec.res, O.STFT_RESOLUTIONS):
+        X = ops.conv1d_fwd(sig, basis, geom).cpu()
+        bins = n_fft // 2 + 1
+        mag = torch.sqrt(torch.clamp(X[:, :bins] ** 2 + X[:, bins:] ** 2, min=1e-8))
+        ref = O.stft_magnitude(x.detach().view(B, L), n_fft, hop, win)
+        assert mag.shape == ref.shape
+        assert (mag.double() - ref).abs().max() < 1e-4 * float(ref.max())
+
+
+def test_adam_matches_torch():
+    from vibravox_b200.optim import FlatAdam
+    torch.manual_seed(5)
+    ps = [torch.randn(33, 7), torch.randn(5), torch.randn(4, 3, 2)]
+    ref = [p.clone().requires_grad_(True) for p in ps]
+    mine = [torch.nn.Parameter(p.clone().to(DEV)) for p in ps]
+    o_ref = torch.optim.Adam(ref, lr=3e-4, betas=(0.5, 0.9))
+    o_mine = FlatAdam(mine, lr=3e-4, betas=(0.5, 0.9))
+    o_mine.keep_autograd_grad([mine[1]])
+    o_mine.materialize()
+    for it in range(3):
+        grads = [torch.randn_like(p) for p in ps]
+        for p, g in zip(ref, grads):
+            p.grad = g.clone()
+        for p, g in zip(mine, grads):
+            if hasattr(p, "_vbx_grad"):
+                p._vbx_grad.copy_(g.to(DEV))
+            else:
+                p.grad = g.to(DEV)
+        o_ref.step(); o_mine.step(); o_ref.zero_grad(); o_mine.zero_grad()
+        assert float(o_mine.grad.abs().sum()) == 0.0
+    for p, q in zip(ref, mine):
+        assert (p.detach() - q.detach().cpu()).abs().max() < 1e-6
+
+
+def test_noise_mix_crop():
+    from vibravox_b200 import ops
+    torch.manual_seed(6)
+    B, Ls, Ln, length = 3, 5000, 20000, 4000
+    body, air, noise = torch.randn(B, 1, Ls), torch.randn(B, 1, Ls), torch.randn(B, 1, Ln)
+    start = torch.tensor([0, 15000, 777], dtype=torch.int32)
+    off = torch.tensor([0, 1000, 500], dtype=torch.int32)
+    ob, oa = ops.noise_mix_crop(*cuda(body, air, noise, start, off), length)
+    for b in range(B):
+        s, o = int(start[b]), int(off[b])
+        mixed = body[b, 0] + noise[b, 0, s:s + Ls]
+        assert torch.allclose(ob[b, 0].cpu(), mixed[o:o + length], atol=1e-6)
+        assert torch.equal(oa[b, 0].cpu(), air[b, 0, o:o + length])

@@ -1,0 +1,189 @@
+"""-m gpu: the drop-in modules and the training step against the CPU oracle and the committed
+golden fixtures (minted from the reference's own modules).  Tolerances: forward 1e-4 relative
+(north_star), measured margin ~1e-6; gradients are bracketed against the fp64 oracle because the
+reference's own fp32 gradients sit up to 2e-3 from fp64."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def relerr(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def build(seed=42, p=2, q=4):
+    from vibravox_b200.torch_modules.dnn.eben_discriminator import DiscriminatorEBENMultiScales
+    from vibravox_b200.torch_modules.dnn.eben_generator import EBENGenerator
+    torch.manual_seed(seed)
+    return EBENGenerator(m=4, n=32, p=p), DiscriminatorEBENMultiScales(q=q, min_channels=24)
+
+
+def test_config1_generator_forward_matches_golden(golden_dir):
+    """BASELINE.json configs[0]: EBENGenerator(m=4,p=2) forward on 1x1x16000, fp32 vs reference."""
+    gold = torch.load(os.path.join(golden_dir, "cfg1_forward.pt"))
+    G, D = build(gold["seed"])
+    x = torch.randn(1, 1, 16000)
+    assert torch.equal(x[0, 0, :8], gold["x_head"])
+    G, D = G.to(DEV), D.to(DEV)
+    with torch.no_grad():
+        xc = G.cut_to_valid_length(x.to(DEV))
+        y, bands = G(xc)
+        emb = D(bands=bands, audio=y)
+    assert y.shape == (1, 1, 15840) and bands.shape == (1, 4, 3968)
+    assert relerr(y, gold["enhanced"]) < 1e-4 and relerr(bands, gold["bands"]) < 1e-4
+    assert (y.cpu() - gold["enhanced"]).abs().max() < 1e-4 * gold["enhanced"].abs().max()
+    for s, shapes, cert, am in zip(emb, gold["emb_shapes"], gold["certainties"], gold["emb_absmean"]):
+        assert [tuple(t.shape) for t in s] == shapes
+        assert relerr(s[-1], cert) < 1e-4
+        for t, m in zip(s, am):
+            assert float(t.abs().mean()) == pytest.approx(m, rel=1e-4)
+
+
+@pytest.mark.parametrize("p,q,B,L", [(2, 4, 2, 8000), (1, 3, 2, 15679), (4, 4, 1, 4000)])
+def test_forward_and_gradients_match_oracle(p, q, B, L):
+    from oracle import eben_oracle as O
+    G, D = build(7, p, q)
+    gs = {k: v.detach().clone() for k, v in G.state_dict().items()}
+    ds = {k: v.detach().clone() for k, v in D.state_dict().items()}
+    body, air = O.synthetic_pairs(B, L, seed=11)
+    # fp64 oracle: forward + all parameter gradients of a scalar that touches every output
+    g64 = {k: v.double().requires_grad_(not k.startswith("pqmf.")) for k, v in gs.items()}
+    d64 = {k: v.double().requires_grad_(True) for k, v in ds.items()}
+    x64 = O.cut_to_valid_length(body.double(), 32, 4)
+    y64, b64 = O.generator_forward(g64, x64, p)
+    e64 = O.discriminator_forward(d64, b64, y64, q, 24)
+    r64 = O.discriminator_forward(d64, O.pqmf_analysis(O.cut_to_valid_length(air.double(), 32, 4),
+                                                       g64["pqmf.analysis_weights"]), O.cut_to_valid_length(air.double(), 32, 4), q, 24)
+    loss64 = O.feature_matching_loss(e64, r64) + O.hinge_loss(e64, 1) + O.hinge_loss(r64, -1)
+    names_g = [k for k in g64 if g64[k].requires_grad]
+    grads64 = torch.autograd.grad(loss64, [g64[k] for k in names_g] + list(d64.values()))
+    # fp32 oracle for the noise bracket
+    g32 = {k: v.clone().requires_grad_(not k.startswith("pqmf.")) for k, v in gs.items()}
+    d32 = {k: v.clone().requires_grad_(True) for k, v in ds.items()}
+    x32 = O.cut_to_valid_length(body, 32, 4)
+    a32 = O.cut_to_valid_length(air, 32, 4)
+    y32, b32 = O.generator_forward(g32, x32, p)
+    e32 = O.discriminator_forward(d32, b32, y32, q, 24)
+    r32 = O.discriminator_forward(d32, O.pqmf_analysis(a32, g32["pqmf.analysis_weights"]), a32, q, 24)
+    loss32 = O.feature_matching_loss(e32, r32) + O.hinge_loss(e32, 1) + O.hinge_loss(r32, -1)
+    grads32 = torch.autograd.grad(loss32, [g32[k] for k in names_g] + list(d32.values()))
+    # CUDA path
+    G, D = G.to(DEV), D.to(DEV)
+    from vibravox_b200.torch_modules.losses.feature_loss import FeatureLossForDiscriminatorMelganMultiScales
+    from vibravox_b200.torch_modules.losses.hinge_loss import HingeLossForDiscriminatorMelganMultiScales
+    xc = G.cut_to_valid_length(body.to(DEV))
+    ac = G.cut_to_valid_length(air.to(DEV))
+    y, bands = G(xc)
+    assert relerr(y, y64) < 1e-5 and relerr(bands, b64) < 1e-5
+    e = D(bands=bands, audio=y)
+    r = D(bands=G.pqmf(ac, "analysis"), audio=ac)
+    for sa, sb in zip(e, e64):
+        for ta, tb in zip(sa, sb):
+            assert ta.shape == tb.shape and relerr(ta, tb) < 1e-4
+    hinge = HingeLossForDiscriminatorMelganMultiScales()
+    loss = FeatureLossForDiscriminatorMelganMultiScales()(e, r) + hinge(e, 1) + hinge(r, -1)
+    assert float(loss) == pytest.approx(float(loss64), rel=2e-5)
+    gp = dict(G.named_parameters())
+    dp = dict(D.named_parameters())
+    params = [gp[k] for k in names_g] + [dp[k] for k in d64]
+    grads = torch.autograd.grad(loss, params)
+    worst = 0.0
+    for name, g, g_32, g_64 in zip(names_g + list(d64), grads, grads32, grads64):
+        noise = relerr(g_32, g_64)
+        err = relerr(g, g_64)
+        # bracket: no worse than 3x the reference's own fp32 noise (+ a floor for tiny tensors)
+        assert err < 3 * noise + 5e-5, (name, err, noise)
+        worst = max(worst, err)
+    print("worst gradient rel-L2 vs fp64:", worst)
+
+
+def test_training_step_matches_reference_golden(golden_dir):
+    """Two consecutive training steps vs the logs of the reference's own eben.py (golden)."""
+    import vibravox_b200
+    from oracle import eben_oracle as O
+    gold = torch.load(os.path.join(golden_dir, "train_step.pt"))
+    body, air = O.synthetic_pairs(gold["B"], gold["S"], seed=gold["data_seed"])
+    lm = vibravox_b200.build_model(seed=gold["model_seed"], device=DEV)
+    batch = {"audio_body_conducted": body.to(DEV), "audio_airborne": air.to(DEV)}
+    for it in range(2):
+        out = lm.training_step(batch)
+        want = gold["steps"][it]
+        for k, v in want["logs"].items():
+            got = float(lm.logged["train/" + k])
+            assert got == pytest.approx(v, rel=3e-4, abs=3e-5), (it, k, got, v)
+        for a, b in zip(lm.atomic_norms_old.cpu().tolist(), want["norms_old"]):
+            assert a == pytest.approx(b, rel=5e-4)
+        assert torch.allclose(out["enhanced"][0, 0, :64].cpu(), want["enhanced_head"], atol=2e-5 if it == 0 else 2e-3)
+    # post-Adam parameters: statistical agreement: sums drift by at most a few lr-sized flips
+    gsd = lm.generator.state_dict()
+    for k, v in gold["g_param_sums_after"].items():
+        n = gsd[k].numel()
+        assert abs(float(gsd[k].double().sum()) - v) <= 2 * 2 * 3e-4 * n ** 0.5 * 4 + 1e-3, k
+    dsd = lm.discriminator.state_dict()
+    for k, v in gold["d_param_absmean_after"].items():
+        assert float(dsd[k].double().abs().mean()) == pytest.approx(v, rel=2e-2, abs=1e-3), k
+
+
+def test_training_step_gradients_bracket_fp64(golden_dir):
+    """Full-step generator / discriminator gradient norms vs the fp64 oracle (grad_bracket.pt)."""
+    import vibravox_b200
+    from oracle import eben_oracle as O
+    from vibravox_b200.torch_modules.utils import share_weight_norm
+    gold = torch.load(os.path.join(golden_dir, "grad_bracket.pt"))
+    body, air = O.synthetic_pairs(gold["B"], gold["S"], seed=gold["data_seed"])
+    lm = vibravox_b200.build_model(seed=42, device=DEV)
+    lm.generator_optimizer.materialize(); lm.discriminator_optimizer.materialize()
+    G = lm.generator
+    x, y = G.cut_to_valid_length(body.to(DEV)), G.cut_to_valid_length(air.to(DEV))
+    lm.toggle_optimizer(lm.generator_optimizer)
+    with share_weight_norm():
+        enh, enh_b = G(x)
+        ref_b = G.pqmf.forward(y, "analysis")
+        losses = lm.compute_atomic_losses("generator", enh, y, enh_b, ref_b)
+        lam = lm.dynamically_balance_losses(losses)
+        for a, b in zip(lm.last_norms.cpu().tolist(), gold["norms64"]):
+            assert a == pytest.approx(b, rel=1e-3)
+        for a, b in zip(lam.cpu().tolist(), gold["lambdas64"]):
+            assert a == pytest.approx(b, rel=1e-3)
+        from vibravox_b200.functional import WeightedSumFn
+        WeightedSumFn.apply(lam, *losses.values()).backward()
+    opt = lm.generator_optimizer
+    opt.gather_autograd_grads()
+    names = [n for n, p in G.named_parameters() if p.requires_grad]
+    for (n, p), slot in zip([(n, p) for n, p in G.named_parameters() if p.requires_grad], opt._slices):
+        want = gold["g_grad_norm64"][n]
+        noise = gold["g_fp32_vs_fp64"][n]
+        assert float(slot.norm()) == pytest.approx(want, rel=3 * noise + 1e-3), n
+    assert len(names) == len(opt._slices)
+
+
+def test_full_size_properties():
+    """BASELINE.json configs[1] sizes (bs=32 x 3 s): size-independent properties instead of an oracle run."""
+    G, D = build(42)
+    G, D = G.to(DEV), D.to(DEV)
+    torch.manual_seed(0)
+    x = (0.1 * torch.randn(32, 1, 48000, device=DEV)).clamp(-1, 1)
+    xc = G.cut_to_valid_length(x)
+    with torch.no_grad():
+        y, bands = G(xc)
+        assert y.shape == (32, 1, 47840) and bands.shape == (32, 4, 11968)
+        assert torch.isfinite(y).all() and float(bands.abs().max()) <= 1.0
+        # batch independence: item 5 alone gives the same result as inside the batch
+        y5, b5 = G(xc[5:6].contiguous())
+        assert (y5 - y[5:6]).abs().max() < 1e-5
+        # PQMF near-perfect reconstruction at full size
+        rec = G.pqmf.synthesis_sum(G.pqmf(xc, "analysis"))
+        snr = 10 * torch.log10((rec ** 2).mean() / ((xc - rec) ** 2).mean())
+        assert float(snr) > 45
+        # discriminator: linear layers are linear => D(2a) first-layer pre-activation scaling holds via shapes
+        emb = D(bands=bands, audio=y)
+        assert [len(s) for s in emb] == [9, 9, 9, 8]
+        assert [tuple(s[-1].shape) for s in emb] == [(32, 1, 375), (32, 1, 365), (32, 1, 355), (32, 1, 187)]
+        e5 = D(bands=bands[5:6].contiguous(), audio=y[5:6].contiguous())
+        for sa, sb in zip(emb, e5):
+            assert (sa[-1][5:6] - sb[-1]).abs().max() < 1e-4

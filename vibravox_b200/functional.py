@@ -1,0 +1,368 @@
+"""autograd.Function wrappers: each forward/backward is one or a few libvbx_b200 kernels.
+
+These give the drop-in nn.Modules (torch_modules/) ordinary PyTorch autograd semantics
+(`loss.backward()`, `torch.autograd.grad(loss, generator.last_conv.weight)` as used by
+lightning_modules/eben.py:225-228 of the reference) while every FLOP runs in the
+hand-written sm_100a kernels.  First-order only (once_differentiable).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import ops
+from .ops import ConvGeom
+
+Tensor = torch.Tensor
+
+
+def _c(t: Tensor) -> Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def grad_slot(p: Tensor) -> Optional[Tensor]:
+    """View into a flat gradient bucket (set by vibravox_b200.optim.FlatAdam on its parameters).
+    When present, backward kernels accumulate the parameter gradient there directly and autograd
+    gets None for that input: no per-parameter grad tensors, no AccumulateGrad adds, one Adam
+    launch and one all-reduce per network."""
+    return getattr(p, "_vbx_grad", None)
+
+
+class WeightNormFn(Function):
+    """w = g * v / ||v||_(dims 1,2)  (torch_modules/utils.py:4-9, weight_norm dim=0).
+    Returns (w, wt): the conv layout and the group-transposed layout the dgrad kernel reads."""
+
+    @staticmethod
+    def forward(ctx, g: Tensor, v: Tensor, groups: int):
+        w, wt, inv = ops.weight_norm_fwd(_c(g), _c(v), groups, want_wt=True)
+        ctx.save_for_backward(g, v, inv)
+        ctx.slots = (grad_slot(g), grad_slot(v))
+        ctx.mark_non_differentiable(wt)
+        return w, wt
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dw, _dwt):
+        g, v, inv = ctx.saved_tensors
+        sg, sv = ctx.slots
+        if sg is not None and sv is not None:      # accumulate straight into the flat gradient bucket
+            ops.weight_norm_bwd(_c(g), _c(v), inv, _c(dw), dg=sg, dv=sv, beta=1.0)
+            return None, None, None
+        dg, dv = ops.weight_norm_bwd(_c(g), _c(v), inv, _c(dw))
+        return dg.view_as(g), dv, None
+
+
+class TransposeWeightFn(Function):
+    """wt for an un-normalised conv weight (first_conv / last_conv); no gradient through wt."""
+
+    @staticmethod
+    def forward(ctx, w: Tensor, groups: int):
+        wt = ops.transpose_weight(_c(w), groups)
+        ctx.mark_non_differentiable(wt)
+        return wt
+
+    @staticmethod
+    def backward(ctx, _):
+        return None, None
+
+
+class ConvFn(Function):
+    """y = LeakyReLU_slope(conv1d(x, w) + bias), halo (reflect and/or zero) folded into the kernel."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, w: Tensor, wt: Optional[Tensor], bias: Optional[Tensor], geom: ConvGeom,
+                slope: float):
+        x, w = _c(x), _c(w)
+        y = ops.conv1d_fwd(x, w, geom, bias=bias, slope=slope)
+        ctx.geom, ctx.slope, ctx.has_bias = geom, slope, bias is not None
+        ctx.w_slot = grad_slot(w)
+        ctx.b_slot = grad_slot(bias) if bias is not None else None
+        ctx.save_for_backward(x, w, wt, y if slope != 1.0 else None)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x, w, wt, y = ctx.saved_tensors
+        geom, slope = ctx.geom, ctx.slope
+        gy = _c(gy)
+        need_x, need_w, _, need_b = ctx.needs_input_grad[:4]
+        dbias = None
+        if ctx.has_bias and need_b:
+            dbias = ctx.b_slot if ctx.b_slot is not None else \
+                torch.zeros((geom.Cout,), device=gy.device, dtype=torch.float32)
+        gp = gy
+        if slope != 1.0 or dbias is not None:
+            out = ops.leaky_relu_bwd(gy, y, slope, dbias=dbias, want_dx=slope != 1.0)
+            gp = out if out is not None else gy
+        dx = dw = None
+        if need_x:
+            if wt is None:
+                wt = ops.transpose_weight(w, geom.groups)
+            dx = ops.conv1d_dgrad(gp, wt, geom, x.shape[2])
+        if need_w:
+            dw = ops.conv1d_wgrad(x, gp, geom, dw=ctx.w_slot)
+        return (dx, None if ctx.w_slot is not None else dw, None,
+                None if ctx.b_slot is not None else dbias, None, None)
+
+
+class ConvTransposeFn(Function):
+    """y = LeakyReLU_slope(conv_transpose1d(x + skip, w)) (DecBlock.forward head,
+    eben_generator.py:251-253).  `geom` is the geometry of the *equivalent forward conv*
+    (Cout = ConvT in_channels, Cin = ConvT out_channels)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, skip: Optional[Tensor], w: Tensor, wt: Tensor, geom: ConvGeom, slope: float,
+                output_padding: int):
+        xs = ops.add(_c(x), _c(skip)) if skip is not None else _c(x)
+        T = xs.shape[2]
+        L = (T - 1) * geom.stride - 2 * geom.pad + geom.dil * (geom.K - 1) + output_padding + 1
+        y = ops.conv1d_dgrad(xs, wt, geom, L, slope=slope)
+        ctx.geom, ctx.slope, ctx.has_skip = geom, slope, skip is not None
+        ctx.save_for_backward(xs, _c(w), y if slope != 1.0 else None)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        xs, w, y = ctx.saved_tensors
+        geom, slope = ctx.geom, ctx.slope
+        gp = _c(gy)
+        if slope != 1.0:
+            gp = ops.leaky_relu_bwd(gp, y, slope)
+        dxs = dw = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            dxs = ops.conv1d_fwd(gp, w, geom)
+        if ctx.needs_input_grad[2]:
+            dw = ops.conv1d_wgrad(gp, xs, geom)
+        return (dxs if ctx.needs_input_grad[0] else None,
+                dxs if (ctx.has_skip and ctx.needs_input_grad[1]) else None, dw, None, None, None, None)
+
+
+class ResidualUnitFn(Function):
+    """out = x + LeakyReLU(pointwise(dilated(x)))   (ResidualUnit.forward, eben_generator.py:314-316).
+    The pointwise kernel's epilogue does the activation and the residual add and emits the
+    1-byte activation mask the backward needs (the mask is not recoverable from `out`)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, w1: Tensor, wt1: Tensor, w2: Tensor, wt2: Tensor, g1: ConvGeom, g2: ConvGeom,
+                slope: float):
+        x = _c(x)
+        h = ops.conv1d_fwd(x, w1, g1)
+        out, mask = ops.conv1d_fwd(h, w2, g2, res=x, slope=slope, want_mask=True)
+        ctx.g1, ctx.g2, ctx.slope = g1, g2, slope
+        ctx.save_for_backward(x, h, mask, wt1, wt2)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, h, mask, wt1, wt2 = ctx.saved_tensors
+        g1, g2, slope = ctx.g1, ctx.g2, ctx.slope
+        g = _c(g)
+        T = x.shape[2]
+        dz = ops.leaky_relu_bwd(g, None, slope, mask=mask)
+        dw2 = ops.conv1d_wgrad(h, dz, g2) if ctx.needs_input_grad[3] else None
+        dh = ops.conv1d_dgrad(dz, wt2, g2, T)
+        dw1 = ops.conv1d_wgrad(x, dh, g1) if ctx.needs_input_grad[1] else None
+        dx = ops.conv1d_dgrad(dh, wt1, g1, T, res=g) if ctx.needs_input_grad[0] else None
+        return dx, dw1, None, dw2, None, None, None, None
+
+
+class LeakyReluFn(Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, slope: float):
+        x = _c(x)
+        ctx.slope = slope
+        ctx.save_for_backward(x)
+        return ops.leaky_relu_fwd(x, slope)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        gy = _c(gy)
+        return ops.leaky_relu_bwd(gy.view(x.shape), x, ctx.slope), None
+
+
+class TanhRecomposeFn(Function):
+    """tanh(x + cat(first_bands, zeros))   (eben_generator.py:203-208)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, first: Tensor, p: int):
+        y = ops.tanh_recompose_fwd(_c(x), _c(first), p)
+        ctx.p = p
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        dx = ops.tanh_bwd(_c(gy), y)
+        dfirst = dx[:, :ctx.p].contiguous() if ctx.needs_input_grad[1] else None
+        return dx, dfirst, None
+
+
+class PQMFAnalysisFn(Function):
+    """F.conv1d(signal, W_a[:bands], stride=m, padding=n-1)   (pqmf.py:194-202)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, w: Tensor, bands: int):
+        x = _c(x)
+        ctx.save_for_backward(w)
+        ctx.L, ctx.bands = x.shape[2], bands
+        return ops.pqmf_analysis(x, w, bands)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        (w,) = ctx.saved_tensors
+        dx = ops.pqmf_synthesis(_c(gy), w, sum_bands=True, L=ctx.L) if ctx.needs_input_grad[0] else None
+        return dx, None, None
+
+
+class PQMFSynthesisFn(Function):
+    """F.conv_transpose1d(bands, W_s, stride=m, groups=m, padding=n-1, output_padding=m-2), optionally
+    fused with the generator's sum over bands   (pqmf.py:204-213, eben_generator.py:209-211)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, w: Tensor, sum_bands: bool):
+        x = _c(x)
+        ctx.save_for_backward(w)
+        ctx.T, ctx.sum_bands, ctx.bands = x.shape[2], sum_bands, x.shape[1]
+        return ops.pqmf_synthesis(x, w, sum_bands)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        (w,) = ctx.saved_tensors
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.pqmf_analysis(_c(gy), w, ctx.bands, T=ctx.T, x_per_band=not ctx.sum_bands)
+        return dx, None, None
+
+
+class FeatureMatchingFn(Function):
+    """sum_i mean|a_i - b_i| / mean|a_i|, times `scale`   (losses/feature_loss.py:37-50)."""
+
+    @staticmethod
+    def forward(ctx, scale: float, n: int, *tensors: Tensor):
+        a, b = [_c(t) for t in tensors[:n]], [_c(t) for t in tensors[n:]]
+        sums = torch.zeros((2 * n,), device=a[0].device, dtype=torch.float64)
+        for i in range(n):
+            ops.l1_pair_sums(a[i], b[i], sums[2 * i:2 * i + 2])
+        loss = ops.fm_finalize(sums, n, scale)
+        ctx.scale, ctx.n, ctx.sums = scale, n, sums
+        ctx.save_for_backward(*a, *b)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, go):
+        n, sums = ctx.n, ctx.sums
+        a, b = ctx.saved_tensors[:n], ctx.saved_tensors[n:]
+        go = _c(go).float()
+        grads: List[Optional[Tensor]] = [None] * (2 * n)
+        for i in range(n):
+            na, nb = ctx.needs_input_grad[2 + i], ctx.needs_input_grad[2 + n + i]
+            if na or nb:
+                grads[i], grads[n + i] = ops.l1_pair_bwd(a[i], b[i], sums[2 * i:2 * i + 2], go, ctx.scale, na, nb)
+        return (None, None, *grads)
+
+
+class HingeFn(Function):
+    """mean over scales of mean(relu(1 - target*certainty))   (losses/hinge_loss.py:35-43)."""
+
+    @staticmethod
+    def forward(ctx, target: float, *certs: Tensor):
+        certs = [_c(c) for c in certs]
+        acc = torch.zeros((1,), device=certs[0].device, dtype=torch.float64)
+        for c in certs:
+            ops.hinge_fwd(c, target, 1.0 / (c.numel() * len(certs)), acc)
+        ctx.target = target
+        ctx.save_for_backward(*certs)
+        return ops.d2f(acc).view(())
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, go):
+        certs = ctx.saved_tensors
+        go = _c(go).float()
+        grads = [ops.hinge_bwd(c, ctx.target, 1.0 / (c.numel() * len(certs)), go) if need else None
+                 for c, need in zip(certs, ctx.needs_input_grad[1:])]
+        return (None, *grads)
+
+
+class MRSTFTFn(Function):
+    """auraloss.freq.MultiResolutionSTFTLoss as configured by multi_stft.yaml:1-18:
+    A-weighting FIR, then per resolution an STFT computed as a strided conv against a windowed
+    DFT basis, magnitude / spectral-convergence / log-magnitude statistics."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, y: Tensor, spec):
+        B, C, L = x.shape
+        x2, y2 = _c(x).view(B * C, 1, L), _c(y).view(B * C, 1, L)
+        if spec.taps is not None:
+            xf = ops.conv1d_fwd(x2, spec.taps, spec.fir_geom)
+            yf = ops.conv1d_fwd(y2, spec.taps, spec.fir_geom)
+        else:
+            xf, yf = x2, y2
+        nres = len(spec.res)
+        stats = torch.zeros((3 * nres,), device=x.device, dtype=torch.float64)
+        counts = []
+        saved = []
+        for r, (geom, basis, _) in enumerate(spec.res):
+            X = ops.conv1d_fwd(xf, basis, geom)
+            Y = ops.conv1d_fwd(yf, basis, geom)
+            ops.stft_stats(X, Y, spec.eps, stats[3 * r:3 * r + 3])
+            counts.append(float(X.numel() // 2))
+            saved += [X, Y]
+        key = (B * C, L)
+        counts_t = spec.counts_cache.get(key)
+        if counts_t is None:
+            counts_t = torch.tensor(counts, dtype=torch.float64).to(x.device)
+            spec.counts_cache[key] = counts_t
+        loss = ops.stft_finalize(stats, counts_t, nres, 1.0 / nres)
+        ctx.spec, ctx.stats, ctx.counts, ctx.shape = spec, stats, counts, (B, C, L)
+        ctx.save_for_backward(*saved)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, go):
+        spec, stats, counts = ctx.spec, ctx.stats, ctx.counts
+        B, C, L = ctx.shape
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("MRSTFT: gradient w.r.t. the target is not implemented")
+        if not ctx.needs_input_grad[0]:
+            return None, None, None
+        go = _c(go).float()
+        nres = len(spec.res)
+        dxf = torch.zeros((B * C, 1, L), device=go.device, dtype=torch.float32)
+        for r, (geom, _, basis_k) in enumerate(spec.res):
+            X, Y = ctx.saved_tensors[2 * r], ctx.saved_tensors[2 * r + 1]
+            dX = ops.stft_bwd(X, Y, spec.eps, stats[3 * r:3 * r + 3], counts[r], go, 1.0 / nres)
+            ops.conv1d_dgrad_scatter(dX, basis_k, geom, L, dxf)
+        dx = ops.conv1d_dgrad(dxf, spec.taps, spec.fir_geom, L) if spec.taps is not None else dxf
+        return dx.view(B, C, L), None, None
+
+
+class WeightedSumFn(Function):
+    """total = sum_i lam_i * loss_i on device scalars (eben.py:106 `sum(atomic_losses.values())`
+    after the in-place scaling of eben.py:237-239; lam is detached there as well)."""
+
+    @staticmethod
+    def forward(ctx, lam: Optional[Tensor], *losses: Tensor):
+        total, _ = ops.weighted_sum([_c(l).view(1) for l in losses], lam)
+        ctx.lam, ctx.n = lam, len(losses)
+        return total
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, go):
+        g = ops.scalar_mul(_c(go).float().view(1), ctx.lam, ctx.n)
+        return (None, *[g[i].view(()) for i in range(ctx.n)])

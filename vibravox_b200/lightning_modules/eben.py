@@ -1,0 +1,216 @@
+"""EBENLightningModule without Lightning (reference: vibravox/lightning_modules/eben.py:9-240).
+
+Same constructor arguments and the same `training_step(batch)` schedule - generator phase
+(G forward, MR-STFT / feature-matching / hinge losses, gradient-norm loss balancing on
+`generator.last_conv.weight`, backward, optimizer step) then discriminator phase on the
+detached pre-update generator outputs - with Lightning's services restated per SURVEY App. B:
+toggle_optimizer = requires_grad flips, manual_backward = .backward() (+ one all-reduce of
+the flat gradient bucket per network when torch.distributed is initialised), self.log =
+device scalars kept in `self.logged` (no host sync inside the step).
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, Optional
+
+import torch
+
+from .. import ops
+from ..functional import WeightedSumFn
+from ..optim import FlatAdam
+from ..parallel import allreduce_sum_
+from ..torch_modules.utils import share_weight_norm
+
+
+class EBENLightningModule(torch.nn.Module):
+    def __init__(self, sample_rate: int, generator: torch.nn.Module, discriminator: torch.nn.Module,
+                 generator_optimizer, discriminator_optimizer,
+                 reconstructive_loss_freq_fn: Optional[torch.nn.Module] = None,
+                 reconstructive_loss_time_fn: Optional[torch.nn.Module] = None,
+                 feature_matching_loss_fn: Optional[torch.nn.Module] = None,
+                 adversarial_loss_fn: Optional[torch.nn.Module] = None,
+                 dynamic_loss_balancing: Optional[str] = None, beta_ema: float = 0.9,
+                 update_discriminator_ratio: float = 1.0, description: Optional[str] = None,
+                 push_to_hub_after_testing: bool = False):
+        super().__init__()
+        self.sample_rate, self.description = sample_rate, description
+        self.generator, self.discriminator = generator, discriminator
+        self.generator_optimizer = generator_optimizer(params=self.generator.parameters())
+        self.discriminator_optimizer = discriminator_optimizer(params=self.discriminator.parameters())
+        if isinstance(self.generator_optimizer, FlatAdam):
+            self.generator_optimizer.keep_autograd_grad([self.generator.last_conv.weight])
+        self.reconstructive_loss_temp_fn = reconstructive_loss_time_fn
+        self.reconstructive_loss_freq_fn = reconstructive_loss_freq_fn
+        self.feature_matching_loss_fn = feature_matching_loss_fn
+        self.adversarial_loss_fn = adversarial_loss_fn
+        assert dynamic_loss_balancing in {None, "simple", "ema"}, \
+            "dynamic_loss_balancing must be in {None, 'simple', 'ema'}"
+        self.dynamic_loss_balancing = dynamic_loss_balancing
+        self.beta_ema = beta_ema
+        assert 0 <= update_discriminator_ratio <= 1, "update_discriminator_ratio must be in [0, 1]"
+        self.update_discriminator_ratio = update_discriminator_ratio
+        self.push_to_hub_after_testing = push_to_hub_after_testing
+        self.automatic_optimization = False
+        # balancing state (eben.py:73,230-235) lives on the device: EMA of the gradient norms
+        self._bal = None
+        self.logged: Dict[str, torch.Tensor] = {}
+
+    # ---- Lightning services, restated --------------------------------------------------------
+    def optimizers(self, use_pl_optimizer: bool = True):
+        return self.generator_optimizer, self.discriminator_optimizer
+
+    def configure_optimizers(self):
+        return [self.generator_optimizer, self.discriminator_optimizer]
+
+    def log(self, name: str, value: torch.Tensor, **_) -> None:
+        self.logged[name] = value.detach() if isinstance(value, torch.Tensor) else value
+
+    def toggle_optimizer(self, optimizer) -> None:
+        mine = {id(p) for g in optimizer.param_groups for p in g["params"]}
+        self._toggled = []
+        for opt in self.configure_optimizers():
+            for g in opt.param_groups:
+                for p in g["params"]:
+                    if id(p) not in mine and p.requires_grad:
+                        p.requires_grad = False
+                        self._toggled.append(p)
+
+    def untoggle_optimizer(self, optimizer) -> None:
+        for p in self._toggled:
+            p.requires_grad = True
+        self._toggled = []
+
+    def manual_backward(self, loss: torch.Tensor, optimizer) -> None:
+        loss.backward()
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            world = torch.distributed.get_world_size()
+            if world > 1:
+                if isinstance(optimizer, FlatAdam):          # one bucket, one all-reduce
+                    optimizer.gather_autograd_grads()
+                    optimizer.grad_scale = allreduce_sum_(optimizer.grad)
+                else:
+                    for g in optimizer.param_groups:
+                        for p in g["params"]:
+                            if p.grad is not None:
+                                torch.distributed.all_reduce(p.grad)
+                                p.grad.div_(world)
+
+    @property
+    def atomic_norms_old(self):
+        return None if self._bal is None else self._bal["old"]
+
+    # ---- the hot path ------------------------------------------------------------------------
+    def training_step(self, batch: Dict[str, torch.Tensor]):
+        corrupted_speech = self.generator.cut_to_valid_length(batch["audio_body_conducted"])
+        reference_speech = self.generator.cut_to_valid_length(batch["audio_airborne"])
+        generator_optimizer, discriminator_optimizer = self.optimizers(use_pl_optimizer=True)
+        for opt in (generator_optimizer, discriminator_optimizer):
+            if isinstance(opt, FlatAdam):
+                opt.materialize()
+
+        # Train Generator
+        self.toggle_optimizer(generator_optimizer)
+        with share_weight_norm():
+            enhanced_speech, decomposed_enhanced_speech = self.generator(corrupted_speech)
+            decomposed_reference_speech = self.generator.pqmf.forward(reference_speech, "analysis")
+            atomic_losses_generator = self.compute_atomic_losses(
+                "generator", enhanced_speech, reference_speech, decomposed_enhanced_speech,
+                decomposed_reference_speech)
+            for key, value in atomic_losses_generator.items():
+                self.log(f"train/generator/{key}", value, sync_dist=True)
+            lambdas = None
+            if self.dynamic_loss_balancing is not None:
+                lambdas = self.dynamically_balance_losses(atomic_losses_generator)
+            backprop_loss_generator = WeightedSumFn.apply(lambdas, *atomic_losses_generator.values())
+            self.log("train/generator/backprop_loss", backprop_loss_generator, sync_dist=True)
+            self.manual_backward(backprop_loss_generator, generator_optimizer)
+        generator_optimizer.step()
+        generator_optimizer.zero_grad()
+        self.untoggle_optimizer(generator_optimizer)
+
+        # Train Discriminator
+        self.toggle_optimizer(discriminator_optimizer)
+        with share_weight_norm():
+            atomic_losses_discriminator = self.compute_atomic_losses(
+                "discriminator", enhanced_speech, reference_speech, decomposed_enhanced_speech,
+                decomposed_reference_speech)
+            update = bool(atomic_losses_discriminator)
+            if update and self.update_discriminator_ratio < 1:
+                update = bool(torch.rand(1) < self.update_discriminator_ratio)
+            if update:
+                for key, value in atomic_losses_discriminator.items():
+                    self.log(f"train/discriminator/{key}", value, sync_dist=True)
+                backprop_loss_discriminator = WeightedSumFn.apply(
+                    None, atomic_losses_discriminator["real_loss"], atomic_losses_discriminator["fake_loss"])
+                self.log("train/discriminator/backprop_loss", backprop_loss_discriminator, sync_dist=True)
+                self.manual_backward(backprop_loss_discriminator, discriminator_optimizer)
+                discriminator_optimizer.step()
+                discriminator_optimizer.zero_grad()
+        self.untoggle_optimizer(discriminator_optimizer)
+
+        return {"corrupted": corrupted_speech, "enhanced": enhanced_speech, "reference": reference_speech}
+
+    def compute_atomic_losses(self, network: str, enhanced_speech, reference_speech, decomposed_enhanced_speech,
+                              decomposed_reference_speech) -> "OrderedDict[str, torch.Tensor]":
+        atomic_losses = OrderedDict()
+        assert network in {"generator", "discriminator"}
+        if network == "generator":
+            if self.reconstructive_loss_freq_fn:
+                atomic_losses["reconstructive_loss_freq"] = self.reconstructive_loss_freq_fn(
+                    enhanced_speech, reference_speech)
+            if self.reconstructive_loss_temp_fn:
+                atomic_losses["reconstructive_loss_temp"] = self.reconstructive_loss_temp_fn(
+                    enhanced_speech, reference_speech)
+            if self.feature_matching_loss_fn or self.adversarial_loss_fn:
+                enhanced_embeddings = self.discriminator(bands=decomposed_enhanced_speech, audio=enhanced_speech)
+                if self.feature_matching_loss_fn:
+                    reference_embeddings = self.discriminator(bands=decomposed_reference_speech,
+                                                              audio=reference_speech)
+                    atomic_losses["feature_matching_loss"] = self.feature_matching_loss_fn(
+                        enhanced_embeddings, reference_embeddings)
+                if self.adversarial_loss_fn:
+                    atomic_losses["adv_loss_gen"] = self.adversarial_loss_fn(embeddings=enhanced_embeddings, target=1)
+        else:
+            if self.adversarial_loss_fn:
+                enhanced_embeddings = self.discriminator(bands=decomposed_enhanced_speech.detach(),
+                                                         audio=enhanced_speech.detach())
+                reference_embeddings = self.discriminator(bands=decomposed_reference_speech, audio=reference_speech)
+                atomic_losses["real_loss"] = self.adversarial_loss_fn(embeddings=reference_embeddings, target=1)
+                atomic_losses["fake_loss"] = self.adversarial_loss_fn(embeddings=enhanced_embeddings, target=-1)
+        return atomic_losses
+
+    def dynamically_balance_losses(self, atomic_losses) -> torch.Tensor:
+        """eben.py:222-240.  Returns the detached lambdas (device tensor); the scaling itself is
+        applied inside WeightedSumFn so the un-scaled losses stay available for logging."""
+        layer = self.generator.last_conv.weight
+        n = len(atomic_losses)
+        dev = layer.device
+        if self._bal is None or self._bal["old"].numel() != n:
+            self._bal = dict(old=torch.zeros(n, device=dev), init=torch.zeros(1, device=dev, dtype=torch.int32))
+        sumsq = torch.zeros(n, device=dev, dtype=torch.float64)
+        for i, loss in enumerate(atomic_losses.values()):
+            grad = torch.autograd.grad(loss, layer, retain_graph=True)[0]
+            ops.sumsq(grad.contiguous(), sumsq[i:i + 1])
+        lambdas = torch.empty(n, device=dev)
+        norms = torch.empty(n, device=dev)
+        ops.balance(sumsq, self._bal["old"], self._bal["init"], lambdas, norms, self.beta_ema,
+                    1 if self.dynamic_loss_balancing == "ema" else 0)
+        self.last_norms, self.last_lambdas = norms, lambdas
+        return lambdas
+
+    @torch.no_grad()
+    def common_eval_step(self, batch: Dict[str, torch.Tensor], batch_idx: int = 0, stage: str = "validation",
+                         dataloader_idx: int = 0):
+        corrupted_speech = self.generator.cut_to_valid_length(batch["audio_body_conducted"])
+        enhanced_speech, decomposed_enhanced_speech = self.generator(corrupted_speech)
+        outputs = {"corrupted": corrupted_speech, "enhanced": enhanced_speech}
+        if "audio_airborne" in batch:
+            reference_speech = self.generator.cut_to_valid_length(batch["audio_airborne"])
+            decomposed_reference_speech = self.generator.pqmf.forward(reference_speech, "analysis")
+            outputs["reference"] = reference_speech
+            for net_type in ["generator", "discriminator"]:
+                for key, value in self.compute_atomic_losses(
+                        net_type, enhanced_speech, reference_speech, decomposed_enhanced_speech,
+                        decomposed_reference_speech).items():
+                    self.log(f"{stage}/{net_type}/{key}", value, sync_dist=True, add_dataloader_idx=False)
+        return outputs

@@ -1,0 +1,326 @@
+"""Tensor-level wrappers over the C ABI (include/vbx.h): raw device pointers + the current
+CUDA stream go down, nothing comes back but a status code.  No autograd here (see
+functional.py) and no fallback: every function raises unless its arguments are CUDA fp32
+contiguous tensors and libvbx_b200.so is loaded.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, Epilogue, check
+
+Tensor = torch.Tensor
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[Tensor], dtype=torch.float32) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.VbxError("vibravox_b200 ops need CUDA tensors (there is no CPU fallback)")
+    if t.dtype != dtype:
+        raise _lib.VbxError(f"expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.VbxError("expected a contiguous tensor")
+    return t.data_ptr()
+
+
+@dataclass(frozen=True)
+class ConvGeom:
+    """Static geometry of a Conv1d layer (channels, taps, stride, dilation, halo)."""
+    Cin: int
+    Cout: int
+    K: int
+    stride: int = 1
+    dil: int = 1
+    pad: int = 0      # total halo each side
+    refl: int = 0     # of which mirrored (PyTorch 'reflect'); the rest is zeros
+    groups: int = 1
+
+    def tout(self, Tin: int) -> int:
+        return (Tin + 2 * self.pad - self.dil * (self.K - 1) - 1) // self.stride + 1
+
+    def desc(self, B: int, Tin: int) -> ConvDesc:
+        return ConvDesc(B, self.Cin, self.Cout, Tin, self.tout(Tin), self.K, self.stride, self.dil,
+                        self.pad, self.refl, self.groups)
+
+
+def _epi(bias=None, res=None, mask=None, slope=1.0, beta=0.0) -> Epilogue:
+    return Epilogue(_p(bias), _p(res), _p(mask, torch.uint8), float(slope), float(beta))
+
+
+# ------------------------------------------------------------------ conv family
+def conv1d_fwd(x: Tensor, w: Tensor, g: ConvGeom, bias: Optional[Tensor] = None,
+               res: Optional[Tensor] = None, slope: float = 1.0, want_mask: bool = False,
+               out: Optional[Tensor] = None, beta: float = 0.0):
+    B, Cin, Tin = x.shape
+    assert Cin == g.Cin and tuple(w.shape) == (g.Cout, g.Cin // g.groups, g.K), (x.shape, w.shape, g)
+    d = g.desc(B, Tin)
+    y = out if out is not None else torch.empty((B, g.Cout, d.Tout), device=x.device, dtype=torch.float32)
+    mask = torch.empty(y.shape, device=x.device, dtype=torch.uint8) if want_mask else None
+    if res is not None:
+        assert res.shape == y.shape
+    e = _epi(bias, res, mask, slope, beta)
+    check(_lib.load().vbx_conv1d_fwd(ctypes.byref(d), _p(x), _p(w), ctypes.byref(e), _p(y), _stream()),
+          "vbx_conv1d_fwd")
+    return (y, mask) if want_mask else y
+
+
+def conv1d_dgrad(dy: Tensor, wt: Tensor, g: ConvGeom, Tin: int, res: Optional[Tensor] = None,
+                 slope: float = 1.0, out: Optional[Tensor] = None, beta: float = 0.0,
+                 bias: Optional[Tensor] = None) -> Tensor:
+    """dx (B,Cin,Tin) from dy (B,Cout,Tout); also the forward of ConvTranspose1d."""
+    B, Cout, Tout = dy.shape
+    d = g.desc(B, Tin)
+    assert Cout == g.Cout and Tout == d.Tout, (dy.shape, g, Tin, d.Tout)
+    assert wt.numel() == g.Cout * (g.Cin // g.groups) * g.K
+    dx = out if out is not None else torch.empty((B, g.Cin, Tin), device=dy.device, dtype=torch.float32)
+    if res is not None:
+        assert res.shape == dx.shape
+    e = _epi(bias, res, None, slope, beta)
+    check(_lib.load().vbx_conv1d_dgrad(ctypes.byref(d), _p(dy), _p(wt), ctypes.byref(e), _p(dx), _stream()),
+          "vbx_conv1d_dgrad")
+    return dx
+
+
+def conv1d_wgrad(x: Tensor, dy: Tensor, g: ConvGeom, dw: Optional[Tensor] = None) -> Tensor:
+    """dw (Cout, Cin/groups, K) += sum_{b,t} dy * x.  Allocates a zeroed dw when none is given."""
+    B, Cin, Tin = x.shape
+    d = g.desc(B, Tin)
+    assert tuple(dy.shape) == (B, g.Cout, d.Tout), (dy.shape, g, Tin)
+    if dw is None:
+        dw = torch.zeros((g.Cout, g.Cin // g.groups, g.K), device=x.device, dtype=torch.float32)
+    check(_lib.load().vbx_conv1d_wgrad(ctypes.byref(d), _p(x), _p(dy), _p(dw), _stream()), "vbx_conv1d_wgrad")
+    return dw
+
+
+def conv1d_dgrad_scatter(dy: Tensor, wk: Tensor, g: ConvGeom, Tin: int, dx: Optional[Tensor] = None) -> Tensor:
+    B = dy.shape[0]
+    d = g.desc(B, Tin)
+    assert tuple(dy.shape) == (B, g.Cout, d.Tout)
+    if dx is None:
+        dx = torch.zeros((B, g.Cin, Tin), device=dy.device, dtype=torch.float32)
+    check(_lib.load().vbx_conv1d_dgrad_scatter(ctypes.byref(d), _p(dy), _p(wk), _p(dx), _stream()),
+          "vbx_conv1d_dgrad_scatter")
+    return dx
+
+
+def transpose_weight(w: Tensor, groups: int) -> Tensor:
+    Cout, Cin_g, K = w.shape
+    wt = torch.empty_like(w)
+    check(_lib.load().vbx_transpose_weight(_p(w), _p(wt), Cout, Cin_g, K, groups, _stream()),
+          "vbx_transpose_weight")
+    return wt
+
+
+# ------------------------------------------------------------------ weight norm
+def weight_norm_fwd(g: Tensor, v: Tensor, groups: int, want_wt: bool = True) -> Tuple[Tensor, Optional[Tensor], Tensor]:
+    R, Cin_g, K = v.shape
+    assert g.numel() == R
+    w = torch.empty_like(v)
+    wt = torch.empty_like(v) if want_wt else None
+    inv = torch.empty((R,), device=v.device, dtype=torch.float32)
+    check(_lib.load().vbx_weight_norm_fwd(_p(g), _p(v), _p(w), _p(wt), _p(inv), R, Cin_g, K, groups, _stream()),
+          "vbx_weight_norm_fwd")
+    return w, wt, inv
+
+
+def weight_norm_bwd(g: Tensor, v: Tensor, inv: Tensor, dw: Tensor, dg: Optional[Tensor] = None,
+                    dv: Optional[Tensor] = None, beta: float = 0.0) -> Tuple[Tensor, Tensor]:
+    R = v.shape[0]
+    row = v.numel() // R
+    dg = dg if dg is not None else torch.empty_like(g)
+    dv = dv if dv is not None else torch.empty_like(v)
+    check(_lib.load().vbx_weight_norm_bwd(_p(g), _p(v), _p(inv), _p(dw), _p(dg), _p(dv), R, row, beta, _stream()),
+          "vbx_weight_norm_bwd")
+    return dg, dv
+
+
+# ------------------------------------------------------------------ PQMF
+def pqmf_analysis(x: Tensor, w: Tensor, bands: int, T: Optional[int] = None, x_per_band: bool = False) -> Tensor:
+    m, _, n = w.shape
+    B, C, L = x.shape
+    assert C == (bands if x_per_band else 1), "PQMF analysis expects a mono signal"
+    if T is None:
+        T = (L + n - 2) // m + 1
+    y = torch.empty((B, bands, T), device=x.device, dtype=torch.float32)
+    check(_lib.load().vbx_pqmf_analysis(_p(x), _p(w), _p(y), B, L, T, m, n, bands, int(x_per_band), _stream()),
+          "vbx_pqmf_analysis")
+    return y
+
+
+def pqmf_synthesis(x: Tensor, w: Tensor, sum_bands: bool, L: Optional[int] = None) -> Tensor:
+    m, _, n = w.shape
+    B, bands, T = x.shape
+    assert bands <= m
+    if L is None:
+        L = m * T - n
+    y = torch.empty((B, 1 if sum_bands else bands, L), device=x.device, dtype=torch.float32)
+    check(_lib.load().vbx_pqmf_synthesis(_p(x), _p(w), _p(y), B, T, L, m, n, bands, int(sum_bands), _stream()),
+          "vbx_pqmf_synthesis")
+    return y
+
+
+# ------------------------------------------------------------------ element-wise
+def leaky_relu_fwd(x: Tensor, slope: float) -> Tensor:
+    y = torch.empty_like(x)
+    check(_lib.load().vbx_leaky_relu_fwd(_p(x), _p(y), x.numel(), slope, _stream()), "vbx_leaky_relu_fwd")
+    return y
+
+
+def leaky_relu_bwd(dy: Tensor, ref: Optional[Tensor], slope: float, mask: Optional[Tensor] = None,
+                   dbias: Optional[Tensor] = None, want_dx: bool = True) -> Optional[Tensor]:
+    B, C, T = dy.shape
+    dx = torch.empty_like(dy) if want_dx else None
+    check(_lib.load().vbx_leaky_relu_bwd(_p(dy), _p(ref), _p(mask, torch.uint8), _p(dx), _p(dbias), B, C, T,
+                                         slope, 0.0, _stream()), "vbx_leaky_relu_bwd")
+    return dx
+
+
+def tanh_recompose_fwd(x: Tensor, first: Optional[Tensor], p: int) -> Tensor:
+    B, m, T = x.shape
+    y = torch.empty_like(x)
+    check(_lib.load().vbx_tanh_recompose_fwd(_p(x), _p(first), _p(y), B, m, p, T, _stream()),
+          "vbx_tanh_recompose_fwd")
+    return y
+
+
+def tanh_bwd(dy: Tensor, y: Tensor) -> Tensor:
+    dx = torch.empty_like(dy)
+    check(_lib.load().vbx_tanh_bwd(_p(dy), _p(y), _p(dx), dy.numel(), _stream()), "vbx_tanh_bwd")
+    return dx
+
+
+def add(a: Tensor, b: Tensor) -> Tensor:
+    assert a.shape == b.shape
+    y = torch.empty_like(a)
+    check(_lib.load().vbx_add(_p(a), _p(b), _p(y), a.numel(), _stream()), "vbx_add")
+    return y
+
+
+def axpby(x: Tensor, y: Tensor, alpha: float, beta: float) -> Tensor:
+    check(_lib.load().vbx_axpby(_p(x), _p(y), x.numel(), alpha, beta, _stream()), "vbx_axpby")
+    return y
+
+
+def fill(t: Tensor, value: float) -> Tensor:
+    check(_lib.load().vbx_fill(_p(t), t.numel(), value, _stream()), "vbx_fill")
+    return t
+
+
+# ------------------------------------------------------------------ losses / reductions
+def _zeros_f64(n: int, device) -> Tensor:
+    return torch.zeros((n,), device=device, dtype=torch.float64)
+
+
+def l1_pair_sums(a: Tensor, b: Tensor, sums: Tensor) -> None:
+    assert a.shape == b.shape
+    check(_lib.load().vbx_l1_pair_sums(_p(a), _p(b), a.numel(), sums.data_ptr(), _stream()), "vbx_l1_pair_sums")
+
+
+def fm_finalize(sums: Tensor, npairs: int, scale: float) -> Tensor:
+    loss = torch.empty((), device=sums.device, dtype=torch.float32)
+    check(_lib.load().vbx_fm_finalize(_p(sums, torch.float64), npairs, scale, _p(loss), _stream()), "vbx_fm_finalize")
+    return loss
+
+
+def l1_pair_bwd(a: Tensor, b: Tensor, sums: Tensor, go: Tensor, scale: float, want_da: bool, want_db: bool):
+    da = torch.empty_like(a) if want_da else None
+    db = torch.empty_like(b) if want_db else None
+    check(_lib.load().vbx_l1_pair_bwd(_p(a), _p(b), a.numel(), sums.data_ptr(), _p(go), scale, _p(da), _p(db),
+                                      _stream()), "vbx_l1_pair_bwd")
+    return da, db
+
+
+def hinge_fwd(c: Tensor, target: float, scale: float, acc: Tensor) -> None:
+    check(_lib.load().vbx_hinge_fwd(_p(c), c.numel(), target, scale, _p(acc, torch.float64), _stream()),
+          "vbx_hinge_fwd")
+
+
+def hinge_bwd(c: Tensor, target: float, scale: float, go: Tensor) -> Tensor:
+    dc = torch.empty_like(c)
+    check(_lib.load().vbx_hinge_bwd(_p(c), c.numel(), target, scale, _p(go), _p(dc), _stream()), "vbx_hinge_bwd")
+    return dc
+
+
+def d2f(src: Tensor, scale: float = 1.0) -> Tensor:
+    dst = torch.empty(src.shape, device=src.device, dtype=torch.float32)
+    check(_lib.load().vbx_d2f(_p(src, torch.float64), _p(dst), src.numel(), scale, _stream()), "vbx_d2f")
+    return dst
+
+
+def stft_stats(X: Tensor, Y: Tensor, eps: float, stats: Tensor) -> None:
+    B, C2, F = X.shape
+    assert X.shape == Y.shape and C2 % 2 == 0
+    check(_lib.load().vbx_stft_stats(_p(X), _p(Y), B, C2 // 2, F, eps, stats.data_ptr(), _stream()), "vbx_stft_stats")
+
+
+def stft_finalize(stats: Tensor, counts: Tensor, nres: int, w: float) -> Tensor:
+    loss = torch.empty((), device=stats.device, dtype=torch.float32)
+    check(_lib.load().vbx_stft_finalize(_p(stats, torch.float64), _p(counts, torch.float64), nres, w, _p(loss),
+                                        _stream()), "vbx_stft_finalize")
+    return loss
+
+
+def stft_bwd(X: Tensor, Y: Tensor, eps: float, stats: Tensor, count: float, go: Tensor, w: float) -> Tensor:
+    B, C2, F = X.shape
+    dX = torch.empty_like(X)
+    check(_lib.load().vbx_stft_bwd(_p(X), _p(Y), B, C2 // 2, F, eps, stats.data_ptr(), float(count), _p(go), w,
+                                   _p(dX), _stream()), "vbx_stft_bwd")
+    return dX
+
+
+def weighted_sum(xs, lam: Optional[Tensor]):
+    n = len(xs)
+    ptrs = [_p(x) for x in xs] + [None] * (4 - n)
+    terms = torch.empty((n,), device=xs[0].device, dtype=torch.float32)
+    total = torch.empty((), device=xs[0].device, dtype=torch.float32)
+    check(_lib.load().vbx_weighted_sum(*ptrs, n, _p(lam), _p(terms), _p(total), _stream()), "vbx_weighted_sum")
+    return total, terms
+
+
+def scalar_mul(go: Tensor, lam: Optional[Tensor], n: int) -> Tensor:
+    out = torch.empty((n,), device=go.device, dtype=torch.float32)
+    check(_lib.load().vbx_scalar_mul(_p(go), _p(lam), _p(out), n, _stream()), "vbx_scalar_mul")
+    return out
+
+
+def sumsq(x: Tensor, acc: Tensor) -> None:
+    check(_lib.load().vbx_sumsq(_p(x), x.numel(), acc.data_ptr(), _stream()), "vbx_sumsq")
+
+
+def balance(sumsq_t: Tensor, norms_old: Tensor, initialised: Tensor, lambdas: Tensor, norms_out: Tensor,
+            beta_ema: float, mode: int) -> None:
+    n = lambdas.numel()
+    check(_lib.load().vbx_balance(_p(sumsq_t, torch.float64), _p(norms_old), _p(initialised, torch.int32),
+                                  _p(lambdas), _p(norms_out), n, beta_ema, mode, _stream()), "vbx_balance")
+
+
+def adam_tick(step: Tensor) -> None:
+    check(_lib.load().vbx_adam_tick(_p(step, torch.int32), _stream()), "vbx_adam_tick")
+
+
+def adam_step(p: Tensor, grad: Tensor, m: Tensor, v: Tensor, step: Tensor, lr: float, b1: float, b2: float,
+              eps: float, grad_scale: float = 1.0) -> None:
+    assert p.numel() == grad.numel() == m.numel() == v.numel()
+    check(_lib.load().vbx_adam_step(_p(p), _p(grad), _p(m), _p(v), p.numel(), _p(step, torch.int32), lr, b1, b2,
+                                    eps, grad_scale, _stream()), "vbx_adam_step")
+
+
+def noise_mix_crop(body: Tensor, air: Tensor, noise: Tensor, start: Tensor, off: Tensor, length: int):
+    B, Ls = body.shape[0], body.shape[-1]
+    Ln = noise.shape[-1]
+    out_body = torch.empty((B, 1, length), device=body.device, dtype=torch.float32)
+    out_air = torch.empty((B, 1, length), device=body.device, dtype=torch.float32)
+    check(_lib.load().vbx_noise_mix_crop(_p(body), _p(air), _p(noise), _p(start, torch.int32), _p(off, torch.int32),
+                                         _p(out_body), _p(out_air), B, Ls, Ln, length, _stream()),
+          "vbx_noise_mix_crop")
+    return out_body, out_air

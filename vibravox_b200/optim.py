@@ -1,0 +1,96 @@
+"""FlatAdam: torch.optim.Adam semantics (configs/lightning_module/optimizer/adam.yaml:1-9 of the
+reference) on ONE flat fp32 bucket per network.
+
+On first use every parameter is re-pointed at a slice of `flat` (values preserved), and gets
+a `_vbx_grad` view into `grad` that the backward kernels (weight-norm backward, wgrad, bias
+reduction) accumulate into directly.  `step()` is then two launches (tick + fused Adam) over
+the whole network, `zero_grad()` one fill, and data-parallel training all-reduces `grad`
+once per network.  Use as `_target_: vibravox_b200.optim.FlatAdam` with
+`_partial_: true`, exactly where the reference config has torch.optim.Adam.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List
+
+import torch
+
+from . import ops
+
+
+class FlatAdam(torch.optim.Optimizer):
+    def __init__(self, params: Iterable[torch.Tensor], lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.0, amsgrad: bool = False):
+        if weight_decay != 0.0 or amsgrad:
+            raise NotImplementedError("FlatAdam implements the reference configuration: weight_decay=0, amsgrad=False")
+        defaults = dict(lr=lr, betas=tuple(betas), eps=eps)
+        super().__init__([p for p in params if p.requires_grad], defaults)
+        if len(self.param_groups) != 1:
+            raise NotImplementedError("FlatAdam supports a single parameter group")
+        self._indirect: List[int] = []      # ids of params whose grads arrive through autograd (.grad)
+        self.flat = self.grad = self.exp_avg = self.exp_avg_sq = self.step_count = None
+        self.grad_scale = 1.0               # set to 1/world_size after a sum all-reduce of `grad`
+
+    # ---- layout ---------------------------------------------------------------------------------
+    def keep_autograd_grad(self, params: Iterable[torch.Tensor]) -> None:
+        """Parameters that must keep ordinary `.grad` semantics (targets of torch.autograd.grad,
+        e.g. generator.last_conv.weight in dynamically_balance_losses, eben.py:223-228)."""
+        assert self.flat is None, "call before the first step / materialize()"
+        self._indirect += [id(p) for p in params]
+
+    @property
+    def params(self) -> List[torch.Tensor]:
+        return self.param_groups[0]["params"]
+
+    def materialize(self) -> None:
+        if self.flat is not None:
+            return
+        ps = self.params
+        dev = ps[0].device
+        if dev.type != "cuda" or any(p.device != dev for p in ps):
+            raise RuntimeError("FlatAdam needs all parameters on one CUDA device (no CPU fallback)")
+        offs, total = [], 0
+        for p in ps:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4          # keep every slice 16-byte aligned
+        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros_like(self.flat)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.step_count = torch.zeros(1, device=dev, dtype=torch.int32)
+        self._slices = []
+        with torch.no_grad():
+            for p, off in zip(ps, offs):
+                n = p.numel()
+                self.flat[off:off + n].copy_(p.data.reshape(-1))
+                p.data = self.flat[off:off + n].view(p.shape)
+                slot = self.grad[off:off + n].view(p.shape)
+                self._slices.append(slot)
+                if id(p) not in self._indirect:
+                    p._vbx_grad = slot
+                p.grad = None
+
+    # ---- torch.optim API ------------------------------------------------------------------------
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        self.materialize()
+        ops.fill(self.grad, 0.0)
+        for p in self.params:
+            p.grad = None
+
+    def gather_autograd_grads(self) -> None:
+        """Fold `.grad` of the keep_autograd_grad parameters into the bucket (before an all-reduce)."""
+        for p, slot in zip(self.params, self._slices):
+            if p.grad is not None:
+                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                ops.axpby(g, slot, 1.0, 1.0)
+                p.grad = None
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        assert closure is None
+        self.materialize()
+        self.gather_autograd_grads()
+        g = self.param_groups[0]
+        ops.adam_tick(self.step_count)
+        ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count, g["lr"],
+                      g["betas"][0], g["betas"][1], g["eps"], self.grad_scale)
+        return None

@@ -1,0 +1,66 @@
+"""DiscriminatorEBENMultiScales drop-in (reference: vibravox/torch_modules/dnn/eben_discriminator.py:10-163).
+`DiscriminatorEBENMultiScales(q=3, min_channels=24).forward(bands, audio) -> List[List[Tensor]]`:
+three PQMF-band discriminators (dilation 1, 2, 3; grouped convs) on `bands[:, -q:, :]` and one
+MelGAN discriminator on the waveform; element 0 of every list is the input, intermediate
+entries are post-LeakyReLU(0.2), the last is the raw certainty map."""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+from torch import nn
+
+try:
+    from huggingface_hub import PyTorchModelHubMixin
+except Exception:  # pragma: no cover
+    class PyTorchModelHubMixin:  # type: ignore
+        pass
+
+from ..utils import normalized_conv1d
+from .melgan_discriminator import DiscriminatorMelGAN, run_stage
+
+
+class DiscriminatorEBEN(nn.Module):
+    def __init__(self, dilation: int = 1, q: int = 3, min_channels: int = 24):
+        super().__init__()
+        self.dilation = dilation
+        assert min_channels % q == 0, "min_channels must be a multiple of q"
+        c = min_channels
+
+        def act():
+            return nn.LeakyReLU(0.2, inplace=True)
+
+        stages = [nn.Sequential(nn.ReflectionPad1d(1),
+                                normalized_conv1d(q, c, kernel_size=(3,), stride=(1,), padding=(1,),
+                                                  dilation=dilation, groups=q), act())]
+        for _ in range(5):
+            stages.append(nn.Sequential(normalized_conv1d(c, 2 * c, kernel_size=(7,), stride=(2,), padding=(3,),
+                                                          dilation=dilation, groups=q), act()))
+            c *= 2
+        stages.append(nn.Sequential(normalized_conv1d(c, c, kernel_size=(5,), stride=(1,), padding=(2,),
+                                                      dilation=dilation, groups=q), act()))
+        stages.append(normalized_conv1d(c, 1, kernel_size=(3,), stride=(1,), padding=(1,), groups=1))
+        self.discriminator = nn.ModuleList(stages)
+
+    def forward(self, bands: torch.Tensor) -> List[torch.Tensor]:
+        embeddings = [bands]
+        for stage in self.discriminator:
+            embeddings.append(run_stage(stage, embeddings[-1]))
+        return embeddings
+
+
+class DiscriminatorEBENMultiScales(nn.Module, PyTorchModelHubMixin):
+    def __init__(self, q: int = 3, min_channels: int = 24):
+        super().__init__()
+        self.q = q
+        self.pqmf_discriminators = nn.ModuleList(
+            [DiscriminatorEBEN(dilation=d, q=q, min_channels=min_channels) for d in (1, 2, 3)])
+        self.melgan_discriminator = DiscriminatorMelGAN(alpha_leaky_relu=0.2)
+
+    def forward(self, bands: torch.Tensor, audio: torch.Tensor) -> List[List[torch.Tensor]]:
+        selected = bands[:, -self.q:, :]
+        if not selected.is_contiguous():
+            selected = selected.contiguous()
+        embeddings = [dis(selected) for dis in self.pqmf_discriminators]
+        embeddings.append(self.melgan_discriminator(audio))
+        return embeddings

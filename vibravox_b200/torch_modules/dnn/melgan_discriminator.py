@@ -1,0 +1,53 @@
+"""DiscriminatorMelGAN drop-in (reference: vibravox/torch_modules/dnn/melgan_discriminator.py:76-169).
+Same container tree (hence state_dict keys); each `conv (+ReflectionPad1d) + bias + LeakyReLU`
+stage is one fused implicit-GEMM kernel launch."""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+from torch import nn
+
+from ...functional import ConvFn
+from ..utils import conv_geom, effective_weight, normalized_conv1d
+
+
+def run_stage(stage: nn.Module, x: torch.Tensor) -> torch.Tensor:
+    """One entry of a discriminator's ModuleList: [ReflectionPad1d] + wn-Conv1d [+ LeakyReLU]."""
+    extra, slope, conv = 0, 1.0, stage
+    if isinstance(stage, nn.Sequential):
+        conv = None
+        for mod in stage:
+            if isinstance(mod, nn.ReflectionPad1d):
+                extra = int(mod.padding[0])
+            elif isinstance(mod, nn.Conv1d):
+                conv = mod
+            elif isinstance(mod, nn.LeakyReLU):
+                slope = mod.negative_slope
+    w, wt = effective_weight(conv)
+    return ConvFn.apply(x, w, wt, conv.bias, conv_geom(conv, extra), slope)
+
+
+class DiscriminatorMelGAN(nn.Module):
+    def __init__(self, alpha_leaky_relu: float):
+        super().__init__()
+        a = alpha_leaky_relu
+
+        def act():
+            return nn.LeakyReLU(a, inplace=True)
+
+        self.discriminator = nn.ModuleList([
+            nn.Sequential(nn.ReflectionPad1d(7), normalized_conv1d(1, 16, kernel_size=(15,), stride=(1,)), act()),
+            nn.Sequential(normalized_conv1d(16, 64, kernel_size=(41,), stride=(4,), padding=20, groups=4), act()),
+            nn.Sequential(normalized_conv1d(64, 256, kernel_size=(41,), stride=(4,), padding=20, groups=4), act()),
+            nn.Sequential(normalized_conv1d(256, 1024, kernel_size=(41,), stride=(4,), padding=20, groups=4), act()),
+            nn.Sequential(normalized_conv1d(1024, 1024, kernel_size=(41,), stride=(4,), padding=20, groups=4), act()),
+            nn.Sequential(normalized_conv1d(1024, 1024, kernel_size=(5,), stride=(1,), padding=2), act()),
+            normalized_conv1d(1024, 1, kernel_size=3, stride=1, padding=1),
+        ])
+
+    def forward(self, audio: torch.Tensor) -> List[torch.Tensor]:
+        embeddings = [audio]
+        for stage in self.discriminator:
+            embeddings.append(run_stage(stage, embeddings[-1]))
+        return embeddings
