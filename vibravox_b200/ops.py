@@ -33,6 +33,11 @@ def _p(t: Optional[Tensor], dtype=torch.float32) -> Optional[int]:
     return t.data_ptr()
 
 
+def require_cuda(device) -> None:
+    if torch.device(device).type != "cuda":
+        raise _lib.VbxError("vibravox_b200 needs CUDA tensors (there is no CPU fallback)")
+
+
 @dataclass(frozen=True)
 class ConvGeom:
     """Static geometry of a Conv1d layer (channels, taps, stride, dilation, halo)."""

@@ -46,8 +46,9 @@ class FlatAdam(torch.optim.Optimizer):
             return
         ps = self.params
         dev = ps[0].device
-        if dev.type != "cuda" or any(p.device != dev for p in ps):
-            raise RuntimeError("FlatAdam needs all parameters on one CUDA device (no CPU fallback)")
+        ops.require_cuda(dev)
+        if any(p.device != dev for p in ps):
+            raise RuntimeError("FlatAdam needs all parameters on one device")
         offs, total = [], 0
         for p in ps:
             offs.append(total)
