@@ -193,11 +193,14 @@ def test_mrstft_loss_and_per_bin_magnitudes():
     from vibravox_b200.torch_modules.losses.mrstft_loss import MultiResolutionSTFTLoss
     torch.manual_seed(4)
     B, L = 2, 15840
-    x = (0.3 * torch.randn(B, 1, L)).double().requires_grad_(True)
+    x = (0.3 * torch.randn(B, 1, L)).double().requires_grad_(True)      # fp32-representable values
     y = (0.3 * torch.randn(B, 1, L)).double()
     taps = O.a_weighting_fir()
     want = O.mrstft_loss(x, y, taps.double())
     (gx,) = torch.autograd.grad(want, x)
+    x32 = x.detach().float().requires_grad_(True)
+    (g32,) = torch.autograd.grad(O.mrstft_loss(x32, y.float(), taps), x32)
+    noise = (g32.double() - gx).norm() / gx.norm()      # the reference arithmetic's own fp32 noise (log of tiny bins)
     mod = MultiResolutionSTFTLoss(fft_sizes=(512, 1024, 2048), hop_sizes=(50, 120, 240),
                                   win_lengths=(240, 600, 1200), sample_rate=16000, perceptual_weighting=True).to(DEV)
     assert torch.allclose(mod.fir_taps.cpu().view(-1), taps, atol=0, rtol=0)
@@ -206,7 +209,8 @@ def test_mrstft_loss_and_per_bin_magnitudes():
     assert float(got) == pytest.approx(float(want), rel=2e-5)
     (gxc,) = torch.autograd.grad(got, xc)
     err = (gxc.cpu().double() - gx).norm() / gx.norm()
-    assert err < 2e-4, float(err)
+    print("mrstft grad rel-L2 vs fp64:", float(err), "fp32 oracle:", float(noise))
+    assert err < 2 * noise + 1e-4, (float(err), float(noise))
     # per-bin magnitudes
     spec = mod._get_spec(torch.device(DEV, torch.cuda.current_device()))
     sig = x.detach().float().view(B, 1, L).to(DEV)

