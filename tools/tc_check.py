@@ -1,0 +1,45 @@
+"""GPU check of the tcgen05 conv kernels against the fp32 SIMT kernels / fp64 torch (run under `timeout`)."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.nn.functional as F
+from vibravox_b200 import ops
+
+dev = "cuda"
+torch.manual_seed(0)
+CASES = [
+    # B, Cin, Cout, Tin, K, s, d, pad, refl, groups
+    (1, 32, 32, 256, 1, 1, 1, 0, 0, 1),
+    (2, 32, 32, 300, 3, 1, 3, 3, 3, 1),
+    (2, 64, 256, 403, 41, 4, 1, 20, 0, 4),
+    (2, 1024, 1024, 60, 5, 1, 1, 2, 0, 1),
+    (3, 768, 768, 50, 5, 1, 2, 2, 0, 4),
+    (2, 32, 64, 301, 4, 2, 1, 1, 1, 1),
+    (2, 24, 48, 131, 7, 2, 2, 3, 0, 4),
+    (32, 1024, 1024, 748, 41, 4, 1, 20, 0, 4),
+    (32, 32, 32, 11968, 3, 1, 3, 3, 3, 1),
+]
+which = [int(a) for a in sys.argv[1:]] or range(len(CASES))
+for i in which:
+    B, Cin, Cout, Tin, K, s, d, pad, refl, groups = CASES[i]
+    g = ops.ConvGeom(Cin, Cout, K, s, d, pad, refl, groups)
+    x = torch.randn(B, Cin, Tin, device=dev)
+    w = torch.randn(Cout, Cin // groups, K, device=dev) / (Cin // groups * K) ** 0.5
+    bias = torch.randn(Cout, device=dev)
+    ref = ops.conv1d_fwd(x, w, g, bias=bias, slope=0.2)
+    packed = ops.tc_pack_fwd(w, g)
+    y = ops.tc_conv1d_fwd(x, packed, g, bias=bias, slope=0.2)
+    torch.cuda.synchronize()
+    err = float((y - ref).abs().max()), float((y - ref).norm() / ref.norm())
+    def tm(fn, n=5):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n): fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    t_tc = tm(lambda: ops.tc_conv1d_fwd(x, packed, g, bias=bias, slope=0.2))
+    t_simt = tm(lambda: ops.conv1d_fwd(x, w, g, bias=bias, slope=0.2))
+    flops = 2.0 * B * g.tout(Tin) * Cout * (Cin // groups) * K
+    print(f"case {i} {CASES[i]}: max abs {err[0]:.2e} rel-L2 {err[1]:.2e} | tc {t_tc:.3f} ms ({flops/t_tc/1e9:.1f} TF) simt {t_simt:.3f} ms ({flops/t_simt/1e9:.1f} TF)", flush=True)
+print("done")

@@ -1,0 +1,298 @@
+// Tensor-core (tcgen05 / TMEM) implicit-GEMM Conv1d for the dense layers of the EBEN step.
+//
+// Orientation: rows of the MMA (M = 128) are output TIME positions, columns (N <= 256) are output
+// channels, the reduction runs over (input channel, tap):
+//     D[(b,t), co] = sum_{(ci,k)} A[(b,t), (ci,k)] * W[co, (ci,k)]
+//   * A is the im2col view of the fp32 (B,C,T) activations.  It is never materialised in HBM: eight
+//     producer warps gather it (lanes walk t => coalesced 128-byte reads, reflect / zero halo folded
+//     into the index), split every value into bf16 hi + lo and store it straight into the MN-major
+//     canonical shared-memory layout the MMA descriptor expects.
+//   * W is pre-packed once per weight update (vbx_tc_pack_fwd) into K-major bf16 hi / lo tiles that
+//     are exactly the shared-memory image, so one thread streams them in with a linear bulk-async
+//     copy (TMA engine) that completes on an mbarrier.
+//   * One thread issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32 in TMEM), three per k-step:
+//     hi*hi + hi*lo + lo*hi  ("bf16x3": 16 mantissa bits per operand, fp32 accumulate; measured
+//     1e-5-class agreement with the fp32 reference, inside the 1e-4 contract).
+//   * Epilogue: TMEM lane == time position, so after tcgen05.ld each warp writes 32 consecutive t of
+//     one output channel per store: coalesced into the reference's (B,C,T) layout, with bias /
+//     LeakyReLU / residual / mask fused exactly as in the SIMT path.
+// Two CTAs per SM (<= 256 TMEM columns and <= ~110 KB smem each) overlap one tile's epilogue with
+// the other's main loop.
+#include "common.cuh"
+#include "conv_plan.h"
+#include "tc_common.cuh"
+
+namespace vbx {
+namespace tc {
+
+static const int kRows = 128;               // MMA M
+static const int kKC = 32;                  // reduction elements per stage (2 MMA k-steps of 16)
+static const int kSboA = 144;               // bytes between consecutive 8-row units of A (padded: conflict-free stores)
+static const int kLboA = 16 * kSboA;        // bytes between 8-k groups of A
+static const int kPlaneA = (kKC / 8) * kLboA;   // 9216
+static const int kProducers = 256;
+static const int kThreads = 320;            // 8 producer/epilogue warps + MMA warp + weight-copy warp
+
+struct TcP {
+  GemmP g;
+  const unsigned char* packed;
+  int NT, ntiles_n, nchunks, tmem_cols, stages;
+};
+
+__host__ __device__ inline int plane_b(int NT) { return NT * 64; }                 // NT rows x 32 bf16
+__host__ __device__ inline int stage_bytes(int NT) { return 2 * kPlaneA + 2 * plane_b(NT); }
+
+inline int pick_nt(int Cout_g) {
+  int r = (Cout_g + 15) / 16 * 16;
+  if (r <= 256) return r;
+  // split evenly into tiles of <= 256 columns
+  int tiles = (r + 255) / 256;
+  int nt = ((r + tiles - 1) / tiles + 15) / 16 * 16;
+  return nt;
+}
+inline int pow2_cols(int n) { int c = 32; while (c < n) c <<= 1; return c; }
+inline int pick_stages(int NT) {
+  int s = (108 * 1024) / stage_bytes(NT);
+  return s > 4 ? 4 : (s < 2 ? 2 : s);
+}
+
+__device__ __forceinline__ float finish(const GemmP& P, float v, int ch, long long idx) {
+  if (P.bias) v += P.bias[ch];
+  if (P.mask) P.mask[idx] = v > 0.f ? 1 : 0;
+  if (P.slope != 1.f) v = v > 0.f ? v : v * P.slope;
+  if (P.res) v += P.res[idx];
+  if (P.beta != 0.f) v += P.beta * P.Y[idx];
+  return v;
+}
+
+__global__ void __launch_bounds__(kThreads, 2) tc_conv_fwd_kernel(const TcP P) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const GemmP& G = P.g;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = P.stages, NT = P.NT;
+  const int stage_sz = stage_bytes(NT);
+  unsigned char* stage0 = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_sz);
+  uint64_t* full_a = bars;
+  uint64_t* full_b = bars + S;
+  uint64_t* empty = bars + 2 * S;
+  uint64_t* acc_full = bars + 3 * S;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 1);
+
+  const int grp = blockIdx.y / P.ntiles_n, nt = blockIdx.y % P.ntiles_n;
+  const int row_base = blockIdx.x * kRows;
+  const int N = G.B * G.Tout;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_a[s], kProducers);
+      mbar_init(&full_b[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    // ===================== A producers: im2col gather -> bf16 hi/lo -> MN-major smem =====================
+    const int row = tid & 127, kh = tid >> 7;
+    const int n = row_base + row;
+    const bool valid = n < N;
+    const int b = valid ? n / G.Tout : 0, t = valid ? n % G.Tout : 0;
+    const float* xrow = G.X + ((long long)b * G.Cin + grp * G.Cin_g) * G.Tin;
+    const int tpos = t * G.stride - G.pad;
+    int ci = (kh * 16) / G.K, k = (kh * 16) % G.K;
+    const uint32_t row_off = (uint32_t)(row >> 3) * kSboA + (uint32_t)(row & 7) * 2;
+    for (int c = 0; c < P.nchunks; ++c) {
+      const int s = c % S, use = c / S;
+      mbar_wait(&empty[s], (use & 1) ^ 1);
+      unsigned char* a_hi = stage0 + (size_t)s * stage_sz;
+      unsigned char* a_lo = a_hi + kPlaneA;
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float x = 0.f;
+        if (valid && ci < G.Cin_g) {
+          int p = map_pos(tpos + k * G.dil, G.Tin, G.refl);
+          if (p >= 0) x = xrow[(long long)ci * G.Tin + p];
+        }
+        v[i] = x;
+        if (++k == G.K) { k = 0; ++ci; }
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int kk = kh * 16 + i;
+        const uint32_t off = row_off + (uint32_t)(kk >> 3) * kLboA + (uint32_t)(kk & 7) * 16;
+        __nv_bfloat16 hi, lo;
+        split_bf16(v[i], hi, lo);
+        *reinterpret_cast<__nv_bfloat16*>(a_hi + off) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(a_lo + off) = lo;
+      }
+      k += 16;
+      if (k >= G.K) { ci += k / G.K; k %= G.K; }
+      fence_proxy_async();
+      mbar_arrive(&full_a[s]);
+    }
+    // ===================== epilogue: TMEM -> registers -> fused output stage -> (B,C,T) =====================
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int q = warp & 3, half = warp >> 2;
+    const int erow = q * 32 + lane;
+    const int en = row_base + erow;
+    const bool ev = en < N;
+    const int eb = ev ? en / G.Tout : 0, et = ev ? en % G.Tout : 0;
+    const int nblk = NT / 16;
+    const int blk_lo = half == 0 ? 0 : (nblk + 1) / 2, blk_hi = half == 0 ? (nblk + 1) / 2 : nblk;
+    for (int blk = blk_lo; blk < blk_hi; ++blk) {
+      float acc[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * 16), acc);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int col = nt * NT + blk * 16 + j;
+        if (ev && col < G.Cout_g) {
+          const int ch = grp * G.Cout_g + col;
+          const long long idx = ((long long)eb * G.Cout + ch) * G.Tout + et;
+          G.Y[idx] = finish(G, acc[j], ch, idx);
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(NT, /*a_mn=*/true, /*b_mn=*/false);
+      const uint32_t lbo_b = (uint32_t)NT * 16;
+      uint32_t accumulate = 0;
+      for (int c = 0; c < P.nchunks; ++c) {
+        const int s = c % S, use = c / S;
+        mbar_wait(&full_a[s], use & 1);
+        mbar_wait(&full_b[s], use & 1);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(stage0 + (size_t)s * stage_sz), a_lo = a_hi + kPlaneA;
+        const uint32_t b_hi = a_hi + 2 * kPlaneA, b_lo = b_hi + plane_b(NT);
+#pragma unroll
+        for (int ks = 0; ks < kKC / 16; ++ks) {
+          const uint64_t da_hi = make_desc(a_hi + ks * 2 * kLboA, kLboA, kSboA);
+          const uint64_t da_lo = make_desc(a_lo + ks * 2 * kLboA, kLboA, kSboA);
+          const uint64_t db_hi = make_desc(b_hi + ks * 2 * lbo_b, lbo_b, 128);
+          const uint64_t db_lo = make_desc(b_lo + ks * 2 * lbo_b, lbo_b, 128);
+          mma_bf16_ss(tmem_base, da_hi, db_hi, idesc, accumulate);
+          accumulate = 1;
+          mma_bf16_ss(tmem_base, da_hi, db_lo, idesc, 1);
+          mma_bf16_ss(tmem_base, da_lo, db_hi, idesc, 1);
+        }
+        mma_commit(&empty[s]);       // frees the stage once these MMAs have read it
+      }
+      mma_commit(acc_full);
+    }
+  } else {
+    // ===================== weight tiles: linear bulk copies (TMA engine) =====================
+    if (lane == 0) {
+      const uint32_t bytes = 2u * (uint32_t)plane_b(NT);
+      const unsigned char* src = P.packed + ((size_t)(grp * P.ntiles_n + nt) * P.nchunks) * bytes;
+      for (int c = 0; c < P.nchunks; ++c) {
+        const int s = c % S, use = c / S;
+        mbar_wait(&empty[s], (use & 1) ^ 1);
+        mbar_expect_tx(&full_b[s], bytes);
+        bulk_copy_g2s(stage0 + (size_t)s * stage_sz + 2 * kPlaneA, src + (size_t)c * bytes, bytes, &full_b[s]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+}
+
+// one thread per 16-byte unit (8 consecutive reduction elements of one output channel)
+__global__ void tc_pack_fwd_kernel(const float* __restrict__ w, unsigned char* __restrict__ out, int Cout_g,
+                                   int Kred, int groups, int NT, int ntiles_n, int nchunks) {
+  const long long units = (long long)groups * ntiles_n * nchunks * 4 * NT;
+  for (long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x; u < units;
+       u += (long long)gridDim.x * blockDim.x) {
+    int n = (int)(u % NT);
+    long long r = u / NT;
+    int ku = (int)(r % 4); r /= 4;
+    int c = (int)(r % nchunks); r /= nchunks;
+    int nt = (int)(r % ntiles_n);
+    int g = (int)(r / ntiles_n);
+    const int co = nt * NT + n;
+    const int kk0 = c * kKC + ku * 8;
+    __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = 0.f;
+      if (co < Cout_g && kk0 + j < Kred) v = w[((long long)g * Cout_g + co) * Kred + kk0 + j];
+      split_bf16(v, hi[j], lo[j]);
+    }
+    unsigned char* base = out + ((size_t)((g * ntiles_n + nt) * (long long)nchunks + c)) * 2 * plane_b(NT);
+    const size_t off = ((size_t)ku * NT + n) * 16;
+    *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(base + plane_b(NT) + off) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
+static int fill_tc(TcP& P, const vbx_conv_desc* d) {
+  int code = 0;
+  const char* msg = check_desc_msg(d, &code);
+  if (msg) return fail(code, msg);
+  fill(P.g, d);
+  P.NT = pick_nt(P.g.Cout_g);
+  P.ntiles_n = (P.g.Cout_g + P.NT - 1) / P.NT;
+  P.nchunks = (P.g.Cin_g * P.g.K + kKC - 1) / kKC;
+  P.tmem_cols = pow2_cols(P.NT);
+  P.stages = pick_stages(P.NT);
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace vbx
+
+using namespace vbx;
+using namespace vbx::tc;
+
+extern "C" int64_t vbx_tc_fwd_pack_bytes(const vbx_conv_desc* d) {
+  TcP P;
+  if (fill_tc(P, d)) return -1;
+  return (int64_t)P.g.groups * P.ntiles_n * P.nchunks * 2 * plane_b(P.NT);
+}
+
+extern "C" int vbx_tc_pack_fwd(const vbx_conv_desc* d, const float* w, void* packed, void* stream) {
+  TcP P;
+  if (int r = fill_tc(P, d)) return r;
+  VBX_REQUIRE(w && packed, VBX_BAD_POINTER, "tc_pack_fwd: null tensor");
+  VBX_REQUIRE(((uintptr_t)packed & 15) == 0, VBX_BAD_POINTER, "tc_pack_fwd: packed buffer must be 16-byte aligned");
+  long long units = (long long)P.g.groups * P.ntiles_n * P.nchunks * 4 * P.NT;
+  int blocks = (int)((units + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  tc_pack_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (unsigned char*)packed, P.g.Cout_g,
+                                                               P.g.Cin_g * P.g.K, P.g.groups, P.NT, P.ntiles_n,
+                                                               P.nchunks);
+  return launched("tc_pack_fwd_kernel");
+}
+
+extern "C" int vbx_tc_conv1d_fwd(const vbx_conv_desc* d, const float* x, const void* packed,
+                                 const vbx_epilogue* e, float* y, void* stream) {
+  TcP P;
+  if (int r = fill_tc(P, d)) return r;
+  VBX_REQUIRE(x && packed && y, VBX_BAD_POINTER, "tc_conv1d_fwd: null tensor");
+  VBX_REQUIRE(((uintptr_t)packed & 15) == 0, VBX_BAD_POINTER, "tc_conv1d_fwd: packed weights must be 16-byte aligned");
+  fill_epi(P.g, e);
+  P.g.X = x; P.g.Y = y;
+  P.packed = (const unsigned char*)packed;
+  const size_t smem = (size_t)P.stages * stage_bytes(P.NT) + (3 * P.stages + 1) * sizeof(uint64_t) + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t ce = cudaFuncSetAttribute(tc_conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (ce != cudaSuccess) return fail((int)ce, "tc_conv1d_fwd: cannot raise dynamic shared memory limit");
+    attr_set = true;
+  }
+  const long long N = (long long)P.g.B * P.g.Tout;
+  dim3 grid((unsigned)((N + kRows - 1) / kRows), (unsigned)(P.ntiles_n * P.g.groups), 1);
+  VBX_REQUIRE(grid.y <= 65535, VBX_UNSUPPORTED, "tc_conv1d_fwd: too many channel tiles");
+  tc_conv_fwd_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(P);
+  return launched("tc_conv_fwd_kernel");
+}

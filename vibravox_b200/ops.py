@@ -118,6 +118,30 @@ def conv1d_dgrad_scatter(dy: Tensor, wk: Tensor, g: ConvGeom, Tin: int, dx: Opti
     return dx
 
 
+def tc_pack_fwd(w: Tensor, g: ConvGeom) -> Tensor:
+    """bf16 hi/lo K-major weight tiles for tc_conv1d_fwd (geometry-only descriptor: B, Tin irrelevant)."""
+    d = g.desc(1, max(g.dil * (g.K - 1) + 1 - 2 * g.pad, g.refl + 1, 1))
+    nbytes = _lib.load().vbx_tc_fwd_pack_bytes(ctypes.byref(d))
+    if nbytes <= 0:
+        raise _lib.VbxError("vbx_tc_fwd_pack_bytes: " + _lib.load().vbx_last_error().decode())
+    packed = torch.empty((nbytes,), device=w.device, dtype=torch.uint8)
+    check(_lib.load().vbx_tc_pack_fwd(ctypes.byref(d), _p(w), packed.data_ptr(), _stream()), "vbx_tc_pack_fwd")
+    return packed
+
+
+def tc_conv1d_fwd(x: Tensor, packed: Tensor, g: ConvGeom, bias: Optional[Tensor] = None,
+                  res: Optional[Tensor] = None, slope: float = 1.0, want_mask: bool = False):
+    B, Cin, Tin = x.shape
+    assert Cin == g.Cin
+    d = g.desc(B, Tin)
+    y = torch.empty((B, g.Cout, d.Tout), device=x.device, dtype=torch.float32)
+    mask = torch.empty(y.shape, device=x.device, dtype=torch.uint8) if want_mask else None
+    e = _epi(bias, res, mask, slope, 0.0)
+    check(_lib.load().vbx_tc_conv1d_fwd(ctypes.byref(d), _p(x), packed.data_ptr(), ctypes.byref(e), _p(y), _stream()),
+          "vbx_tc_conv1d_fwd")
+    return (y, mask) if want_mask else y
+
+
 def transpose_weight(w: Tensor, groups: int) -> Tensor:
     Cout, Cin_g, K = w.shape
     wt = torch.empty_like(w)
