@@ -77,10 +77,14 @@ VBX_API int vbx_conv1d_dgrad_scatter(const vbx_conv_desc* d, const float* dy, co
 /* ---- tensor-core (tcgen05 / TMEM) variants of the same contractions, bf16x3 split operands, fp32
  * accumulate.  Weights are pre-packed once per weight update into K-major bf16 hi/lo tiles
  * (vbx_tc_*_pack_bytes gives the buffer size, -1 on a bad descriptor); activations stay fp32 (B,C,T). */
-VBX_API int64_t vbx_tc_fwd_pack_bytes(const vbx_conv_desc* d);
-VBX_API int vbx_tc_pack_fwd(const vbx_conv_desc* d, const float* w, void* packed, void* stream);
+/* mode 0 = forward pack (columns = output channels), 1 = dgrad pack (columns = input channels, one
+ * tile set per stride phase).  w is the plain W[co][ci_g][k]. */
+VBX_API int64_t vbx_tc_pack_bytes(const vbx_conv_desc* d, int32_t mode);
+VBX_API int vbx_tc_pack(const vbx_conv_desc* d, int32_t mode, const float* w, void* packed, void* stream);
 VBX_API int vbx_tc_conv1d_fwd(const vbx_conv_desc* d, const float* x, const void* packed, const vbx_epilogue* e,
                       float* y, void* stream);
+VBX_API int vbx_tc_conv1d_dgrad(const vbx_conv_desc* d, const float* dy, const void* packed, const vbx_epilogue* e,
+                        float* dx, void* stream);
 /* W[co][ci_g][k] -> Wt[g][ci_g][co_g][k]  (layout for vbx_conv1d_dgrad) */
 VBX_API int vbx_transpose_weight(const float* w, float* wt, int32_t Cout, int32_t Cin_g, int32_t K,
                          int32_t groups, void* stream);

@@ -18,6 +18,11 @@ CASES = [
     (2, 24, 48, 131, 7, 2, 2, 3, 0, 4),
     (32, 1024, 1024, 748, 41, 4, 1, 20, 0, 4),
     (32, 32, 32, 11968, 3, 1, 3, 3, 3, 1),
+    (2, 16, 32, 257, 16, 8, 1, 7, 7, 1),
+    (2, 24, 48, 131, 7, 2, 3, 3, 0, 4),
+    (2, 128, 256, 64, 16, 8, 1, 4, 0, 1),
+    (32, 256, 1024, 2990, 41, 4, 1, 20, 0, 4),
+    (32, 1024, 1024, 187, 5, 1, 1, 2, 0, 1),
 ]
 which = [int(a) for a in sys.argv[1:]] or range(len(CASES))
 for i in which:
@@ -27,7 +32,7 @@ for i in which:
     w = torch.randn(Cout, Cin // groups, K, device=dev) / (Cin // groups * K) ** 0.5
     bias = torch.randn(Cout, device=dev)
     ref = ops.conv1d_fwd(x, w, g, bias=bias, slope=0.2)
-    packed = ops.tc_pack_fwd(w, g)
+    packed = ops.tc_pack(w, g, 0)
     y = ops.tc_conv1d_fwd(x, packed, g, bias=bias, slope=0.2)
     torch.cuda.synchronize()
     err = float((y - ref).abs().max()), float((y - ref).norm() / ref.norm())
@@ -42,4 +47,16 @@ for i in which:
     t_simt = tm(lambda: ops.conv1d_fwd(x, w, g, bias=bias, slope=0.2))
     flops = 2.0 * B * g.tout(Tin) * Cout * (Cin // groups) * K
     print(f"case {i} {CASES[i]}: max abs {err[0]:.2e} rel-L2 {err[1]:.2e} | tc {t_tc:.3f} ms ({flops/t_tc/1e9:.1f} TF) simt {t_simt:.3f} ms ({flops/t_simt/1e9:.1f} TF)", flush=True)
+    # dgrad
+    dyv = torch.randn_like(ref)
+    wt = ops.transpose_weight(w, groups)
+    r2 = torch.randn(B, Cin, Tin, device=dev)
+    dref = ops.conv1d_dgrad(dyv, wt, g, Tin, res=r2, slope=0.5)
+    pk = ops.tc_pack(w, g, 1)
+    dgot = ops.tc_conv1d_dgrad(dyv, pk, g, Tin, res=r2, slope=0.5)
+    torch.cuda.synchronize()
+    derr = float((dgot - dref).abs().max()), float((dgot - dref).norm() / dref.norm())
+    t_dtc = tm(lambda: ops.tc_conv1d_dgrad(dyv, pk, g, Tin))
+    t_dsimt = tm(lambda: ops.conv1d_dgrad(dyv, wt, g, Tin))
+    print(f"   dgrad: max abs {derr[0]:.2e} rel-L2 {derr[1]:.2e} | tc {t_dtc:.3f} ms ({flops/t_dtc/1e9:.1f} TF) simt {t_dsimt:.3f} ms ({flops/t_dsimt/1e9:.1f} TF)")
 print("done")

@@ -86,11 +86,11 @@ VBX_HD DgradPhase dgrad_phase(const GemmP& P, int ph) {
 struct DgradImg {
   int k0, kstep, ntaps, tstep, kd0_hi, phase;
 };
-// image 0: p = u ; image 1: p = -u (left mirror) ; image 2: p = 2(Tin-1)-u (right mirror)
-VBX_HD DgradImg dgrad_img(const GemmP& P, int r, int img) {
+// taps k = k0 + j*kstep (j < ntaps) are the ones with (k*dil) % stride == phase; for those
+// (p + pad - k*dil)/stride = (p + pad)/stride - kd0_hi - j*tstep.
+VBX_HD DgradImg dgrad_taps(const GemmP& P, int phase) {
   DgradImg I;
-  int p0 = img == 0 ? r : (img == 1 ? -r : 2 * (P.Tin - 1) - r);
-  I.phase = mod_pos(p0 + P.pad, P.stride);
+  I.phase = phase;
   int g = gcd_i(P.dil, P.stride);
   I.kstep = P.stride / g;
   I.tstep = P.dil / g;
@@ -100,6 +100,25 @@ VBX_HD DgradImg dgrad_img(const GemmP& P, int r, int img) {
   I.ntaps = I.k0 < 0 ? 0 : (P.K - 1 - I.k0) / I.kstep + 1;
   I.kd0_hi = I.k0 < 0 ? 0 : (I.k0 * P.dil) / P.stride;
   return I;
+}
+// image 0: p = u ; image 1: p = -u (left mirror) ; image 2: p = 2(Tin-1)-u (right mirror)
+VBX_HD DgradImg dgrad_img(const GemmP& P, int r, int img) {
+  int p0 = img == 0 ? r : (img == 1 ? -r : 2 * (P.Tin - 1) - r);
+  return dgrad_taps(P, mod_pos(p0 + P.pad, P.stride));
+}
+// does a tile of `tile` consecutive columns starting at n_lo of phase `ph` touch mirror image `img`?
+VBX_HD bool dgrad_tile_needs_img(const GemmP& P, int ph, int n_lo, int tile, int img) {
+  if (img == 0) return true;
+  if (P.refl == 0) return false;
+  DgradPhase d = dgrad_phase(P, ph);
+  int N = P.B * d.Up;
+  int n_hi = n_lo + tile - 1;
+  if (n_lo >= N) return false;
+  if (n_hi >= N) n_hi = N - 1;
+  if (n_lo / d.Up != n_hi / d.Up) return true;
+  int u_lo = d.r + (n_lo % d.Up) * P.stride, u_hi = d.r + (n_hi % d.Up) * P.stride;
+  if (img == 1) return u_lo <= P.refl && u_hi >= 1;
+  return u_hi >= P.Tin - 1 - P.refl && u_lo <= P.Tin - 2;
 }
 
 template <int TM_, int TN_, int RM_, int RN_>
@@ -228,17 +247,7 @@ struct Tile {
 
   // DGRAD only: does this block need mirror image `img` (uniform across the block)?
   static VBX_HD bool dgrad_need_img(const GemmP& P, Blk blk, int img) {
-    if (img == 0) return true;
-    if (P.refl == 0) return false;
-    DgradPhase ph = dgrad_phase(P, blk.z);
-    int N = P.B * ph.Up;
-    int n_lo = blk.x * TN, n_hi = n_lo + TN - 1;
-    if (n_lo >= N) return false;
-    if (n_hi >= N) n_hi = N - 1;
-    if (n_lo / ph.Up != n_hi / ph.Up) return true;
-    int u_lo = ph.r + (n_lo % ph.Up) * P.stride, u_hi = ph.r + (n_hi % ph.Up) * P.stride;
-    if (img == 1) return u_lo <= P.refl && u_hi >= 1;
-    return u_hi >= P.Tin - 1 - P.refl && u_lo <= P.Tin - 2;
+    return dgrad_tile_needs_img(P, blk.z, blk.x * TN, TN, img);
   }
 
   // DGRAD only: set up the loaders for one mirror image; returns the reduction length

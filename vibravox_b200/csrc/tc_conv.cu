@@ -37,18 +37,23 @@ struct TcP {
   GemmP g;
   const unsigned char* packed;
   int NT, ntiles_n, nchunks, tmem_cols, stages;
+  int nphase;       // DGRAD: packed tiles are indexed [g][nt][phase][chunk], nchunks = chunks per phase
+};
+
+// one reduction segment of a tile: FWD has one; DGRAD has one per mirror image it touches
+struct Seg {
+  int nchunks, phase, img;
+  int k0, kstep, ntaps, tstep, kd0_hi;
 };
 
 __host__ __device__ inline int plane_b(int NT) { return NT * 64; }                 // NT rows x 32 bf16
 __host__ __device__ inline int stage_bytes(int NT) { return 2 * kPlaneA + 2 * plane_b(NT); }
 
-inline int pick_nt(int Cout_g) {
-  int r = (Cout_g + 15) / 16 * 16;
+inline int pick_nt(int Cn) {
+  int r = (Cn + 15) / 16 * 16;
   if (r <= 256) return r;
-  // split evenly into tiles of <= 256 columns
-  int tiles = (r + 255) / 256;
-  int nt = ((r + tiles - 1) / tiles + 15) / 16 * 16;
-  return nt;
+  int tiles = (r + 255) / 256;                      // split evenly into tiles of <= 256 columns
+  return ((r + tiles - 1) / tiles + 15) / 16 * 16;
 }
 inline int pow2_cols(int n) { int c = 32; while (c < n) c <<= 1; return c; }
 inline int pick_stages(int NT) {
@@ -65,7 +70,10 @@ __device__ __forceinline__ float finish(const GemmP& P, float v, int ch, long lo
   return v;
 }
 
-__global__ void __launch_bounds__(kThreads, 2) tc_conv_fwd_kernel(const TcP P) {
+// MODE FWD  : rows (b,t),  cols co, reduction (ci,k):  A = x[b,ci,map(t*s + k*d - pad)]
+// MODE DGRAD: rows (b,u) of one phase, cols ci, reduction (co,j): A = dy[b,co,(u+pad-k*d)/s]
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const TcP P) {
   extern __shared__ __align__(128) unsigned char smem[];
   const GemmP& G = P.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -78,10 +86,22 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_fwd_kernel(const TcP P) {
   uint64_t* empty = bars + 2 * S;
   uint64_t* acc_full = bars + 3 * S;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 1);
+  Seg* segs = reinterpret_cast<Seg*>(tmem_slot + 2);
+  int* nseg_p = reinterpret_cast<int*>(segs + 3);
 
   const int grp = blockIdx.y / P.ntiles_n, nt = blockIdx.y % P.ntiles_n;
   const int row_base = blockIdx.x * kRows;
-  const int N = G.B * G.Tout;
+  const int Cred = MODE == FWD ? G.Cin_g : G.Cout_g;     // channels walked by the reduction
+  const int Ccol = MODE == FWD ? G.Cout_g : G.Cin_g;     // channels along the MMA N dimension
+  DgradPhase dp{0, 0};
+  int N;
+  if (MODE == FWD) {
+    N = G.B * G.Tout;
+  } else {
+    dp = dgrad_phase(G, blockIdx.z);
+    N = G.B * dp.Up;
+  }
+  if (row_base >= N) return;                             // uniform (DGRAD phases differ in length)
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
@@ -91,73 +111,123 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_fwd_kernel(const TcP P) {
     }
     mbar_init(acc_full, 1);
     fence_barrier_init();
+    int ns = 0;
+    if (MODE == FWD) {
+      segs[0] = Seg{P.nchunks, 0, 0, 0, 1, G.K, 0, 0};
+      ns = 1;
+    } else {
+      for (int img = 0; img < 3; ++img) {
+        if (!dgrad_tile_needs_img(G, blockIdx.z, row_base, kRows, img)) continue;
+        DgradImg im = dgrad_img(G, dp.r, img);
+        const int nch = (G.Cout_g * im.ntaps + kKC - 1) / kKC;
+        if (nch == 0) continue;
+        segs[ns++] = Seg{nch, im.phase, img, im.k0, im.kstep, im.ntaps, im.tstep, im.kd0_hi};
+      }
+    }
+    *nseg_p = ns;
   }
   if (warp == 8) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int nseg = *nseg_p;
 
   if (warp < 8) {
     // ===================== A producers: im2col gather -> bf16 hi/lo -> MN-major smem =====================
     const int row = tid & 127, kh = tid >> 7;
     const int n = row_base + row;
-    const bool valid = n < N;
-    const int b = valid ? n / G.Tout : 0, t = valid ? n % G.Tout : 0;
-    const float* xrow = G.X + ((long long)b * G.Cin + grp * G.Cin_g) * G.Tin;
-    const int tpos = t * G.stride - G.pad;
-    int ci = (kh * 16) / G.K, k = (kh * 16) % G.K;
+    const bool in_range = n < N;
     const uint32_t row_off = (uint32_t)(row >> 3) * kSboA + (uint32_t)(row & 7) * 2;
-    for (int c = 0; c < P.nchunks; ++c) {
-      const int s = c % S, use = c / S;
-      mbar_wait(&empty[s], (use & 1) ^ 1);
-      unsigned char* a_hi = stage0 + (size_t)s * stage_sz;
-      unsigned char* a_lo = a_hi + kPlaneA;
-      float v[16];
+    int c = 0;                                           // global chunk counter (pipeline position)
+    for (int sg = 0; sg < nseg; ++sg) {
+      const Seg seg = segs[sg];
+      bool valid = in_range;
+      const float* src = G.X;
+      int base = 0;                                      // FWD: t*s - pad ; DGRAD: T0
+      const int Kmod = MODE == FWD ? G.K : seg.ntaps;    // taps per reduction channel
+      if (MODE == FWD) {
+        const int b = valid ? n / G.Tout : 0, t = valid ? n % G.Tout : 0;
+        src += ((long long)b * G.Cin + grp * G.Cin_g) * G.Tin;
+        base = t * G.stride - G.pad;
+      } else {
+        const int b = valid ? n / dp.Up : 0, u = dp.r + (valid ? n % dp.Up : 0) * G.stride;
+        int p = u;
+        if (seg.img == 1) { p = -u; if (u < 1 || u > G.refl) valid = false; }
+        else if (seg.img == 2) { p = 2 * (G.Tin - 1) - u; if (u > G.Tin - 2 || u < G.Tin - 1 - G.refl) valid = false; }
+        src += ((long long)b * G.Cout + grp * G.Cout_g) * G.Tout;
+        base = (p + G.pad) / G.stride - seg.kd0_hi;      // p + pad >= 0 because refl <= pad
+      }
+      int ch = (kh * 16) / Kmod, k = (kh * 16) % Kmod;
+      for (int cs = 0; cs < seg.nchunks; ++cs, ++c) {
+        const int s = c % S, use = c / S;
+        mbar_wait(&empty[s], (use & 1) ^ 1);
+        unsigned char* a_hi = stage0 + (size_t)s * stage_sz;
+        unsigned char* a_lo = a_hi + kPlaneA;
+        float v[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float x = 0.f;
-        if (valid && ci < G.Cin_g) {
-          int p = map_pos(tpos + k * G.dil, G.Tin, G.refl);
-          if (p >= 0) x = xrow[(long long)ci * G.Tin + p];
+        for (int i = 0; i < 16; ++i) {
+          float x = 0.f;
+          if (valid && ch < Cred) {
+            if (MODE == FWD) {
+              int p = map_pos(base + k * G.dil, G.Tin, G.refl);
+              if (p >= 0) x = src[(long long)ch * G.Tin + p];
+            } else {
+              int t = base - k * seg.tstep;
+              if (t >= 0 && t < G.Tout) x = src[(long long)ch * G.Tout + t];
+            }
+          }
+          v[i] = x;
+          if (++k == Kmod) { k = 0; ++ch; }
         }
-        v[i] = x;
-        if (++k == G.K) { k = 0; ++ci; }
-      }
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int kk = kh * 16 + i;
-        const uint32_t off = row_off + (uint32_t)(kk >> 3) * kLboA + (uint32_t)(kk & 7) * 16;
-        __nv_bfloat16 hi, lo;
-        split_bf16(v[i], hi, lo);
-        *reinterpret_cast<__nv_bfloat16*>(a_hi + off) = hi;
-        *reinterpret_cast<__nv_bfloat16*>(a_lo + off) = lo;
+        for (int i = 0; i < 16; ++i) {
+          const int kk = kh * 16 + i;
+          const uint32_t off = row_off + (uint32_t)(kk >> 3) * kLboA + (uint32_t)(kk & 7) * 16;
+          __nv_bfloat16 hi, lo;
+          split_bf16(v[i], hi, lo);
+          *reinterpret_cast<__nv_bfloat16*>(a_hi + off) = hi;
+          *reinterpret_cast<__nv_bfloat16*>(a_lo + off) = lo;
+        }
+        k += 16;
+        if (k >= Kmod) { ch += k / Kmod; k %= Kmod; }
+        fence_proxy_async();
+        mbar_arrive(&full_a[s]);
       }
-      k += 16;
-      if (k >= G.K) { ci += k / G.K; k %= G.K; }
-      fence_proxy_async();
-      mbar_arrive(&full_a[s]);
     }
     // ===================== epilogue: TMEM -> registers -> fused output stage -> (B,C,T) =====================
     mbar_wait(acc_full, 0);
     tc_fence_after();
     const int q = warp & 3, half = warp >> 2;
-    const int erow = q * 32 + lane;
-    const int en = row_base + erow;
+    const int en = row_base + q * 32 + lane;
     const bool ev = en < N;
-    const int eb = ev ? en / G.Tout : 0, et = ev ? en % G.Tout : 0;
+    long long out_base;                                  // index of (b, first channel of the group, position)
+    int Tlen, Ctot;
+    if (MODE == FWD) {
+      const int eb = ev ? en / G.Tout : 0, et = ev ? en % G.Tout : 0;
+      Tlen = G.Tout; Ctot = G.Cout;
+      out_base = ((long long)eb * Ctot + grp * Ccol) * Tlen + et;
+    } else {
+      const int eb = ev ? en / dp.Up : 0, eu = dp.r + (ev ? en % dp.Up : 0) * G.stride;
+      Tlen = G.Tin; Ctot = G.Cin;
+      out_base = ((long long)eb * Ctot + grp * Ccol) * Tlen + eu;
+    }
     const int nblk = NT / 16;
     const int blk_lo = half == 0 ? 0 : (nblk + 1) / 2, blk_hi = half == 0 ? (nblk + 1) / 2 : nblk;
     for (int blk = blk_lo; blk < blk_hi; ++blk) {
       float acc[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * 16), acc);
+      if (nseg > 0) {
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * 16), acc);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+      }
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int col = nt * NT + blk * 16 + j;
-        if (ev && col < G.Cout_g) {
-          const int ch = grp * G.Cout_g + col;
-          const long long idx = ((long long)eb * G.Cout + ch) * G.Tout + et;
-          G.Y[idx] = finish(G, acc[j], ch, idx);
+        if (ev && col < Ccol) {
+          const long long idx = out_base + (long long)col * Tlen;
+          G.Y[idx] = finish(G, acc[j], grp * Ccol + col, idx);
         }
       }
     }
@@ -167,38 +237,48 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_fwd_kernel(const TcP P) {
       const uint32_t idesc = make_idesc_bf16(NT, /*a_mn=*/true, /*b_mn=*/false);
       const uint32_t lbo_b = (uint32_t)NT * 16;
       uint32_t accumulate = 0;
-      for (int c = 0; c < P.nchunks; ++c) {
-        const int s = c % S, use = c / S;
-        mbar_wait(&full_a[s], use & 1);
-        mbar_wait(&full_b[s], use & 1);
-        tc_fence_after();
-        const uint32_t a_hi = smem_u32(stage0 + (size_t)s * stage_sz), a_lo = a_hi + kPlaneA;
-        const uint32_t b_hi = a_hi + 2 * kPlaneA, b_lo = b_hi + plane_b(NT);
+      int c = 0;
+      for (int sg = 0; sg < nseg; ++sg) {
+        const int nch = segs[sg].nchunks;
+        for (int cs = 0; cs < nch; ++cs, ++c) {
+          const int s = c % S, use = c / S;
+          mbar_wait(&full_a[s], use & 1);
+          mbar_wait(&full_b[s], use & 1);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(stage0 + (size_t)s * stage_sz), a_lo = a_hi + kPlaneA;
+          const uint32_t b_hi = a_hi + 2 * kPlaneA, b_lo = b_hi + plane_b(NT);
 #pragma unroll
-        for (int ks = 0; ks < kKC / 16; ++ks) {
-          const uint64_t da_hi = make_desc(a_hi + ks * 2 * kLboA, kLboA, kSboA);
-          const uint64_t da_lo = make_desc(a_lo + ks * 2 * kLboA, kLboA, kSboA);
-          const uint64_t db_hi = make_desc(b_hi + ks * 2 * lbo_b, lbo_b, 128);
-          const uint64_t db_lo = make_desc(b_lo + ks * 2 * lbo_b, lbo_b, 128);
-          mma_bf16_ss(tmem_base, da_hi, db_hi, idesc, accumulate);
-          accumulate = 1;
-          mma_bf16_ss(tmem_base, da_hi, db_lo, idesc, 1);
-          mma_bf16_ss(tmem_base, da_lo, db_hi, idesc, 1);
+          for (int ks = 0; ks < kKC / 16; ++ks) {
+            const uint64_t da_hi = make_desc(a_hi + ks * 2 * kLboA, kLboA, kSboA);
+            const uint64_t da_lo = make_desc(a_lo + ks * 2 * kLboA, kLboA, kSboA);
+            const uint64_t db_hi = make_desc(b_hi + ks * 2 * lbo_b, lbo_b, 128);
+            const uint64_t db_lo = make_desc(b_lo + ks * 2 * lbo_b, lbo_b, 128);
+            mma_bf16_ss(tmem_base, da_hi, db_hi, idesc, accumulate);
+            accumulate = 1;
+            mma_bf16_ss(tmem_base, da_hi, db_lo, idesc, 1);
+            mma_bf16_ss(tmem_base, da_lo, db_hi, idesc, 1);
+          }
+          mma_commit(&empty[s]);       // frees the stage once these MMAs have read it
         }
-        mma_commit(&empty[s]);       // frees the stage once these MMAs have read it
       }
-      mma_commit(acc_full);
+      if (nseg > 0) mma_commit(acc_full);
+      else mbar_arrive(acc_full);
     }
   } else {
     // ===================== weight tiles: linear bulk copies (TMA engine) =====================
     if (lane == 0) {
       const uint32_t bytes = 2u * (uint32_t)plane_b(NT);
-      const unsigned char* src = P.packed + ((size_t)(grp * P.ntiles_n + nt) * P.nchunks) * bytes;
-      for (int c = 0; c < P.nchunks; ++c) {
-        const int s = c % S, use = c / S;
-        mbar_wait(&empty[s], (use & 1) ^ 1);
-        mbar_expect_tx(&full_b[s], bytes);
-        bulk_copy_g2s(stage0 + (size_t)s * stage_sz + 2 * kPlaneA, src + (size_t)c * bytes, bytes, &full_b[s]);
+      int c = 0;
+      for (int sg = 0; sg < nseg; ++sg) {
+        const Seg seg = segs[sg];
+        const unsigned char* src =
+            P.packed + (((size_t)(grp * P.ntiles_n + nt) * P.nphase + seg.phase) * P.nchunks) * bytes;
+        for (int cs = 0; cs < seg.nchunks; ++cs, ++c) {
+          const int s = c % S, use = c / S;
+          mbar_wait(&empty[s], (use & 1) ^ 1);
+          mbar_expect_tx(&full_b[s], bytes);
+          bulk_copy_g2s(stage0 + (size_t)s * stage_sz + 2 * kPlaneA, src + (size_t)cs * bytes, bytes, &full_b[s]);
+        }
       }
     }
   }
@@ -207,45 +287,102 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_fwd_kernel(const TcP P) {
   if (warp == 8) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
 }
 
-// one thread per 16-byte unit (8 consecutive reduction elements of one output channel)
-__global__ void tc_pack_fwd_kernel(const float* __restrict__ w, unsigned char* __restrict__ out, int Cout_g,
-                                   int Kred, int groups, int NT, int ntiles_n, int nchunks) {
-  const long long units = (long long)groups * ntiles_n * nchunks * 4 * NT;
+// Weight pre-pack: one thread per 16-byte unit (8 consecutive reduction elements of one column).
+// FWD  : column = co, reduction kk = (ci,k)          -> W[co][kk]
+// DGRAD: column = ci, reduction kk = (co,j) of phase -> W[co][ci][k0 + j*kstep]
+template <int MODE>
+__global__ void tc_pack_kernel(const float* __restrict__ w, unsigned char* __restrict__ out, const TcP P) {
+  const GemmP& G = P.g;
+  const int NT = P.NT;
+  const int Ccol = MODE == FWD ? G.Cout_g : G.Cin_g;
+  const long long units = (long long)G.groups * P.ntiles_n * P.nphase * P.nchunks * 4 * NT;
   for (long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x; u < units;
        u += (long long)gridDim.x * blockDim.x) {
     int n = (int)(u % NT);
     long long r = u / NT;
     int ku = (int)(r % 4); r /= 4;
-    int c = (int)(r % nchunks); r /= nchunks;
-    int nt = (int)(r % ntiles_n);
-    int g = (int)(r / ntiles_n);
-    const int co = nt * NT + n;
+    int c = (int)(r % P.nchunks); r /= P.nchunks;
+    int ph = (int)(r % P.nphase); r /= P.nphase;
+    int nt = (int)(r % P.ntiles_n);
+    int g = (int)(r / P.ntiles_n);
+    const int col = nt * NT + n;
     const int kk0 = c * kKC + ku * 8;
+    DgradImg im = dgrad_taps(G, MODE == FWD ? 0 : ph);
     __align__(16) __nv_bfloat16 hi[8], lo[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float v = 0.f;
-      if (co < Cout_g && kk0 + j < Kred) v = w[((long long)g * Cout_g + co) * Kred + kk0 + j];
+      const int kk = kk0 + j;
+      if (col < Ccol) {
+        if (MODE == FWD) {
+          if (kk < G.Cin_g * G.K) v = w[((long long)g * G.Cout_g + col) * G.Cin_g * G.K + kk];
+        } else if (im.ntaps > 0) {
+          const int co = kk / im.ntaps, jj = kk % im.ntaps;
+          if (co < G.Cout_g)
+            v = w[(((long long)g * G.Cout_g + co) * G.Cin_g + col) * G.K + im.k0 + jj * im.kstep];
+        }
+      }
       split_bf16(v, hi[j], lo[j]);
     }
-    unsigned char* base = out + ((size_t)((g * ntiles_n + nt) * (long long)nchunks + c)) * 2 * plane_b(NT);
+    unsigned char* base =
+        out + ((((size_t)(g * P.ntiles_n + nt) * P.nphase + ph) * P.nchunks + c)) * 2 * plane_b(NT);
     const size_t off = ((size_t)ku * NT + n) * 16;
     *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<const uint4*>(hi);
     *reinterpret_cast<uint4*>(base + plane_b(NT) + off) = *reinterpret_cast<const uint4*>(lo);
   }
 }
 
-static int fill_tc(TcP& P, const vbx_conv_desc* d) {
+static int fill_tc(TcP& P, const vbx_conv_desc* d, int mode) {
   int code = 0;
   const char* msg = check_desc_msg(d, &code);
   if (msg) return fail(code, msg);
   fill(P.g, d);
-  P.NT = pick_nt(P.g.Cout_g);
-  P.ntiles_n = (P.g.Cout_g + P.NT - 1) / P.NT;
-  P.nchunks = (P.g.Cin_g * P.g.K + kKC - 1) / kKC;
+  const int Ccol = mode == FWD ? P.g.Cout_g : P.g.Cin_g;
+  P.NT = pick_nt(Ccol);
+  P.ntiles_n = (Ccol + P.NT - 1) / P.NT;
+  if (mode == FWD) {
+    P.nphase = 1;
+    P.nchunks = (P.g.Cin_g * P.g.K + kKC - 1) / kKC;
+  } else {
+    P.nphase = P.g.stride;
+    int g = gcd_i(P.g.dil, P.g.stride);
+    int kstep = P.g.stride / g;
+    int max_taps = (P.g.K + kstep - 1) / kstep;
+    P.nchunks = (P.g.Cout_g * max_taps + kKC - 1) / kKC;
+  }
   P.tmem_cols = pow2_cols(P.NT);
   P.stages = pick_stages(P.NT);
   return 0;
+}
+
+static size_t smem_bytes(const TcP& P) {
+  return (size_t)P.stages * stage_bytes(P.NT) + (3 * P.stages + 1) * sizeof(uint64_t) + 16 + 3 * sizeof(Seg) + 16;
+}
+
+template <int MODE>
+static int launch_tc(const TcP& P, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t ce = cudaFuncSetAttribute(tc_conv_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (ce != cudaSuccess) return fail((int)ce, "tc_conv: cannot raise the dynamic shared memory limit");
+    attr_set = true;
+  }
+  long long rows = MODE == FWD ? (long long)P.g.B * P.g.Tout
+                               : (long long)P.g.B * ((P.g.Tin + P.g.stride - 1) / P.g.stride);
+  dim3 grid((unsigned)((rows + kRows - 1) / kRows), (unsigned)(P.ntiles_n * P.g.groups),
+            (unsigned)(MODE == FWD ? 1 : P.g.stride));
+  if (grid.y > 65535 || grid.z > 65535) return fail(VBX_UNSUPPORTED, "tc_conv: grid too large");
+  tc_conv_kernel<MODE><<<grid, kThreads, smem_bytes(P), st>>>(P);
+  return launched("tc_conv_kernel");
+}
+
+template <int MODE>
+static int pack_tc(const TcP& P, const float* w, void* packed, cudaStream_t st) {
+  long long units = (long long)P.g.groups * P.ntiles_n * P.nphase * P.nchunks * 4 * P.NT;
+  int blocks = (int)((units + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  tc_pack_kernel<MODE><<<blocks, 256, 0, st>>>(w, (unsigned char*)packed, P);
+  return launched("tc_pack_kernel");
 }
 
 }  // namespace tc
@@ -254,45 +391,47 @@ static int fill_tc(TcP& P, const vbx_conv_desc* d) {
 using namespace vbx;
 using namespace vbx::tc;
 
-extern "C" int64_t vbx_tc_fwd_pack_bytes(const vbx_conv_desc* d) {
-  TcP P;
-  if (fill_tc(P, d)) return -1;
-  return (int64_t)P.g.groups * P.ntiles_n * P.nchunks * 2 * plane_b(P.NT);
+static int64_t pack_bytes(const TcP& P) {
+  return (int64_t)P.g.groups * P.ntiles_n * P.nphase * P.nchunks * 2 * plane_b(P.NT);
 }
 
-extern "C" int vbx_tc_pack_fwd(const vbx_conv_desc* d, const float* w, void* packed, void* stream) {
+extern "C" int64_t vbx_tc_pack_bytes(const vbx_conv_desc* d, int32_t mode) {
   TcP P;
-  if (int r = fill_tc(P, d)) return r;
-  VBX_REQUIRE(w && packed, VBX_BAD_POINTER, "tc_pack_fwd: null tensor");
-  VBX_REQUIRE(((uintptr_t)packed & 15) == 0, VBX_BAD_POINTER, "tc_pack_fwd: packed buffer must be 16-byte aligned");
-  long long units = (long long)P.g.groups * P.ntiles_n * P.nchunks * 4 * P.NT;
-  int blocks = (int)((units + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  tc_pack_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (unsigned char*)packed, P.g.Cout_g,
-                                                               P.g.Cin_g * P.g.K, P.g.groups, P.NT, P.ntiles_n,
-                                                               P.nchunks);
-  return launched("tc_pack_fwd_kernel");
+  if (mode != FWD && mode != DGRAD) return -1;
+  if (fill_tc(P, d, mode)) return -1;
+  return pack_bytes(P);
+}
+
+extern "C" int vbx_tc_pack(const vbx_conv_desc* d, int32_t mode, const float* w, void* packed, void* stream) {
+  TcP P;
+  VBX_REQUIRE(mode == FWD || mode == DGRAD, VBX_UNSUPPORTED, "tc_pack: mode must be 0 (fwd) or 1 (dgrad)");
+  if (int r = fill_tc(P, d, mode)) return r;
+  VBX_REQUIRE(w && packed, VBX_BAD_POINTER, "tc_pack: null tensor");
+  VBX_REQUIRE(((uintptr_t)packed & 15) == 0, VBX_BAD_POINTER, "tc_pack: packed buffer must be 16-byte aligned");
+  return mode == FWD ? pack_tc<FWD>(P, w, packed, (cudaStream_t)stream)
+                     : pack_tc<DGRAD>(P, w, packed, (cudaStream_t)stream);
 }
 
 extern "C" int vbx_tc_conv1d_fwd(const vbx_conv_desc* d, const float* x, const void* packed,
                                  const vbx_epilogue* e, float* y, void* stream) {
   TcP P;
-  if (int r = fill_tc(P, d)) return r;
+  if (int r = fill_tc(P, d, FWD)) return r;
   VBX_REQUIRE(x && packed && y, VBX_BAD_POINTER, "tc_conv1d_fwd: null tensor");
   VBX_REQUIRE(((uintptr_t)packed & 15) == 0, VBX_BAD_POINTER, "tc_conv1d_fwd: packed weights must be 16-byte aligned");
   fill_epi(P.g, e);
   P.g.X = x; P.g.Y = y;
   P.packed = (const unsigned char*)packed;
-  const size_t smem = (size_t)P.stages * stage_bytes(P.NT) + (3 * P.stages + 1) * sizeof(uint64_t) + 16;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t ce = cudaFuncSetAttribute(tc_conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (ce != cudaSuccess) return fail((int)ce, "tc_conv1d_fwd: cannot raise dynamic shared memory limit");
-    attr_set = true;
-  }
-  const long long N = (long long)P.g.B * P.g.Tout;
-  dim3 grid((unsigned)((N + kRows - 1) / kRows), (unsigned)(P.ntiles_n * P.g.groups), 1);
-  VBX_REQUIRE(grid.y <= 65535, VBX_UNSUPPORTED, "tc_conv1d_fwd: too many channel tiles");
-  tc_conv_fwd_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(P);
-  return launched("tc_conv_fwd_kernel");
+  return launch_tc<FWD>(P, (cudaStream_t)stream);
+}
+
+extern "C" int vbx_tc_conv1d_dgrad(const vbx_conv_desc* d, const float* dy, const void* packed,
+                                   const vbx_epilogue* e, float* dx, void* stream) {
+  TcP P;
+  if (int r = fill_tc(P, d, DGRAD)) return r;
+  VBX_REQUIRE(dy && packed && dx, VBX_BAD_POINTER, "tc_conv1d_dgrad: null tensor");
+  VBX_REQUIRE(((uintptr_t)packed & 15) == 0, VBX_BAD_POINTER, "tc_conv1d_dgrad: packed weights must be 16-byte aligned");
+  fill_epi(P.g, e);
+  P.g.X = dy; P.g.Y = dx;
+  P.packed = (const unsigned char*)packed;
+  return launch_tc<DGRAD>(P, (cudaStream_t)stream);
 }

@@ -118,14 +118,20 @@ def conv1d_dgrad_scatter(dy: Tensor, wk: Tensor, g: ConvGeom, Tin: int, dx: Opti
     return dx
 
 
-def tc_pack_fwd(w: Tensor, g: ConvGeom) -> Tensor:
-    """bf16 hi/lo K-major weight tiles for tc_conv1d_fwd (geometry-only descriptor: B, Tin irrelevant)."""
-    d = g.desc(1, max(g.dil * (g.K - 1) + 1 - 2 * g.pad, g.refl + 1, 1))
-    nbytes = _lib.load().vbx_tc_fwd_pack_bytes(ctypes.byref(d))
+def _geom_only_desc(g: ConvGeom) -> ConvDesc:
+    """A valid descriptor for calls that depend on the geometry only (weight packing)."""
+    tin = max(g.dil * (g.K - 1) + 1 - 2 * g.pad, g.refl + 1, 1)
+    return g.desc(1, tin + (-(tin + 2 * g.pad - g.dil * (g.K - 1) - 1)) % g.stride)
+
+
+def tc_pack(w: Tensor, g: ConvGeom, mode: int) -> Tensor:
+    """bf16 hi/lo K-major weight tiles for the tensor-core kernels (mode 0 = fwd, 1 = dgrad)."""
+    d = _geom_only_desc(g)
+    nbytes = _lib.load().vbx_tc_pack_bytes(ctypes.byref(d), mode)
     if nbytes <= 0:
-        raise _lib.VbxError("vbx_tc_fwd_pack_bytes: " + _lib.load().vbx_last_error().decode())
+        raise _lib.VbxError("vbx_tc_pack_bytes: " + _lib.load().vbx_last_error().decode())
     packed = torch.empty((nbytes,), device=w.device, dtype=torch.uint8)
-    check(_lib.load().vbx_tc_pack_fwd(ctypes.byref(d), _p(w), packed.data_ptr(), _stream()), "vbx_tc_pack_fwd")
+    check(_lib.load().vbx_tc_pack(ctypes.byref(d), mode, _p(w), packed.data_ptr(), _stream()), "vbx_tc_pack")
     return packed
 
 
@@ -136,10 +142,26 @@ def tc_conv1d_fwd(x: Tensor, packed: Tensor, g: ConvGeom, bias: Optional[Tensor]
     d = g.desc(B, Tin)
     y = torch.empty((B, g.Cout, d.Tout), device=x.device, dtype=torch.float32)
     mask = torch.empty(y.shape, device=x.device, dtype=torch.uint8) if want_mask else None
+    if res is not None:
+        assert res.shape == y.shape
     e = _epi(bias, res, mask, slope, 0.0)
     check(_lib.load().vbx_tc_conv1d_fwd(ctypes.byref(d), _p(x), packed.data_ptr(), ctypes.byref(e), _p(y), _stream()),
           "vbx_tc_conv1d_fwd")
     return (y, mask) if want_mask else y
+
+
+def tc_conv1d_dgrad(dy: Tensor, packed: Tensor, g: ConvGeom, Tin: int, res: Optional[Tensor] = None,
+                    slope: float = 1.0) -> Tensor:
+    B, Cout, Tout = dy.shape
+    d = g.desc(B, Tin)
+    assert Cout == g.Cout and Tout == d.Tout, (dy.shape, g, Tin, d.Tout)
+    dx = torch.empty((B, g.Cin, Tin), device=dy.device, dtype=torch.float32)
+    if res is not None:
+        assert res.shape == dx.shape
+    e = _epi(None, res, None, slope, 0.0)
+    check(_lib.load().vbx_tc_conv1d_dgrad(ctypes.byref(d), _p(dy), packed.data_ptr(), ctypes.byref(e), _p(dx),
+                                          _stream()), "vbx_tc_conv1d_dgrad")
+    return dx
 
 
 def transpose_weight(w: Tensor, groups: int) -> Tensor:
