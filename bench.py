@@ -109,8 +109,9 @@ def layer_microbench(device, B, L):
     To = g.tout(T3)
     flops = 2.0 * B * To * 1024 * 256 * 41
     byt = 4.0 * (B * 1024 * T3 + B * 1024 * To + w.numel())
-    t = timeit(lambda: ops.conv1d_fwd(x, w, g, bias=bias, slope=0.2), reps=5, warm=2)
-    out.append({"kernel": "gemm_conv_kernel<FWD> melgan.4 (1024->1024,k41,s4,g4)", "bound": "tensor",
+    t = timeit(lambda: ops.conv_fwd(x, w, g, bias=bias, slope=0.2), reps=5, warm=2)
+    kname = "tc_conv_kernel<FWD> (tcgen05, bf16x3)" if ops.use_tc(g, "fwd") else "gemm_conv_kernel<FWD> (fp32 FMA)"
+    out.append({"kernel": kname + " melgan.4 (1024->1024,k41,s4,g4)", "bound": "tensor",
                 "achieved": flops / t / 1e12, "peak": tens, "unit": "TFLOP/s", "frac": flops / t / 1e12 / tens,
                 "ms": t * 1e3, "algorithmic_bytes": byt, "peak_source": src + " bf16 sustained", "traffic": None})
     # (b) generator residual unit convs at C=32, T=11968
@@ -122,10 +123,10 @@ def layer_microbench(device, B, L):
         g1 = ops.ConvGeom(C, C, 3, 1, 3, 3, 3, 1)
         g2 = ops.ConvGeom(C, C, 1, 1, 1, 0, 0, 1)
         byt = 4.0 * 2 * B * C * T
-        t1 = timeit(lambda: ops.conv1d_fwd(xg, w1, g1))
-        t2 = timeit(lambda: ops.conv1d_fwd(xg, w2, g2, res=xg, slope=0.01))
+        t1 = timeit(lambda: ops.conv_fwd(xg, w1, g1))
+        t2 = timeit(lambda: ops.conv_fwd(xg, w2, g2, res=xg, slope=0.01))
         for nm, tt, bb in (("dilated k3 d3", t1, byt), ("pointwise+lrelu+res", t2, byt * 1.5)):
-            out.append({"kernel": f"gemm_conv_kernel<FWD> residual {nm} C={C} T={T}", "bound": "hbm",
+            out.append({"kernel": f"conv fwd residual {nm} C={C} T={T}", "bound": "hbm",
                         "achieved": bb / tt / 1e9, "peak": hbm, "unit": "GB/s", "frac": bb / tt / 1e9 / hbm,
                         "ms": tt * 1e3, "algorithmic_bytes": bb, "peak_source": src + " copy", "traffic": None})
     return out
@@ -166,6 +167,13 @@ def run_ours(args):
         wall = time.perf_counter() - t0
         return parallel.max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev), wall
 
+    if args.profile:
+        step()
+        torch.cuda.synchronize()
+        t_dev, _ = timed(step, args.steps)
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": t_dev / args.steps * 1e3}))
+        return
     for _ in range(max(args.warmup, 3)):
         step()
     sampler = ClockSampler(local_rank)
@@ -199,12 +207,15 @@ def run_ours(args):
 
     if rank != 0:
         return
+    from vibravox_b200 import ops as _ops
+    dtype = ("fp32 storage; contractions on tcgen05 tensor cores with bf16x3 split operands, fp32 accumulate"
+             if _ops.TC_ENABLED else "fp32")
     kernels = layer_microbench(dev, B, L) if not args.no_micro else []
     roof = dict(kernels[0]) if kernels else None
     line = {
         "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
         "config": {"workload": f"EBEN BWE full train step (gen+disc+MR-STFT/FM/hinge, EMA balancing, 2x Adam) "
                                f"bs={B}x{args.seconds:g}s@16kHz per GPU (L={L} after cut_to_valid_length), "
                                f"m=4 n=32 p=2 q=4 min_channels=24, reference schedule",
@@ -270,8 +281,12 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=4)
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-micro", action="store_true")
+    ap.add_argument("--no-tc", action="store_true", help="fp32 FMA kernels everywhere (VBX_TC=0)")
+    ap.add_argument("--profile", action="store_true", help="1 warm-up + --steps steps only (for ncu)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.no_tc:
+        os.environ["VBX_TC"] = "0"
     if args.impl == "reference":
         run_reference(args)
     else:

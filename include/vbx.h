@@ -85,6 +85,8 @@ VBX_API int vbx_tc_conv1d_fwd(const vbx_conv_desc* d, const float* x, const void
                       float* y, void* stream);
 VBX_API int vbx_tc_conv1d_dgrad(const vbx_conv_desc* d, const float* dy, const void* packed, const vbx_epilogue* e,
                         float* dx, void* stream);
+/* dw += sum dy*x on tensor cores (both operands gathered from the fp32 activations; nothing packed) */
+VBX_API int vbx_tc_conv1d_wgrad(const vbx_conv_desc* d, const float* x, const float* dy, float* dw, void* stream);
 /* W[co][ci_g][k] -> Wt[g][ci_g][co_g][k]  (layout for vbx_conv1d_dgrad) */
 VBX_API int vbx_transpose_weight(const float* w, float* wt, int32_t Cout, int32_t Cin_g, int32_t K,
                          int32_t groups, void* stream);

@@ -261,6 +261,8 @@ _NAMES = [k for k, v in list(globals().items()) if callable(v) and not k.startsw
 @contextlib.contextmanager
 def cpu_ops():
     saved = {k: getattr(ops, k) for k in _NAMES}
+    saved["TC_ENABLED"] = ops.TC_ENABLED
+    ops.TC_ENABLED = False
     try:
         for k in _NAMES:
             setattr(ops, k, globals()[k])

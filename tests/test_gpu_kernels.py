@@ -261,3 +261,45 @@ def test_noise_mix_crop():
         mixed = body[b, 0] + noise[b, 0, s:s + Ls]
         assert torch.allclose(ob[b, 0].cpu(), mixed[o:o + length], atol=1e-6)
         assert torch.equal(oa[b, 0].cpu(), air[b, 0, o:o + length])
+
+
+TC_CASES = [
+    (1, 32, 32, 256, 1, 1, 1, 0, 0, 1), (2, 32, 32, 300, 3, 1, 9, 9, 9, 1), (2, 64, 256, 403, 41, 4, 1, 20, 0, 4),
+    (2, 1024, 1024, 60, 5, 1, 1, 2, 0, 1), (3, 768, 768, 50, 5, 1, 2, 2, 0, 4), (2, 32, 64, 301, 4, 2, 1, 1, 1, 1),
+    (2, 24, 48, 131, 7, 2, 2, 3, 0, 4), (2, 24, 48, 131, 7, 2, 3, 3, 0, 4), (2, 16, 32, 257, 16, 8, 1, 7, 7, 1),
+    (2, 128, 256, 64, 16, 8, 1, 4, 0, 1), (2, 2, 32, 100, 3, 1, 1, 1, 1, 1), (2, 256, 64, 62, 7, 1, 1, 3, 3, 1),
+    (5, 40, 24, 97, 5, 3, 2, 4, 2, 2),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=[str(c) for c in TC_CASES])
+def test_tensor_core_conv_family_matches_fp64(case):
+    """tcgen05 kernels (bf16x3 split operands, fp32 TMEM accumulate) vs torch fp64: forward with the fused
+    epilogue, dgrad (phases + reflect images), wgrad (split reduction).  Tolerance 1e-4 relative (contract);
+    measured ~3e-6 + 2.4e-9 per reduction element (accumulator rounding)."""
+    from vibravox_b200 import ops
+    B, Cin, Cout, Tin, K, s, d, pad, refl, groups = case
+    geom = ops.ConvGeom(Cin, Cout, K, s, d, pad, refl, groups)
+    torch.manual_seed(sum(case))
+    To = tout(Tin, K, s, d, pad)
+    x = torch.randn(B, Cin, Tin)
+    w = torch.randn(Cout, Cin // groups, K) / (Cin // groups * K) ** 0.5
+    bias, res = torch.randn(Cout), torch.randn(B, Cout, To)
+    x64, w64 = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    pre = F.conv1d(ref_padded(x64, pad, refl), w64, bias.double(), s, 0, d, groups)
+    want = F.leaky_relu(pre, 0.2) + res.double()
+    xc, wc, bc, rc = cuda(x, w, bias, res)
+    y, mask = ops.tc_conv1d_fwd(xc, ops.tc_pack(wc, geom, 0), geom, bias=bc, res=rc, slope=0.2, want_mask=True)
+    assert (y.cpu().double() - want).norm() / want.norm() < 1e-4
+    assert (y.cpu().double() - want).abs().max() < 2e-4 * float(want.abs().max())
+    assert (mask.cpu().bool() != (pre > 0)).float().mean() < 1e-3
+    dy = torch.randn(B, Cout, To)
+    plain = F.conv1d(ref_padded(x64, pad, refl), w64, None, s, 0, d, groups)
+    gx, gw = torch.autograd.grad(plain, (x64, w64), dy.double())
+    dyc = dy.to(DEV)
+    r2 = torch.randn(B, Cin, Tin)
+    dx = ops.tc_conv1d_dgrad(dyc, ops.tc_pack(wc, geom, 1), geom, Tin, res=r2.to(DEV))
+    assert (dx.cpu().double() - (gx + r2.double())).abs().max() < 2e-4 * float(gx.abs().max())
+    dw = ops.tc_conv1d_wgrad(xc, dyc, geom)
+    assert (dw.cpu().double() - gw).abs().max() < 2e-4 * float(gw.abs().max())
+    assert (dw.cpu().double() - gw).norm() / gw.norm() < 1e-4

@@ -16,6 +16,17 @@ def relerr(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
+@pytest.fixture(params=["tc", "fma"])
+def path(request):
+    """Run every parity test on both contraction paths: tcgen05 tensor cores with bf16x3 split operands
+    (the default) and the fp32 FMA kernels (VBX_TC=0)."""
+    from vibravox_b200 import ops
+    old = ops.TC_ENABLED
+    ops.TC_ENABLED = request.param == "tc"
+    yield request.param
+    ops.TC_ENABLED = old
+
+
 def build(seed=42, p=2, q=4):
     from vibravox_b200.torch_modules.dnn.eben_discriminator import DiscriminatorEBENMultiScales
     from vibravox_b200.torch_modules.dnn.eben_generator import EBENGenerator
@@ -23,7 +34,7 @@ def build(seed=42, p=2, q=4):
     return EBENGenerator(m=4, n=32, p=p), DiscriminatorEBENMultiScales(q=q, min_channels=24)
 
 
-def test_config1_generator_forward_matches_golden(golden_dir):
+def test_config1_generator_forward_matches_golden(golden_dir, path):
     """BASELINE.json configs[0]: EBENGenerator(m=4,p=2) forward on 1x1x16000, fp32 vs reference."""
     gold = torch.load(os.path.join(golden_dir, "cfg1_forward.pt"))
     G, D = build(gold["seed"])
@@ -45,7 +56,7 @@ def test_config1_generator_forward_matches_golden(golden_dir):
 
 
 @pytest.mark.parametrize("p,q,B,L", [(2, 4, 2, 8000), (1, 3, 2, 15679), (4, 4, 2, 6000)])
-def test_forward_and_gradients_match_oracle(p, q, B, L):
+def test_forward_and_gradients_match_oracle(p, q, B, L, path):
     from oracle import eben_oracle as O
     G, D = build(7, p, q)
     gs = {k: v.detach().clone() for k, v in G.state_dict().items()}
@@ -79,7 +90,9 @@ def test_forward_and_gradients_match_oracle(p, q, B, L):
     xc = G.cut_to_valid_length(body.to(DEV))
     ac = G.cut_to_valid_length(air.to(DEV))
     y, bands = G(xc)
-    assert relerr(y, y64) < 1e-5 and relerr(bands, b64) < 1e-5
+    ftol = 1e-5 if path == "fma" else 1e-4          # fp32-grade on the FMA path; the 1e-4 contract on bf16x3
+    print(path, "G forward rel-L2 vs fp64:", relerr(y, y64), relerr(bands, b64))
+    assert relerr(y, y64) < ftol and relerr(bands, b64) < ftol
     e = D(bands=bands, audio=y)
     r = D(bands=G.pqmf(ac, "analysis"), audio=ac)
     for sa, sb in zip(e, e64):
@@ -87,7 +100,7 @@ def test_forward_and_gradients_match_oracle(p, q, B, L):
             assert ta.shape == tb.shape and relerr(ta, tb) < 1e-4
     hinge = HingeLossForDiscriminatorMelganMultiScales()
     loss = FeatureLossForDiscriminatorMelganMultiScales()(e, r) + hinge(e, 1) + hinge(r, -1)
-    assert float(loss) == pytest.approx(float(loss64), rel=2e-5)
+    assert float(loss) == pytest.approx(float(loss64), rel=2e-5 if path == "fma" else 2e-4)
     gp = dict(G.named_parameters())
     dp = dict(D.named_parameters())
     params = [gp[k] for k in names_g] + [dp[k] for k in d64]
@@ -97,7 +110,7 @@ def test_forward_and_gradients_match_oracle(p, q, B, L):
         rows.append((relerr(g, g_64), relerr(g_32, g_64), name, float(g_64.norm())))
     rows.sort(reverse=True)
     os.makedirs("gpurun_out", exist_ok=True)
-    with open(f"gpurun_out/grad_table_p{p}q{q}.txt", "w") as f:
+    with open(f"gpurun_out/grad_table_{path}_p{p}q{q}.txt", "w") as f:
         for err, noise, name, nrm in rows:
             f.write(f"{err:.3e} {noise:.3e} {nrm:.3e} {name}\n")
     # Per tensor: no worse than 3x the reference's own fp32 noise, with a floor.  The floor is what a single
@@ -119,7 +132,7 @@ def test_forward_and_gradients_match_oracle(p, q, B, L):
         assert e < 3 * n32 + 5e-4, (tag, e, n32)
 
 
-def test_training_step_matches_reference_golden(golden_dir):
+def test_training_step_matches_reference_golden(golden_dir, path):
     """Two consecutive training steps vs the logs of the reference's own eben.py (golden)."""
     import vibravox_b200
     from oracle import eben_oracle as O
@@ -146,7 +159,7 @@ def test_training_step_matches_reference_golden(golden_dir):
         assert float(dsd[k].double().abs().mean()) == pytest.approx(v, rel=2e-2, abs=1e-3), k
 
 
-def test_training_step_gradients_bracket_fp64(golden_dir):
+def test_training_step_gradients_bracket_fp64(golden_dir, path):
     """Full-step generator / discriminator gradient norms vs the fp64 oracle (grad_bracket.pt)."""
     import vibravox_b200
     from oracle import eben_oracle as O
@@ -179,7 +192,7 @@ def test_training_step_gradients_bracket_fp64(golden_dir):
     assert len(names) == len(opt._slices)
 
 
-def test_full_size_properties():
+def test_full_size_properties(path):
     """BASELINE.json configs[1] sizes (bs=32 x 3 s): size-independent properties instead of an oracle run."""
     G, D = build(42)
     G, D = G.to(DEV), D.to(DEV)

@@ -59,4 +59,12 @@ for i in which:
     t_dtc = tm(lambda: ops.tc_conv1d_dgrad(dyv, pk, g, Tin))
     t_dsimt = tm(lambda: ops.conv1d_dgrad(dyv, wt, g, Tin))
     print(f"   dgrad: max abs {derr[0]:.2e} rel-L2 {derr[1]:.2e} | tc {t_dtc:.3f} ms ({flops/t_dtc/1e9:.1f} TF) simt {t_dsimt:.3f} ms ({flops/t_dsimt/1e9:.1f} TF)")
+    # wgrad
+    wref = ops.conv1d_wgrad(x, dyv, g)
+    wgot = ops.tc_conv1d_wgrad(x, dyv, g)
+    torch.cuda.synchronize()
+    werr = float((wgot - wref).abs().max() / wref.abs().max()), float((wgot - wref).norm() / wref.norm())
+    t_wtc = tm(lambda: ops.tc_conv1d_wgrad(x, dyv, g, dw=wgot))
+    t_wsimt = tm(lambda: ops.conv1d_wgrad(x, dyv, g, dw=wref))
+    print(f"   wgrad: max rel {werr[0]:.2e} rel-L2 {werr[1]:.2e} | tc {t_wtc:.3f} ms ({flops/t_wtc/1e9:.1f} TF) simt {t_wsimt:.3f} ms ({flops/t_wsimt/1e9:.1f} TF)")
 print("done")

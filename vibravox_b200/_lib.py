@@ -46,6 +46,7 @@ SIGNATURES = {
     "vbx_tc_pack": [_PD, c_int, c_p, c_p, c_p],
     "vbx_tc_conv1d_fwd": [_PD, c_p, c_p, _PE, c_p, c_p],
     "vbx_tc_conv1d_dgrad": [_PD, c_p, c_p, _PE, c_p, c_p],
+    "vbx_tc_conv1d_wgrad": [_PD, c_p, c_p, c_p, c_p],
     "vbx_transpose_weight": [c_p, c_p, c_int, c_int, c_int, c_int, c_p],
     "vbx_weight_norm_fwd": [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p],
     "vbx_weight_norm_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_f, c_p],

@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "conv_plan.h"
 #include "tc_common.cuh"
+#include <limits.h>
 
 namespace vbx {
 namespace tc {
@@ -391,6 +392,160 @@ static int pack_tc(const TcP& P, const float* w, void* packed, cudaStream_t st) 
 using namespace vbx;
 using namespace vbx::tc;
 
+// ---------------------------------------------------------------------------------------------
+// WGRAD on tensor cores: dW[co, (ci,k)] += sum_{(b,t)} dy[b,co,t] * x[b,ci,map(t*s + k*d - pad)].
+// Rows of the MMA are output channels (M = 128 lanes), columns are (ci,k) (N <= 256), and the
+// reduction walks TIME, which is the contiguous axis of both operands: both tiles are K-major and
+// both are gathered by the producer warps (lanes walk t: coalesced), nothing is pre-packed.
+// The (b,t) range is split over blockIdx.z; partial tiles are added with fp32 reductions.
+static const int kLboW = kRows * 16 + 16;     // A: bytes between 8-t units (+16: conflict-free 2-byte stores)
+
+struct TcW {
+  GemmP g;
+  int NT, ntiles_n, mtiles, tmem_cols, stages;
+  int red_per;      // reduction elements per blockIdx.z (multiple of 32)
+};
+__host__ __device__ inline int lbo_wb(int NT) { return NT * 16 + 16; }
+__host__ __device__ inline int wstage_bytes(int NT) { return 2 * 4 * kLboW + 2 * 4 * lbo_wb(NT); }
+
+__global__ void __launch_bounds__(kThreads, 2) tc_wgrad_kernel(const TcW P) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const GemmP& G = P.g;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = P.stages, NT = P.NT;
+  const int stage_sz = wstage_bytes(NT);
+  const int plane_a = 4 * kLboW, plane_bw = 4 * lbo_wb(NT);
+  unsigned char* stage0 = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_sz);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + S;
+  uint64_t* acc_full = bars + 2 * S;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
+  int2* rowinfo = reinterpret_cast<int2*>(tmem_slot + 2);          // per column n: (ci*Tin, k*d - pad)
+
+  const int per_g = P.mtiles * P.ntiles_n;
+  const int grp = blockIdx.y / per_g, mt = (blockIdx.y % per_g) / P.ntiles_n, nt = blockIdx.y % P.ntiles_n;
+  const int Ncols = G.Cin_g * G.K;
+  const int total = G.B * G.Tout;
+  const int red_lo = blockIdx.z * P.red_per;
+  const int red_hi = min(red_lo + P.red_per, total);
+  if (red_lo >= red_hi) return;
+  const int nchunks = (red_hi - red_lo + kKC - 1) / kKC;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], kProducers); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  for (int i = tid; i < NT; i += kThreads) {
+    const int n = nt * NT + i;
+    int2 ri = make_int2(0, INT_MIN);
+    if (n < Ncols) { const int ci = n / G.K, k = n % G.K; ri = make_int2(ci * G.Tin, k * G.dil - G.pad); }
+    rowinfo[i] = ri;
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    // ===================== producers: dy rows and im2col'd x rows, lanes walk t =====================
+    const uint32_t lane_off = (uint32_t)(lane >> 3) * 0 + (uint32_t)(lane & 7) * 2;   // + ku*LBO below
+    const int ku = lane >> 3;
+    const int co_base = mt * kRows;
+    for (int c = 0; c < nchunks; ++c) {
+      const int s = c % S, use = c / S;
+      const int r = red_lo + c * kKC + lane;
+      const bool rv = r < red_hi;
+      const int b = rv ? r / G.Tout : 0, t = rv ? r % G.Tout : 0;
+      const float* dyp = G.DY + ((long long)b * G.Cout + grp * G.Cout_g + co_base) * G.Tout + t;
+      const float* xp = G.X + ((long long)b * G.Cin + grp * G.Cin_g) * G.Tin;
+      const int ts = t * G.stride;
+      mbar_wait(&empty[s], (use & 1) ^ 1);
+      unsigned char* a_hi = stage0 + (size_t)s * stage_sz;
+      unsigned char* a_lo = a_hi + plane_a;
+      unsigned char* b_hi = a_lo + plane_a;
+      unsigned char* b_lo = b_hi + plane_bw;
+      const int rows_a = min(kRows, G.Cout_g - co_base);
+      // A rows (output channels): warp w takes rows w, w+8, ...
+#pragma unroll 4
+      for (int m = warp; m < kRows; m += 8) {
+        float v = (rv && m < rows_a) ? dyp[(long long)m * G.Tout] : 0.f;
+        __nv_bfloat16 hi, lo;
+        split_bf16(v, hi, lo);
+        const uint32_t off = (uint32_t)ku * kLboW + (uint32_t)m * 16 + lane_off;
+        *reinterpret_cast<__nv_bfloat16*>(a_hi + off) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(a_lo + off) = lo;
+      }
+      const uint32_t lbo_b = (uint32_t)lbo_wb(NT);
+#pragma unroll 4
+      for (int n = warp; n < NT; n += 8) {
+        const int2 ri = rowinfo[n];
+        float v = 0.f;
+        if (rv && ri.y != INT_MIN) {
+          const int p = map_pos(ts + ri.y, G.Tin, G.refl);
+          if (p >= 0) v = xp[ri.x + p];
+        }
+        __nv_bfloat16 hi, lo;
+        split_bf16(v, hi, lo);
+        const uint32_t off = (uint32_t)ku * lbo_b + (uint32_t)n * 16 + lane_off;
+        *reinterpret_cast<__nv_bfloat16*>(b_hi + off) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(b_lo + off) = lo;
+      }
+      fence_proxy_async();
+      mbar_arrive(&full[s]);
+    }
+    // ===================== epilogue: TMEM -> fp32 reductions into dW =====================
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int q = warp & 3, half = warp >> 2;
+    const int co = co_base + q * 32 + lane;
+    const bool ev = co < G.Cout_g;
+    float* dst = G.Y + ((long long)grp * G.Cout_g + co) * Ncols;
+    const int nblk = NT / 16;
+    const int blk_lo = half == 0 ? 0 : (nblk + 1) / 2, blk_hi = half == 0 ? (nblk + 1) / 2 : nblk;
+    for (int blk = blk_lo; blk < blk_hi; ++blk) {
+      float acc[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * 16), acc);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int n = nt * NT + blk * 16 + j;
+        if (ev && n < Ncols) atomicAdd(dst + n, acc[j]);
+      }
+    }
+  } else if (warp == 8) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(NT, /*a_mn=*/false, /*b_mn=*/false);
+      const uint32_t lbo_b = (uint32_t)lbo_wb(NT);
+      uint32_t accumulate = 0;
+      for (int c = 0; c < nchunks; ++c) {
+        const int s = c % S, use = c / S;
+        mbar_wait(&full[s], use & 1);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(stage0 + (size_t)s * stage_sz), a_lo = a_hi + plane_a;
+        const uint32_t b_hi = a_lo + plane_a, b_lo = b_hi + plane_bw;
+#pragma unroll
+        for (int ks = 0; ks < kKC / 16; ++ks) {
+          const uint64_t da_hi = make_desc(a_hi + ks * 2 * kLboW, kLboW, 128);
+          const uint64_t da_lo = make_desc(a_lo + ks * 2 * kLboW, kLboW, 128);
+          const uint64_t db_hi = make_desc(b_hi + ks * 2 * lbo_b, lbo_b, 128);
+          const uint64_t db_lo = make_desc(b_lo + ks * 2 * lbo_b, lbo_b, 128);
+          mma_bf16_ss(tmem_base, da_hi, db_hi, idesc, accumulate);
+          accumulate = 1;
+          mma_bf16_ss(tmem_base, da_hi, db_lo, idesc, 1);
+          mma_bf16_ss(tmem_base, da_lo, db_hi, idesc, 1);
+        }
+        mma_commit(&empty[s]);
+      }
+      mma_commit(acc_full);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+}
+
 static int64_t pack_bytes(const TcP& P) {
   return (int64_t)P.g.groups * P.ntiles_n * P.nphase * P.nchunks * 2 * plane_b(P.NT);
 }
@@ -434,4 +589,44 @@ extern "C" int vbx_tc_conv1d_dgrad(const vbx_conv_desc* d, const float* dy, cons
   P.g.X = dy; P.g.Y = dx;
   P.packed = (const unsigned char*)packed;
   return launch_tc<DGRAD>(P, (cudaStream_t)stream);
+}
+
+extern "C" int vbx_tc_conv1d_wgrad(const vbx_conv_desc* d, const float* x, const float* dy, float* dw,
+                                   void* stream) {
+  int code = 0;
+  const char* msg = check_desc_msg(d, &code);
+  if (msg) return fail(code, msg);
+  VBX_REQUIRE(x && dy && dw, VBX_BAD_POINTER, "tc_conv1d_wgrad: null tensor");
+  TcW P;
+  fill(P.g, d);
+  P.g.X = x; P.g.DY = dy; P.g.Y = dw;
+  const int Ncols = P.g.Cin_g * P.g.K;
+  P.NT = pick_nt(Ncols);
+  P.ntiles_n = (Ncols + P.NT - 1) / P.NT;
+  P.mtiles = (P.g.Cout_g + kRows - 1) / kRows;
+  P.tmem_cols = pow2_cols(P.NT);
+  int st = (108 * 1024) / wstage_bytes(P.NT);
+  P.stages = st > 4 ? 4 : (st < 2 ? 2 : st);
+  const long long total = (long long)P.g.B * P.g.Tout;
+  const long long tiles = (long long)P.ntiles_n * P.mtiles * P.g.groups;
+  long long want = (148 * 4 + tiles - 1) / tiles;
+  long long max_split = (total + kKC * 8 - 1) / (kKC * 8);            // >= 8 chunks per slice
+  if (want > max_split) want = max_split;
+  if (want < 1) want = 1;
+  if (want > 65535) want = 65535;
+  long long per = (total + want - 1) / want;
+  per = (per + kKC - 1) / kKC * kKC;
+  P.red_per = (int)per;
+  dim3 grid(1, (unsigned)tiles, (unsigned)((total + per - 1) / per));
+  VBX_REQUIRE(grid.y <= 65535 && grid.z <= 65535, VBX_UNSUPPORTED, "tc_conv1d_wgrad: grid too large");
+  const size_t smem = (size_t)P.stages * wstage_bytes(P.NT) + (2 * P.stages + 1) * sizeof(uint64_t) + 16 +
+                      (size_t)P.NT * sizeof(int2) + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t ce = cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (ce != cudaSuccess) return fail((int)ce, "tc_conv1d_wgrad: cannot raise the dynamic shared memory limit");
+    attr_set = true;
+  }
+  tc_wgrad_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(P);
+  return launched("tc_wgrad_kernel");
 }

@@ -76,7 +76,7 @@ class ConvFn(Function):
     def forward(ctx, x: Tensor, w: Tensor, wt: Optional[Tensor], bias: Optional[Tensor], geom: ConvGeom,
                 slope: float):
         x, w = _c(x), _c(w)
-        y = ops.conv1d_fwd(x, w, geom, bias=bias, slope=slope)
+        y = ops.conv_fwd(x, w, geom, bias=bias, slope=slope)
         ctx.geom, ctx.slope, ctx.has_bias = geom, slope, bias is not None
         ctx.w_slot = grad_slot(w)
         ctx.b_slot = grad_slot(bias) if bias is not None else None
@@ -100,11 +100,9 @@ class ConvFn(Function):
             gp = out if out is not None else gy
         dx = dw = None
         if need_x:
-            if wt is None:
-                wt = ops.transpose_weight(w, geom.groups)
-            dx = ops.conv1d_dgrad(gp, wt, geom, x.shape[2])
+            dx = ops.conv_dgrad(gp, w, wt, geom, x.shape[2])
         if need_w:
-            dw = ops.conv1d_wgrad(x, gp, geom, dw=ctx.w_slot)
+            dw = ops.conv_wgrad(x, gp, geom, dw=ctx.w_slot)
         return (dx, None if ctx.w_slot is not None else dw, None,
                 None if ctx.b_slot is not None else dbias, None, None)
 
@@ -120,7 +118,7 @@ class ConvTransposeFn(Function):
         xs = ops.add(_c(x), _c(skip)) if skip is not None else _c(x)
         T = xs.shape[2]
         L = (T - 1) * geom.stride - 2 * geom.pad + geom.dil * (geom.K - 1) + output_padding + 1
-        y = ops.conv1d_dgrad(xs, wt, geom, L, slope=slope)
+        y = ops.conv_dgrad(xs, w, wt, geom, L, slope=slope)
         ctx.geom, ctx.slope, ctx.has_skip = geom, slope, skip is not None
         ctx.save_for_backward(xs, _c(w), y if slope != 1.0 else None)
         return y
@@ -135,9 +133,9 @@ class ConvTransposeFn(Function):
             gp = ops.leaky_relu_bwd(gp, y, slope)
         dxs = dw = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
-            dxs = ops.conv1d_fwd(gp, w, geom)
+            dxs = ops.conv_fwd(gp, w, geom)
         if ctx.needs_input_grad[2]:
-            dw = ops.conv1d_wgrad(gp, xs, geom)
+            dw = ops.conv_wgrad(gp, xs, geom)
         return (dxs if ctx.needs_input_grad[0] else None,
                 dxs if (ctx.has_skip and ctx.needs_input_grad[1]) else None, dw, None, None, None, None)
 
@@ -151,24 +149,24 @@ class ResidualUnitFn(Function):
     def forward(ctx, x: Tensor, w1: Tensor, wt1: Tensor, w2: Tensor, wt2: Tensor, g1: ConvGeom, g2: ConvGeom,
                 slope: float):
         x = _c(x)
-        h = ops.conv1d_fwd(x, w1, g1)
-        out, mask = ops.conv1d_fwd(h, w2, g2, res=x, slope=slope, want_mask=True)
+        h = ops.conv_fwd(x, w1, g1)
+        out, mask = ops.conv_fwd(h, w2, g2, res=x, slope=slope, want_mask=True)
         ctx.g1, ctx.g2, ctx.slope = g1, g2, slope
-        ctx.save_for_backward(x, h, mask, wt1, wt2)
+        ctx.save_for_backward(x, h, mask, wt1, wt2, w1, w2)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g):
-        x, h, mask, wt1, wt2 = ctx.saved_tensors
+        x, h, mask, wt1, wt2, w1, w2 = ctx.saved_tensors
         g1, g2, slope = ctx.g1, ctx.g2, ctx.slope
         g = _c(g)
         T = x.shape[2]
         dz = ops.leaky_relu_bwd(g, None, slope, mask=mask)
-        dw2 = ops.conv1d_wgrad(h, dz, g2) if ctx.needs_input_grad[3] else None
-        dh = ops.conv1d_dgrad(dz, wt2, g2, T)
-        dw1 = ops.conv1d_wgrad(x, dh, g1) if ctx.needs_input_grad[1] else None
-        dx = ops.conv1d_dgrad(dh, wt1, g1, T, res=g) if ctx.needs_input_grad[0] else None
+        dw2 = ops.conv_wgrad(h, dz, g2) if ctx.needs_input_grad[3] else None
+        dh = ops.conv_dgrad(dz, w2, wt2, g2, T)
+        dw1 = ops.conv_wgrad(x, dh, g1) if ctx.needs_input_grad[1] else None
+        dx = ops.conv_dgrad(dh, w1, wt1, g1, T, res=g) if ctx.needs_input_grad[0] else None
         return dx, dw1, None, dw2, None, None, None, None
 
 

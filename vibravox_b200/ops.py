@@ -6,6 +6,7 @@ contiguous tensors and libvbx_b200.so is loaded.
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -162,6 +163,16 @@ def tc_conv1d_dgrad(dy: Tensor, packed: Tensor, g: ConvGeom, Tin: int, res: Opti
     check(_lib.load().vbx_tc_conv1d_dgrad(ctypes.byref(d), _p(dy), packed.data_ptr(), ctypes.byref(e), _p(dx),
                                           _stream()), "vbx_tc_conv1d_dgrad")
     return dx
+
+
+def tc_conv1d_wgrad(x: Tensor, dy: Tensor, g: ConvGeom, dw: Optional[Tensor] = None) -> Tensor:
+    B, Cin, Tin = x.shape
+    d = g.desc(B, Tin)
+    assert tuple(dy.shape) == (B, g.Cout, d.Tout), (dy.shape, g, Tin)
+    if dw is None:
+        dw = torch.zeros((g.Cout, g.Cin // g.groups, g.K), device=x.device, dtype=torch.float32)
+    check(_lib.load().vbx_tc_conv1d_wgrad(ctypes.byref(d), _p(x), _p(dy), _p(dw), _stream()), "vbx_tc_conv1d_wgrad")
+    return dw
 
 
 def transpose_weight(w: Tensor, groups: int) -> Tensor:
@@ -375,3 +386,55 @@ def noise_mix_crop(body: Tensor, air: Tensor, noise: Tensor, start: Tensor, off:
                                          _p(out_body), _p(out_air), B, Ls, Ln, length, _stream()),
           "vbx_noise_mix_crop")
     return out_body, out_air
+
+
+# ------------------------------------------------------------------ kernel selection
+# Dense-enough layers run on the tcgen05 tensor-core kernels (bf16x3 split operands, fp32 accumulate);
+# the rest (a handful of tiny-channel layers, the STFT-as-conv with stride >= 50) on the fp32 FMA
+# kernels.  VBX_TC=0 forces the fp32 FMA kernels everywhere.
+TC_ENABLED = os.environ.get("VBX_TC", "1") != "0"
+TC_FWD, TC_DGRAD = 0, 1
+
+
+def use_tc(g: ConvGeom, kind: str) -> bool:
+    if not TC_ENABLED or g.stride > 8:
+        return False
+    cin_g, cout_g = g.Cin // g.groups, g.Cout // g.groups
+    if kind == "fwd":
+        return cout_g >= 8
+    if kind == "dgrad":
+        return cin_g >= 8
+    return cout_g >= 16 and cin_g * g.K >= 8          # wgrad
+
+
+def get_pack(w: Tensor, g: ConvGeom, mode: int) -> Tensor:
+    """Packed bf16 hi/lo tiles of `w`, cached on the tensor object (an effective weight lives for one
+    phase of one step; parameters used directly are keyed by their version counter)."""
+    cache = w.__dict__.setdefault("_vbx_packs", {})
+    key = (g, mode, w._version)
+    pk = cache.get(key)
+    if pk is None:
+        pk = tc_pack(w if w.is_contiguous() else w.contiguous(), g, mode)
+        cache.clear()
+        cache[key] = pk
+    return pk
+
+
+def conv_fwd(x: Tensor, w: Tensor, g: ConvGeom, bias=None, res=None, slope: float = 1.0, want_mask: bool = False):
+    if use_tc(g, "fwd"):
+        return tc_conv1d_fwd(x, get_pack(w, g, TC_FWD), g, bias=bias, res=res, slope=slope, want_mask=want_mask)
+    return conv1d_fwd(x, w, g, bias=bias, res=res, slope=slope, want_mask=want_mask)
+
+
+def conv_dgrad(dy: Tensor, w: Tensor, wt: Optional[Tensor], g: ConvGeom, Tin: int, res=None, slope: float = 1.0):
+    if use_tc(g, "dgrad"):
+        return tc_conv1d_dgrad(dy, get_pack(w, g, TC_DGRAD), g, Tin, res=res, slope=slope)
+    if wt is None:
+        wt = transpose_weight(w, g.groups)
+    return conv1d_dgrad(dy, wt, g, Tin, res=res, slope=slope)
+
+
+def conv_wgrad(x: Tensor, dy: Tensor, g: ConvGeom, dw: Optional[Tensor] = None) -> Tensor:
+    if use_tc(g, "wgrad"):
+        return tc_conv1d_wgrad(x, dy, g, dw=dw)
+    return conv1d_wgrad(x, dy, g, dw=dw)
