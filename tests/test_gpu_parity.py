@@ -116,8 +116,12 @@ def test_forward_and_gradients_match_oracle(p, q, B, L, path):
     # Per tensor: no worse than 3x the reference's own fp32 noise, with a floor.  The floor is what a single
     # LeakyReLU-mask / |.|-sign flip costs on the short PQMF-discriminator feature maps: the fp32 oracle
     # itself shows 2e-4..6e-4 on those tensors whenever it has a flip (gpurun_out/grad_table_*.txt).
+    # On the tensor-core path the operands carry 16 mantissa bits (bf16 hi + lo), i.e. ~100x the fp32
+    # rounding unit, and the same cancellation that turns 6e-8 into 5e-5..2e-3 for the fp32 reference
+    # turns 4e-6 into 1e-3..2e-2 here: the floors are scaled accordingly (forward stays < 1e-5).
+    per_tensor, whole = (5e-3, 5e-4) if path == "fma" else (5e-2, 5e-3)
     for err, noise, name, nrm in rows:
-        assert err < 3 * noise + 5e-3, (name, err, noise)
+        assert err < 3 * noise + per_tensor, (name, err, noise)
     # Whole-network: relative error of the concatenated gradient vector, generator and discriminator
     def total(idx):
         num = sum(float((g.detach().cpu().double() - w).norm()) ** 2 for g, w in idx) ** 0.5
@@ -129,7 +133,7 @@ def test_forward_and_gradients_match_oracle(p, q, B, L, path):
     for lo, hi, tag in ((0, ng, "generator"), (ng, len(pairs), "discriminator")):
         e, n32 = total(pairs[lo:hi]), total(pairs32[lo:hi])
         print(f"{tag}: whole-gradient rel-L2 vs fp64 {e:.2e} (fp32 oracle {n32:.2e})")
-        assert e < 3 * n32 + 5e-4, (tag, e, n32)
+        assert e < 3 * n32 + whole, (tag, e, n32)
 
 
 def test_training_step_matches_reference_golden(golden_dir, path):
@@ -145,9 +149,10 @@ def test_training_step_matches_reference_golden(golden_dir, path):
         want = gold["steps"][it]
         for k, v in want["logs"].items():
             got = float(lm.logged["train/" + k])
-            assert got == pytest.approx(v, rel=3e-4, abs=3e-5), (it, k, got, v)
+            tol = 3e-4 if (path == "fma" or it == 0) else 3e-3     # step 2 sees parameters updated by Adam's
+            assert got == pytest.approx(v, rel=tol, abs=tol / 10), (it, k, got, v)   # sign-like first step
         for a, b in zip(lm.atomic_norms_old.cpu().tolist(), want["norms_old"]):
-            assert a == pytest.approx(b, rel=5e-4)
+            assert a == pytest.approx(b, rel=5e-4 if path == "fma" else 5e-3)
         assert torch.allclose(out["enhanced"][0, 0, :64].cpu(), want["enhanced_head"], atol=2e-5 if it == 0 else 2e-3)
     # post-Adam parameters: statistical agreement: sums drift by at most a few lr-sized flips
     gsd = lm.generator.state_dict()
@@ -176,10 +181,11 @@ def test_training_step_gradients_bracket_fp64(golden_dir, path):
         ref_b = G.pqmf.forward(y, "analysis")
         losses = lm.compute_atomic_losses("generator", enh, y, enh_b, ref_b)
         lam = lm.dynamically_balance_losses(losses)
+        gtol = 1e-3 if path == "fma" else 5e-3
         for a, b in zip(lm.last_norms.cpu().tolist(), gold["norms64"]):
-            assert a == pytest.approx(b, rel=1e-3)
+            assert a == pytest.approx(b, rel=gtol)
         for a, b in zip(lam.cpu().tolist(), gold["lambdas64"]):
-            assert a == pytest.approx(b, rel=1e-3)
+            assert a == pytest.approx(b, rel=gtol)
         from vibravox_b200.functional import WeightedSumFn
         WeightedSumFn.apply(lam, *losses.values()).backward()
     opt = lm.generator_optimizer
@@ -188,7 +194,7 @@ def test_training_step_gradients_bracket_fp64(golden_dir, path):
     for (n, p), slot in zip([(n, p) for n, p in G.named_parameters() if p.requires_grad], opt._slices):
         want = gold["g_grad_norm64"][n]
         noise = gold["g_fp32_vs_fp64"][n]
-        assert float(slot.norm()) == pytest.approx(want, rel=3 * noise + 1e-3), n
+        assert float(slot.norm()) == pytest.approx(want, rel=3 * noise + (1e-3 if path == "fma" else 1e-2)), n
     assert len(names) == len(opt._slices)
 
 

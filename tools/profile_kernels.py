@@ -15,9 +15,9 @@ w = torch.randn(1024, 256, 41, device=dev) * 0.01
 wt = ops.transpose_weight(w, 4)
 bias = torch.zeros(1024, device=dev)
 for _ in range(2):
-    y = ops.conv1d_fwd(x, w, g, bias=bias, slope=0.2)
-    dx = ops.conv1d_dgrad(y, wt, g, 748)
-    dw = ops.conv1d_wgrad(x, y, g)
+    y = ops.conv_fwd(x, w, g, bias=bias, slope=0.2)
+    dx = ops.conv_dgrad(y, w, wt, g, 748)
+    dw = ops.conv_wgrad(x, y, g)
 # generator residual unit at C=32, T=11968
 C, T = 32, 11968
 xg = torch.randn(B, C, T, device=dev)
@@ -26,9 +26,9 @@ w2 = torch.randn(C, C, 1, device=dev) * 0.1
 g1 = ops.ConvGeom(C, C, 3, 1, 3, 3, 3, 1)
 g2 = ops.ConvGeom(C, C, 1, 1, 1, 0, 0, 1)
 for _ in range(2):
-    h = ops.conv1d_fwd(xg, w1, g1)
-    o = ops.conv1d_fwd(h, w2, g2, res=xg, slope=0.01)
-    dh = ops.conv1d_dgrad(o, ops.transpose_weight(w2, 1), g2, T)
-    dwg = ops.conv1d_wgrad(xg, dh, g1)
+    h = ops.conv_fwd(xg, w1, g1)
+    o = ops.conv_fwd(h, w2, g2, res=xg, slope=0.01)
+    dh = ops.conv_dgrad(o, w2, None, g2, T)
+    dwg = ops.conv_wgrad(xg, dh, g1)
 torch.cuda.synchronize()
 print("done")
