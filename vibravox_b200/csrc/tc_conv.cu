@@ -159,41 +159,73 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const TcP P) {
         src += ((long long)b * G.Cout + grp * G.Cout_g) * G.Tout;
         base = (p + G.pad) / G.stride - seg.kd0_hi;      // p + pad >= 0 because refl <= pad
       }
+      // Reduction walk of this thread: kk = kh*16 + i (i < 16) of every 32-element chunk, i.e. channel
+      // `ch`, tap `k`, element offset `off` = ch*chan_stride + position(k).  Rows whose whole tap span lies
+      // inside the signal take the lean path (one predicated load + one add per element).
+      const int chan_stride = MODE == FWD ? G.Tin : G.Tout;
+      const int dstep = MODE == FWD ? G.dil : -seg.tstep;
+      const int span_lo = MODE == FWD ? base : base - (Kmod - 1) * seg.tstep;
+      const int span_hi = MODE == FWD ? base + (Kmod - 1) * G.dil : base;
+      const bool interior = valid && span_lo >= 0 && span_hi < chan_stride;
+      const int wrap = chan_stride - Kmod * dstep;
       int ch = (kh * 16) / Kmod, k = (kh * 16) % Kmod;
-      for (int cs = 0; cs < seg.nchunks; ++cs, ++c) {
-        const int s = c % S, use = c / S;
-        mbar_wait(&empty[s], (use & 1) ^ 1);
-        unsigned char* a_hi = stage0 + (size_t)s * stage_sz;
-        unsigned char* a_lo = a_hi + kPlaneA;
-        float v[16];
+      int off = ch * chan_stride + base + k * dstep;
+      auto gather16 = [&](float(&v)[16]) {
+        if (interior) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float x = 0.f;
-          if (valid && ch < Cred) {
-            if (MODE == FWD) {
-              int p = map_pos(base + k * G.dil, G.Tin, G.refl);
-              if (p >= 0) x = src[(long long)ch * G.Tin + p];
-            } else {
-              int t = base - k * seg.tstep;
-              if (t >= 0 && t < G.Tout) x = src[(long long)ch * G.Tout + t];
-            }
+          for (int i = 0; i < 16; ++i) {
+            v[i] = ch < Cred ? src[off] : 0.f;
+            off += dstep;
+            if (++k == Kmod) { k = 0; ++ch; off += wrap; }
           }
-          v[i] = x;
-          if (++k == Kmod) { k = 0; ++ch; }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float x = 0.f;
+            if (valid && ch < Cred) {
+              if (MODE == FWD) {
+                int p = map_pos(base + k * G.dil, G.Tin, G.refl);
+                if (p >= 0) x = src[ch * G.Tin + p];
+              } else {
+                int t = base - k * seg.tstep;
+                if (t >= 0 && t < G.Tout) x = src[ch * G.Tout + t];
+              }
+            }
+            v[i] = x;
+            if (++k == Kmod) { k = 0; ++ch; }
+          }
         }
+        k += 16;                                         // skip the 16 elements of the other half-warp group
+        if (k >= Kmod) { ch += k / Kmod; k %= Kmod; }
+        off = ch * chan_stride + base + k * dstep;
+      };
+      auto store16 = [&](const float(&v)[16], int cc) {
+        const int s = cc % S, use = cc / S;
+        mbar_wait(&empty[s], (use & 1) ^ 1);
+        unsigned char* a_hi = stage0 + (size_t)s * stage_sz + row_off;
+        unsigned char* a_lo = a_hi + kPlaneA;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int kk = kh * 16 + i;
-          const uint32_t off = row_off + (uint32_t)(kk >> 3) * kLboA + (uint32_t)(kk & 7) * 16;
+          const uint32_t o = (uint32_t)(kk >> 3) * kLboA + (uint32_t)(kk & 7) * 16;
           __nv_bfloat16 hi, lo;
           split_bf16(v[i], hi, lo);
-          *reinterpret_cast<__nv_bfloat16*>(a_hi + off) = hi;
-          *reinterpret_cast<__nv_bfloat16*>(a_lo + off) = lo;
+          *reinterpret_cast<__nv_bfloat16*>(a_hi + o) = hi;
+          *reinterpret_cast<__nv_bfloat16*>(a_lo + o) = lo;
         }
-        k += 16;
-        if (k >= Kmod) { ch += k / Kmod; k %= Kmod; }
         fence_proxy_async();
         mbar_arrive(&full_a[s]);
+      };
+      // software pipeline: the loads of chunk cs+1 are in flight while chunk cs is converted and stored
+      float va[16], vb[16];
+      const int nch = seg.nchunks;
+      gather16(va);
+      for (int cs = 0; cs < nch; cs += 2) {
+        if (cs + 1 < nch) gather16(vb);
+        store16(va, c++);
+        if (cs + 1 >= nch) break;
+        if (cs + 2 < nch) gather16(va);
+        store16(vb, c++);
       }
     }
     // ===================== epilogue: TMEM -> registers -> fused output stage -> (B,C,T) =====================
@@ -422,6 +454,8 @@ __global__ void __launch_bounds__(kThreads, 2) tc_wgrad_kernel(const TcW P) {
   uint64_t* acc_full = bars + 2 * S;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
   int2* rowinfo = reinterpret_cast<int2*>(tmem_slot + 2);          // per column n: (ci*Tin, k*d - pad)
+  int* roff = reinterpret_cast<int*>(rowinfo + NT);                // per column n: ci*Tin + k*d - pad
+  int* kspan = roff + NT;                                          // [min, max] of k*d - pad over the tile
 
   const int per_g = P.mtiles * P.ntiles_n;
   const int grp = blockIdx.y / per_g, mt = (blockIdx.y % per_g) / P.ntiles_n, nt = blockIdx.y % P.ntiles_n;
@@ -442,6 +476,15 @@ __global__ void __launch_bounds__(kThreads, 2) tc_wgrad_kernel(const TcW P) {
     int2 ri = make_int2(0, INT_MIN);
     if (n < Ncols) { const int ci = n / G.K, k = n % G.K; ri = make_int2(ci * G.Tin, k * G.dil - G.pad); }
     rowinfo[i] = ri;
+    roff[i] = n < Ncols ? ri.x + ri.y : INT_MIN;
+  }
+  if (tid == 0) {
+    // columns of a tile cover consecutive (ci,k): if they span a whole channel all taps occur
+    const int n_lo = nt * NT, n_hi = min(n_lo + NT, Ncols) - 1;
+    int klo = n_lo % G.K, khi = n_hi % G.K;
+    if (n_hi / G.K != n_lo / G.K) { klo = 0; khi = G.K - 1; }
+    kspan[0] = klo * G.dil - G.pad;
+    kspan[1] = khi * G.dil - G.pad;
   }
   if (warp == 8) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
   tc_fence_before();
@@ -451,50 +494,65 @@ __global__ void __launch_bounds__(kThreads, 2) tc_wgrad_kernel(const TcW P) {
 
   if (warp < 8) {
     // ===================== producers: dy rows and im2col'd x rows, lanes walk t =====================
-    const uint32_t lane_off = (uint32_t)(lane >> 3) * 0 + (uint32_t)(lane & 7) * 2;   // + ku*LBO below
+    const uint32_t lane_off = (uint32_t)(lane & 7) * 2;
     const int ku = lane >> 3;
     const int co_base = mt * kRows;
+    const int rows_a = min(kRows, G.Cout_g - co_base);
+    const uint32_t lbo_b = (uint32_t)lbo_wb(NT);
+    const int kmin = kspan[0], kmax = kspan[1];          // range of k*d - pad over this tile's columns
+    int r = red_lo + lane;
+    int b = r / G.Tout, t = r % G.Tout;
     for (int c = 0; c < nchunks; ++c) {
       const int s = c % S, use = c / S;
-      const int r = red_lo + c * kKC + lane;
       const bool rv = r < red_hi;
-      const int b = rv ? r / G.Tout : 0, t = rv ? r % G.Tout : 0;
       const float* dyp = G.DY + ((long long)b * G.Cout + grp * G.Cout_g + co_base) * G.Tout + t;
       const float* xp = G.X + ((long long)b * G.Cin + grp * G.Cin_g) * G.Tin;
       const int ts = t * G.stride;
+      const bool interior = rv && ts + kmin >= 0 && ts + kmax < G.Tin;
       mbar_wait(&empty[s], (use & 1) ^ 1);
-      unsigned char* a_hi = stage0 + (size_t)s * stage_sz;
+      unsigned char* a_hi = stage0 + (size_t)s * stage_sz + (uint32_t)ku * kLboW + lane_off;
       unsigned char* a_lo = a_hi + plane_a;
-      unsigned char* b_hi = a_lo + plane_a;
+      unsigned char* b_hi = stage0 + (size_t)s * stage_sz + 2 * plane_a + (uint32_t)ku * lbo_b + lane_off;
       unsigned char* b_lo = b_hi + plane_bw;
-      const int rows_a = min(kRows, G.Cout_g - co_base);
       // A rows (output channels): warp w takes rows w, w+8, ...
-#pragma unroll 4
+#pragma unroll 8
       for (int m = warp; m < kRows; m += 8) {
-        float v = (rv && m < rows_a) ? dyp[(long long)m * G.Tout] : 0.f;
+        float v = (rv && m < rows_a) ? dyp[m * G.Tout] : 0.f;
         __nv_bfloat16 hi, lo;
         split_bf16(v, hi, lo);
-        const uint32_t off = (uint32_t)ku * kLboW + (uint32_t)m * 16 + lane_off;
-        *reinterpret_cast<__nv_bfloat16*>(a_hi + off) = hi;
-        *reinterpret_cast<__nv_bfloat16*>(a_lo + off) = lo;
+        *reinterpret_cast<__nv_bfloat16*>(a_hi + m * 16) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(a_lo + m * 16) = lo;
       }
-      const uint32_t lbo_b = (uint32_t)lbo_wb(NT);
-#pragma unroll 4
-      for (int n = warp; n < NT; n += 8) {
-        const int2 ri = rowinfo[n];
-        float v = 0.f;
-        if (rv && ri.y != INT_MIN) {
-          const int p = map_pos(ts + ri.y, G.Tin, G.refl);
-          if (p >= 0) v = xp[ri.x + p];
+      if (interior) {
+        const float* xt = xp + ts;
+#pragma unroll 8
+        for (int n = warp; n < NT; n += 8) {
+          const int ro = roff[n];
+          float v = ro != INT_MIN ? xt[ro] : 0.f;
+          __nv_bfloat16 hi, lo;
+          split_bf16(v, hi, lo);
+          *reinterpret_cast<__nv_bfloat16*>(b_hi + n * 16) = hi;
+          *reinterpret_cast<__nv_bfloat16*>(b_lo + n * 16) = lo;
         }
-        __nv_bfloat16 hi, lo;
-        split_bf16(v, hi, lo);
-        const uint32_t off = (uint32_t)ku * lbo_b + (uint32_t)n * 16 + lane_off;
-        *reinterpret_cast<__nv_bfloat16*>(b_hi + off) = hi;
-        *reinterpret_cast<__nv_bfloat16*>(b_lo + off) = lo;
+      } else {
+#pragma unroll 4
+        for (int n = warp; n < NT; n += 8) {
+          const int2 ri = rowinfo[n];
+          float v = 0.f;
+          if (rv && ri.y != INT_MIN) {
+            const int p = map_pos(ts + ri.y, G.Tin, G.refl);
+            if (p >= 0) v = xp[ri.x + p];
+          }
+          __nv_bfloat16 hi, lo;
+          split_bf16(v, hi, lo);
+          *reinterpret_cast<__nv_bfloat16*>(b_hi + n * 16) = hi;
+          *reinterpret_cast<__nv_bfloat16*>(b_lo + n * 16) = lo;
+        }
       }
       fence_proxy_async();
       mbar_arrive(&full[s]);
+      r += kKC; t += kKC;
+      while (t >= G.Tout) { t -= G.Tout; ++b; }
     }
     // ===================== epilogue: TMEM -> fp32 reductions into dW =====================
     mbar_wait(acc_full, 0);
@@ -620,7 +678,7 @@ extern "C" int vbx_tc_conv1d_wgrad(const vbx_conv_desc* d, const float* x, const
   dim3 grid(1, (unsigned)tiles, (unsigned)((total + per - 1) / per));
   VBX_REQUIRE(grid.y <= 65535 && grid.z <= 65535, VBX_UNSUPPORTED, "tc_conv1d_wgrad: grid too large");
   const size_t smem = (size_t)P.stages * wstage_bytes(P.NT) + (2 * P.stages + 1) * sizeof(uint64_t) + 16 +
-                      (size_t)P.NT * sizeof(int2) + 16;
+                      (size_t)P.NT * (sizeof(int2) + sizeof(int)) + 2 * sizeof(int) + 16;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t ce = cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

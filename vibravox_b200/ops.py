@@ -403,7 +403,7 @@ def use_tc(g: ConvGeom, kind: str) -> bool:
     if kind == "fwd":
         return cout_g >= 8
     if kind == "dgrad":
-        return cin_g >= 8
+        return cin_g >= 4
     return cout_g >= 16 and cin_g * g.K >= 8          # wgrad
 
 
