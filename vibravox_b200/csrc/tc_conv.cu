@@ -22,6 +22,7 @@
 #include "conv_plan.h"
 #include "tc_common.cuh"
 #include <limits.h>
+#include <stdlib.h>
 
 namespace vbx {
 namespace tc {
@@ -39,6 +40,7 @@ struct TcP {
   const unsigned char* packed;
   int NT, ntiles_n, nchunks, tmem_cols, stages;
   int nphase;       // DGRAD: packed tiles are indexed [g][nt][phase][chunk], nchunks = chunks per phase
+  int pipe;         // producers prefetch the next chunk's gathers before storing the current one
 };
 
 // one reduction segment of a tile: FWD has one; DGRAD has one per mirror image it touches
@@ -219,13 +221,20 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const TcP P) {
       // software pipeline: the loads of chunk cs+1 are in flight while chunk cs is converted and stored
       float va[16], vb[16];
       const int nch = seg.nchunks;
-      gather16(va);
-      for (int cs = 0; cs < nch; cs += 2) {
-        if (cs + 1 < nch) gather16(vb);
-        store16(va, c++);
-        if (cs + 1 >= nch) break;
-        if (cs + 2 < nch) gather16(va);
-        store16(vb, c++);
+      if (P.pipe) {
+        gather16(va);
+        for (int cs = 0; cs < nch; cs += 2) {
+          if (cs + 1 < nch) gather16(vb);
+          store16(va, c++);
+          if (cs + 1 >= nch) break;
+          if (cs + 2 < nch) gather16(va);
+          store16(vb, c++);
+        }
+      } else {
+        for (int cs = 0; cs < nch; ++cs) {
+          gather16(va);
+          store16(va, c++);
+        }
       }
     }
     // ===================== epilogue: TMEM -> registers -> fused output stage -> (B,C,T) =====================
@@ -385,6 +394,8 @@ static int fill_tc(TcP& P, const vbx_conv_desc* d, int mode) {
   }
   P.tmem_cols = pow2_cols(P.NT);
   P.stages = pick_stages(P.NT);
+  static const int pipe_env = getenv("VBX_TC_PIPE") ? atoi(getenv("VBX_TC_PIPE")) : 0;
+  P.pipe = pipe_env;
   return 0;
 }
 
