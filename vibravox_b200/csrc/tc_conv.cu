@@ -59,9 +59,18 @@ inline int pick_nt(int Cn) {
   return ((r + tiles - 1) / tiles + 15) / 16 * 16;
 }
 inline int pow2_cols(int n) { int c = 32; while (c < n) c <<= 1; return c; }
-inline int pick_stages(int NT) {
-  int s = (108 * 1024) / stage_bytes(NT);
-  return s > 4 ? 4 : (s < 2 ? 2 : s);
+// Pipeline depth.  A weight tile takes ~1.5k cycles to arrive through the bulk-copy engine and the gathers
+// see L2 latency too, while one stage is worth 768 tensor-core cycles at N = 256: long reductions get the
+// whole SM (one CTA, up to 4-6 stages); short ones keep two CTAs per SM so that one tile's epilogue
+// overlaps the other's main loop.
+static const int kSmemMax = 225 * 1024;
+inline int pick_stages_for(int stage_sz, int nchunks) {
+  const int budget = nchunks >= 12 ? kSmemMax - 2048 : 108 * 1024;
+  int s = budget / stage_sz;
+  const int cap = nchunks >= 12 ? 6 : 4;
+  s = s > cap ? cap : s;
+  if (s > nchunks) s = nchunks;
+  return s < 2 ? 2 : s;
 }
 
 __device__ __forceinline__ float finish(const GemmP& P, float v, int ch, long long idx) {
@@ -393,7 +402,7 @@ static int fill_tc(TcP& P, const vbx_conv_desc* d, int mode) {
     P.nchunks = (P.g.Cout_g * max_taps + kKC - 1) / kKC;
   }
   P.tmem_cols = pow2_cols(P.NT);
-  P.stages = pick_stages(P.NT);
+  P.stages = pick_stages_for(stage_bytes(P.NT), P.nchunks);
   static const int pipe_env = getenv("VBX_TC_PIPE") ? atoi(getenv("VBX_TC_PIPE")) : 0;
   P.pipe = pipe_env;
   return 0;
@@ -407,7 +416,7 @@ template <int MODE>
 static int launch_tc(const TcP& P, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t ce = cudaFuncSetAttribute(tc_conv_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t ce = cudaFuncSetAttribute(tc_conv_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
     if (ce != cudaSuccess) return fail((int)ce, "tc_conv: cannot raise the dynamic shared memory limit");
     attr_set = true;
   }
@@ -674,8 +683,6 @@ extern "C" int vbx_tc_conv1d_wgrad(const vbx_conv_desc* d, const float* x, const
   P.ntiles_n = (Ncols + P.NT - 1) / P.NT;
   P.mtiles = (P.g.Cout_g + kRows - 1) / kRows;
   P.tmem_cols = pow2_cols(P.NT);
-  int st = (108 * 1024) / wstage_bytes(P.NT);
-  P.stages = st > 4 ? 4 : (st < 2 ? 2 : st);
   const long long total = (long long)P.g.B * P.g.Tout;
   const long long tiles = (long long)P.ntiles_n * P.mtiles * P.g.groups;
   long long want = (148 * 4 + tiles - 1) / tiles;
@@ -686,13 +693,14 @@ extern "C" int vbx_tc_conv1d_wgrad(const vbx_conv_desc* d, const float* x, const
   long long per = (total + want - 1) / want;
   per = (per + kKC - 1) / kKC * kKC;
   P.red_per = (int)per;
+  P.stages = pick_stages_for(wstage_bytes(P.NT), (int)(per / kKC));
   dim3 grid(1, (unsigned)tiles, (unsigned)((total + per - 1) / per));
   VBX_REQUIRE(grid.y <= 65535 && grid.z <= 65535, VBX_UNSUPPORTED, "tc_conv1d_wgrad: grid too large");
   const size_t smem = (size_t)P.stages * wstage_bytes(P.NT) + (2 * P.stages + 1) * sizeof(uint64_t) + 16 +
                       (size_t)P.NT * (sizeof(int2) + sizeof(int)) + 2 * sizeof(int) + 16;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t ce = cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t ce = cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
     if (ce != cudaSuccess) return fail((int)ce, "tc_conv1d_wgrad: cannot raise the dynamic shared memory limit");
     attr_set = true;
   }
