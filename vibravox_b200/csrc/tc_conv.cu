@@ -40,7 +40,7 @@ struct TcP {
   const unsigned char* packed;
   int NT, ntiles_n, nchunks, tmem_cols, stages;
   int nphase;       // DGRAD: packed tiles are indexed [g][nt][phase][chunk], nchunks = chunks per phase
-  int pipe;         // producers prefetch the next chunk's gathers before storing the current one
+  int cpad;         // reduction channels padded to a multiple of 8 (or to 1/2/4): kk = tap*cpad + channel
 };
 
 // one reduction segment of a tile: FWD has one; DGRAD has one per mirror image it touches
@@ -65,9 +65,9 @@ inline int pow2_cols(int n) { int c = 32; while (c < n) c <<= 1; return c; }
 // overlaps the other's main loop.
 static const int kSmemMax = 225 * 1024;
 inline int pick_stages_for(int stage_sz, int nchunks) {
-  const int budget = nchunks >= 12 ? kSmemMax - 2048 : 108 * 1024;
+  const int budget = 108 * 1024;
   int s = budget / stage_sz;
-  const int cap = nchunks >= 12 ? 6 : 4;
+  const int cap = 4;
   s = s > cap ? cap : s;
   if (s > nchunks) s = nchunks;
   return s < 2 ? 2 : s;
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const TcP P) {
       for (int img = 0; img < 3; ++img) {
         if (!dgrad_tile_needs_img(G, blockIdx.z, row_base, kRows, img)) continue;
         DgradImg im = dgrad_img(G, dp.r, img);
-        const int nch = (G.Cout_g * im.ntaps + kKC - 1) / kKC;
+        const int nch = (P.cpad * im.ntaps + kKC - 1) / kKC;
         if (nch == 0) continue;
         segs[ns++] = Seg{nch, im.phase, img, im.k0, im.kstep, im.ntaps, im.tstep, im.kd0_hi};
       }
@@ -147,103 +147,90 @@ __global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const TcP P) {
 
   if (warp < 8) {
     // ===================== A producers: im2col gather -> bf16 hi/lo -> MN-major smem =====================
-    const int row = tid & 127, kh = tid >> 7;
-    const int n = row_base + row;
-    const bool in_range = n < N;
-    const uint32_t row_off = (uint32_t)(row >> 3) * kSboA + (uint32_t)(row & 7) * 2;
+    // Reduction order is tap-major / channel-minor: kk = tap*cpad + channel (cpad = channel count padded
+    // to 8, or to 1/2/4 for tiny layers).  A thread owns a PAIR of adjacent rows (time positions) and the
+    // 8 consecutive kk of one k8-group per chunk; when cpad % 8 == 0 those are 8 channels of ONE tap, so the
+    // halo / reflect / validity logic runs once per 16 loaded values and the loads walk a constant stride.
+    // Two rows are split with one packed convert (cvt.rn.bf16x2) and stored with one 4-byte store per plane.
+    const int pair = tid & 63, kq = tid >> 6;
+    const int r0 = 2 * pair;
+    const uint32_t st_off = (uint32_t)kq * kLboA + (uint32_t)(r0 >> 3) * kSboA + (uint32_t)(r0 & 7) * 2;
+    const int cpad = P.cpad;
+    const int chan_stride = MODE == FWD ? G.Tin : G.Tout;
     int c = 0;                                           // global chunk counter (pipeline position)
     for (int sg = 0; sg < nseg; ++sg) {
       const Seg seg = segs[sg];
-      bool valid = in_range;
-      const float* src = G.X;
-      int base = 0;                                      // FWD: t*s - pad ; DGRAD: T0
-      const int Kmod = MODE == FWD ? G.K : seg.ntaps;    // taps per reduction channel
-      if (MODE == FWD) {
-        const int b = valid ? n / G.Tout : 0, t = valid ? n % G.Tout : 0;
-        src += ((long long)b * G.Cin + grp * G.Cin_g) * G.Tin;
-        base = t * G.stride - G.pad;
-      } else {
-        const int b = valid ? n / dp.Up : 0, u = dp.r + (valid ? n % dp.Up : 0) * G.stride;
-        int p = u;
-        if (seg.img == 1) { p = -u; if (u < 1 || u > G.refl) valid = false; }
-        else if (seg.img == 2) { p = 2 * (G.Tin - 1) - u; if (u > G.Tin - 2 || u < G.Tin - 1 - G.refl) valid = false; }
-        src += ((long long)b * G.Cout + grp * G.Cout_g) * G.Tout;
-        base = (p + G.pad) / G.stride - seg.kd0_hi;      // p + pad >= 0 because refl <= pad
-      }
-      // Reduction walk of this thread: kk = kh*16 + i (i < 16) of every 32-element chunk, i.e. channel
-      // `ch`, tap `k`, element offset `off` = ch*chan_stride + position(k).  Rows whose whole tap span lies
-      // inside the signal take the lean path (one predicated load + one add per element).
-      const int chan_stride = MODE == FWD ? G.Tin : G.Tout;
-      const int dstep = MODE == FWD ? G.dil : -seg.tstep;
-      const int span_lo = MODE == FWD ? base : base - (Kmod - 1) * seg.tstep;
-      const int span_hi = MODE == FWD ? base + (Kmod - 1) * G.dil : base;
-      const bool interior = valid && span_lo >= 0 && span_hi < chan_stride;
-      const int wrap = chan_stride - Kmod * dstep;
-      int ch = (kh * 16) / Kmod, k = (kh * 16) % Kmod;
-      int off = ch * chan_stride + base + k * dstep;
-      auto gather16 = [&](float(&v)[16]) {
-        if (interior) {
+      const int Kmod = MODE == FWD ? G.K : seg.ntaps;    // taps walked by the reduction
+      const float* srcr[2];
+      int baser[2];
+      bool validr[2];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            v[i] = ch < Cred ? src[off] : 0.f;
-            off += dstep;
-            if (++k == Kmod) { k = 0; ++ch; off += wrap; }
-          }
+      for (int h = 0; h < 2; ++h) {
+        const int n = row_base + r0 + h;
+        bool valid = n < N;
+        const float* src = G.X;
+        int base;
+        if (MODE == FWD) {
+          const int b = valid ? n / G.Tout : 0, t = valid ? n % G.Tout : 0;
+          src += ((long long)b * G.Cin + grp * G.Cin_g) * G.Tin;
+          base = t * G.stride - G.pad;
         } else {
+          const int b = valid ? n / dp.Up : 0, u = dp.r + (valid ? n % dp.Up : 0) * G.stride;
+          int p = u;
+          if (seg.img == 1) { p = -u; if (u < 1 || u > G.refl) valid = false; }
+          else if (seg.img == 2) { p = 2 * (G.Tin - 1) - u; if (u > G.Tin - 2 || u < G.Tin - 1 - G.refl) valid = false; }
+          src += ((long long)b * G.Cout + grp * G.Cout_g) * G.Tout;
+          base = (p + G.pad) / G.stride - seg.kd0_hi;    // p + pad >= 0 because refl <= pad
+        }
+        srcr[h] = src; baser[h] = base; validr[h] = valid;
+      }
+      // position of tap `tap` for row h, or -1 (zero halo / outside)
+      auto tap_pos = [&](int h, int tap) -> int {
+        if (!validr[h] || tap >= Kmod) return -1;
+        if (MODE == FWD) return map_pos(baser[h] + tap * G.dil, G.Tin, G.refl);
+        const int t = baser[h] - tap * seg.tstep;
+        return (t >= 0 && t < G.Tout) ? t : -1;
+      };
+      int tap = 0, c0 = kq * 8;                          // cpad % 8 == 0 walk: (tap, first channel) of this thread's run
+      if ((cpad & 7) == 0) { tap = c0 / cpad; c0 %= cpad; }
+      for (int cs = 0; cs < seg.nchunks; ++cs, ++c) {
+        float xa[8], xb[8];
+        if ((cpad & 7) == 0) {
+          const int pa = tap_pos(0, tap), pb = tap_pos(1, tap);
+          const int nvalid = Cred - c0;
+          const float* qa = srcr[0] + (long long)c0 * chan_stride + (pa >= 0 ? pa : 0);
+          const float* qb = srcr[1] + (long long)c0 * chan_stride + (pb >= 0 ? pb : 0);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float x = 0.f;
-            if (valid && ch < Cred) {
-              if (MODE == FWD) {
-                int p = map_pos(base + k * G.dil, G.Tin, G.refl);
-                if (p >= 0) x = src[ch * G.Tin + p];
-              } else {
-                int t = base - k * seg.tstep;
-                if (t >= 0 && t < G.Tout) x = src[ch * G.Tout + t];
-              }
-            }
-            v[i] = x;
-            if (++k == Kmod) { k = 0; ++ch; }
+          for (int i = 0; i < 8; ++i) {
+            xa[i] = (pa >= 0 && i < nvalid) ? qa[i * chan_stride] : 0.f;
+            xb[i] = (pb >= 0 && i < nvalid) ? qb[i * chan_stride] : 0.f;
+          }
+          c0 += kKC;
+          while (c0 >= cpad) { c0 -= cpad; ++tap; }
+        } else {                                         // cpad in {1,2,4}: a run spans 8/cpad taps
+          const int kk0 = cs * kKC + kq * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int kk = kk0 + i, tp = kk / cpad, ci = kk % cpad;
+            const int pa = tap_pos(0, tp), pb = tap_pos(1, tp);
+            xa[i] = (pa >= 0 && ci < Cred) ? srcr[0][ci * chan_stride + pa] : 0.f;
+            xb[i] = (pb >= 0 && ci < Cred) ? srcr[1][ci * chan_stride + pb] : 0.f;
           }
         }
-        k += 16;                                         // skip the 16 elements of the other half-warp group
-        if (k >= Kmod) { ch += k / Kmod; k %= Kmod; }
-        off = ch * chan_stride + base + k * dstep;
-      };
-      auto store16 = [&](const float(&v)[16], int cc) {
-        const int s = cc % S, use = cc / S;
+        const int s = c % S, use = c / S;
         mbar_wait(&empty[s], (use & 1) ^ 1);
-        unsigned char* a_hi = stage0 + (size_t)s * stage_sz + row_off;
+        unsigned char* a_hi = stage0 + (size_t)s * stage_sz + st_off;
         unsigned char* a_lo = a_hi + kPlaneA;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int kk = kh * 16 + i;
-          const uint32_t o = (uint32_t)(kk >> 3) * kLboA + (uint32_t)(kk & 7) * 16;
-          __nv_bfloat16 hi, lo;
-          split_bf16(v[i], hi, lo);
-          *reinterpret_cast<__nv_bfloat16*>(a_hi + o) = hi;
-          *reinterpret_cast<__nv_bfloat16*>(a_lo + o) = lo;
+        for (int i = 0; i < 8; ++i) {
+          const __nv_bfloat162 hi2 = __floats2bfloat162_rn(xa[i], xb[i]);      // .x = row r0, .y = row r0+1
+          const float2 hf = __bfloat1622float2(hi2);
+          const __nv_bfloat162 lo2 = __floats2bfloat162_rn(xa[i] - hf.x, xb[i] - hf.y);
+          *reinterpret_cast<__nv_bfloat162*>(a_hi + i * 16) = hi2;
+          *reinterpret_cast<__nv_bfloat162*>(a_lo + i * 16) = lo2;
         }
         fence_proxy_async();
         mbar_arrive(&full_a[s]);
-      };
-      // software pipeline: the loads of chunk cs+1 are in flight while chunk cs is converted and stored
-      float va[16], vb[16];
-      const int nch = seg.nchunks;
-      if (P.pipe) {
-        gather16(va);
-        for (int cs = 0; cs < nch; cs += 2) {
-          if (cs + 1 < nch) gather16(vb);
-          store16(va, c++);
-          if (cs + 1 >= nch) break;
-          if (cs + 2 < nch) gather16(va);
-          store16(vb, c++);
-        }
-      } else {
-        for (int cs = 0; cs < nch; ++cs) {
-          gather16(va);
-          store16(va, c++);
-        }
       }
     }
     // ===================== epilogue: TMEM -> registers -> fused output stage -> (B,C,T) =====================
@@ -364,13 +351,13 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, unsigned char* __res
     for (int j = 0; j < 8; ++j) {
       float v = 0.f;
       const int kk = kk0 + j;
+      const int tap = kk / P.cpad, cr = kk % P.cpad;     // tap-major / channel-minor reduction order
       if (col < Ccol) {
         if (MODE == FWD) {
-          if (kk < G.Cin_g * G.K) v = w[((long long)g * G.Cout_g + col) * G.Cin_g * G.K + kk];
-        } else if (im.ntaps > 0) {
-          const int co = kk / im.ntaps, jj = kk % im.ntaps;
-          if (co < G.Cout_g)
-            v = w[(((long long)g * G.Cout_g + co) * G.Cin_g + col) * G.K + im.k0 + jj * im.kstep];
+          if (tap < G.K && cr < G.Cin_g)
+            v = w[(((long long)g * G.Cout_g + col) * G.Cin_g + cr) * G.K + tap];
+        } else if (tap < im.ntaps && cr < G.Cout_g) {
+          v = w[(((long long)g * G.Cout_g + cr) * G.Cin_g + col) * G.K + im.k0 + tap * im.kstep];
         }
       }
       split_bf16(v, hi[j], lo[j]);
@@ -391,20 +378,20 @@ static int fill_tc(TcP& P, const vbx_conv_desc* d, int mode) {
   const int Ccol = mode == FWD ? P.g.Cout_g : P.g.Cin_g;
   P.NT = pick_nt(Ccol);
   P.ntiles_n = (Ccol + P.NT - 1) / P.NT;
+  const int Cred = mode == FWD ? P.g.Cin_g : P.g.Cout_g;
+  P.cpad = Cred >= 5 ? (Cred + 7) / 8 * 8 : (Cred >= 3 ? 4 : Cred);
   if (mode == FWD) {
     P.nphase = 1;
-    P.nchunks = (P.g.Cin_g * P.g.K + kKC - 1) / kKC;
+    P.nchunks = (P.cpad * P.g.K + kKC - 1) / kKC;
   } else {
     P.nphase = P.g.stride;
     int g = gcd_i(P.g.dil, P.g.stride);
     int kstep = P.g.stride / g;
     int max_taps = (P.g.K + kstep - 1) / kstep;
-    P.nchunks = (P.g.Cout_g * max_taps + kKC - 1) / kKC;
+    P.nchunks = (P.cpad * max_taps + kKC - 1) / kKC;
   }
   P.tmem_cols = pow2_cols(P.NT);
   P.stages = pick_stages_for(stage_bytes(P.NT), P.nchunks);
-  static const int pipe_env = getenv("VBX_TC_PIPE") ? atoi(getenv("VBX_TC_PIPE")) : 0;
-  P.pipe = pipe_env;
   return 0;
 }
 
@@ -514,65 +501,73 @@ __global__ void __launch_bounds__(kThreads, 2) tc_wgrad_kernel(const TcW P) {
 
   if (warp < 8) {
     // ===================== producers: dy rows and im2col'd x rows, lanes walk t =====================
-    const uint32_t lane_off = (uint32_t)(lane & 7) * 2;
-    const int ku = lane >> 3;
+    // A half-warp covers the 32 reduction positions of one row (16 lanes x 2 consecutive t); the two
+    // halves take rows 4 apart so that their 4-byte stores land in different banks.  16 rows per pass.
+    const int tp = lane & 15, half = lane >> 4;
+    const int rl = (warp & 3) + 4 * half + 8 * (warp >> 2);          // row within a 16-row pass
+    const int ku = tp >> 2;
+    const uint32_t lane_off = (uint32_t)(tp & 3) * 4;
     const int co_base = mt * kRows;
     const int rows_a = min(kRows, G.Cout_g - co_base);
     const uint32_t lbo_b = (uint32_t)lbo_wb(NT);
     const int kmin = kspan[0], kmax = kspan[1];          // range of k*d - pad over this tile's columns
-    int r = red_lo + lane;
-    int b = r / G.Tout, t = r % G.Tout;
     for (int c = 0; c < nchunks; ++c) {
       const int s = c % S, use = c / S;
-      const bool rv = r < red_hi;
-      const float* dyp = G.DY + ((long long)b * G.Cout + grp * G.Cout_g + co_base) * G.Tout + t;
-      const float* xp = G.X + ((long long)b * G.Cin + grp * G.Cin_g) * G.Tin;
-      const int ts = t * G.stride;
-      const bool interior = rv && ts + kmin >= 0 && ts + kmax < G.Tin;
+      // the two reduction elements of this lane: r, r+1 (may straddle a batch boundary)
+      const int r = red_lo + c * kKC + 2 * tp;
+      const bool v0 = r < red_hi, v1 = r + 1 < red_hi;
+      const int b0 = v0 ? r / G.Tout : 0, t0 = v0 ? r % G.Tout : 0;
+      int b1 = b0, t1 = t0 + 1;
+      if (t1 >= G.Tout) { t1 = 0; ++b1; }
+      if (!v1) { b1 = 0; t1 = 0; }
+      const float* dy0 = G.DY + ((long long)b0 * G.Cout + grp * G.Cout_g + co_base) * G.Tout + t0;
+      const float* dy1 = G.DY + ((long long)b1 * G.Cout + grp * G.Cout_g + co_base) * G.Tout + t1;
+      const float* x0 = G.X + ((long long)b0 * G.Cin + grp * G.Cin_g) * G.Tin;
+      const float* x1 = G.X + ((long long)b1 * G.Cin + grp * G.Cin_g) * G.Tin;
+      const int ts0 = t0 * G.stride, ts1 = t1 * G.stride;
+      const bool interior = v0 && v1 && ts0 + kmin >= 0 && ts0 + kmax < G.Tin && ts1 + kmin >= 0 && ts1 + kmax < G.Tin;
       mbar_wait(&empty[s], (use & 1) ^ 1);
       unsigned char* a_hi = stage0 + (size_t)s * stage_sz + (uint32_t)ku * kLboW + lane_off;
       unsigned char* a_lo = a_hi + plane_a;
       unsigned char* b_hi = stage0 + (size_t)s * stage_sz + 2 * plane_a + (uint32_t)ku * lbo_b + lane_off;
       unsigned char* b_lo = b_hi + plane_bw;
-      // A rows (output channels): warp w takes rows w, w+8, ...
-#pragma unroll 8
-      for (int m = warp; m < kRows; m += 8) {
-        float v = (rv && m < rows_a) ? dyp[m * G.Tout] : 0.f;
-        __nv_bfloat16 hi, lo;
-        split_bf16(v, hi, lo);
-        *reinterpret_cast<__nv_bfloat16*>(a_hi + m * 16) = hi;
-        *reinterpret_cast<__nv_bfloat16*>(a_lo + m * 16) = lo;
+      auto put = [](unsigned char* hi_p, unsigned char* lo_p, float a, float b) {
+        const __nv_bfloat162 hi2 = __floats2bfloat162_rn(a, b);
+        const float2 hf = __bfloat1622float2(hi2);
+        *reinterpret_cast<__nv_bfloat162*>(hi_p) = hi2;
+        *reinterpret_cast<__nv_bfloat162*>(lo_p) = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+      };
+#pragma unroll
+      for (int j = 0; j < kRows / 16; ++j) {
+        const int m = j * 16 + rl;
+        const float a = (v0 && m < rows_a) ? dy0[m * G.Tout] : 0.f;
+        const float b = (v1 && m < rows_a) ? dy1[m * G.Tout] : 0.f;
+        put(a_hi + m * 16, a_lo + m * 16, a, b);
       }
       if (interior) {
-        const float* xt = xp + ts;
-#pragma unroll 8
-        for (int n = warp; n < NT; n += 8) {
+        const float* xt0 = x0 + ts0;
+        const float* xt1 = x1 + ts1;
+#pragma unroll 4
+        for (int n = rl; n < NT; n += 16) {
           const int ro = roff[n];
-          float v = ro != INT_MIN ? xt[ro] : 0.f;
-          __nv_bfloat16 hi, lo;
-          split_bf16(v, hi, lo);
-          *reinterpret_cast<__nv_bfloat16*>(b_hi + n * 16) = hi;
-          *reinterpret_cast<__nv_bfloat16*>(b_lo + n * 16) = lo;
+          const float a = ro != INT_MIN ? xt0[ro] : 0.f;
+          const float b = ro != INT_MIN ? xt1[ro] : 0.f;
+          put(b_hi + n * 16, b_lo + n * 16, a, b);
         }
       } else {
-#pragma unroll 4
-        for (int n = warp; n < NT; n += 8) {
+#pragma unroll 2
+        for (int n = rl; n < NT; n += 16) {
           const int2 ri = rowinfo[n];
-          float v = 0.f;
-          if (rv && ri.y != INT_MIN) {
-            const int p = map_pos(ts + ri.y, G.Tin, G.refl);
-            if (p >= 0) v = xp[ri.x + p];
+          float a = 0.f, b = 0.f;
+          if (ri.y != INT_MIN) {
+            if (v0) { const int p = map_pos(ts0 + ri.y, G.Tin, G.refl); if (p >= 0) a = x0[ri.x + p]; }
+            if (v1) { const int p = map_pos(ts1 + ri.y, G.Tin, G.refl); if (p >= 0) b = x1[ri.x + p]; }
           }
-          __nv_bfloat16 hi, lo;
-          split_bf16(v, hi, lo);
-          *reinterpret_cast<__nv_bfloat16*>(b_hi + n * 16) = hi;
-          *reinterpret_cast<__nv_bfloat16*>(b_lo + n * 16) = lo;
+          put(b_hi + n * 16, b_lo + n * 16, a, b);
         }
       }
       fence_proxy_async();
       mbar_arrive(&full[s]);
-      r += kKC; t += kKC;
-      while (t >= G.Tout) { t -= G.Tout; ++b; }
     }
     // ===================== epilogue: TMEM -> fp32 reductions into dW =====================
     mbar_wait(acc_full, 0);
