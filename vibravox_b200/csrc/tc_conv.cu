@@ -503,8 +503,8 @@ __global__ void __launch_bounds__(kThreads, 2) tc_wgrad_kernel(const TcW P) {
     // ===================== producers: dy rows and im2col'd x rows, lanes walk t =====================
     // A half-warp covers the 32 reduction positions of one row (16 lanes x 2 consecutive t); the two
     // halves take rows 4 apart so that their 4-byte stores land in different banks.  16 rows per pass.
-    const int tp = lane & 15, half = lane >> 4;
-    const int rl = (warp & 3) + 4 * half + 8 * (warp >> 2);          // row within a 16-row pass
+    const int tp = lane & 15, hw = lane >> 4;
+    const int rl = (warp & 3) + 4 * hw + 8 * (warp >> 2);          // row within a 16-row pass
     const int ku = tp >> 2;
     const uint32_t lane_off = (uint32_t)(tp & 3) * 4;
     const int co_base = mt * kRows;
