@@ -151,6 +151,14 @@ VBX_API int vbx_hinge_bwd(const float* c, int64_t n, float target, float scale, 
                   void* stream);
 /* double -> float scalar copy(s) with optional scaling */
 VBX_API int vbx_d2f(const double* src, float* dst, int32_t n, float scale, void* stream);
+/* STFT framing (torch.stft center/reflect semantics restricted to the non-zero window support):
+ * U[b,k,f] = x[b, mirror(f*hop + k - pad)], F = (L + 2*pad - K)/hop + 1; and the adjoint
+ * dx[b,p] = beta*dx[b,p] + sum dU[b,k,f] over the (f,k) that read p.  The DFT itself is then a
+ * pointwise (K=1) conv over the frame axis and runs on the conv kernels. */
+VBX_API int vbx_unfold_frames(const float* x, float* U, int32_t B, int32_t L, int32_t K, int32_t hop, int32_t pad,
+                      void* stream);
+VBX_API int vbx_fold_frames(const float* dU, float* dx, int32_t B, int32_t L, int32_t K, int32_t hop, int32_t pad,
+                    float beta, void* stream);
 /* STFT loss statistics (auraloss.freq.STFTLoss as configured by multi_stft.yaml:1-18).
  * X, Y: (B, 2*bins, F) outputs of the STFT-as-conv (rows [0,bins) real, [bins,2bins) imaginary).
  * stats[0] += sum (ym-xm)^2, stats[1] += sum ym^2, stats[2] += sum |log xm - log ym| (double),

@@ -187,6 +187,21 @@ def d2f(src, scale=1.0):
     return (src * scale).float()
 
 
+def unfold_frames(x, K, hop, pad):
+    xp = F.pad(x, (pad, pad), mode="reflect")
+    return xp.unfold(2, K, hop)[:, 0].transpose(1, 2).contiguous()
+
+
+def fold_frames(dU, L, hop, pad, dx=None):
+    with torch.enable_grad():
+        x0 = torch.zeros(dU.shape[0], 1, L, requires_grad=True)
+        (g,) = torch.autograd.grad(unfold_frames(x0, dU.shape[1], hop, pad), x0, dU)
+    if dx is None:
+        return g
+    dx += g
+    return dx
+
+
 def _mags(X, eps):
     bins = X.shape[1] // 2
     return torch.sqrt(torch.clamp(X[:, :bins] ** 2 + X[:, bins:] ** 2, min=eps))
@@ -262,7 +277,9 @@ _NAMES = [k for k, v in list(globals().items()) if callable(v) and not k.startsw
 def cpu_ops():
     saved = {k: getattr(ops, k) for k in _NAMES}
     saved["TC_ENABLED"] = ops.TC_ENABLED
+    saved["STFT_VIA_FRAMES"] = ops.STFT_VIA_FRAMES
     ops.TC_ENABLED = False
+    ops.STFT_VIA_FRAMES = True
     try:
         for k in _NAMES:
             setattr(ops, k, globals()[k])

@@ -186,11 +186,13 @@ def test_elementwise_and_losses():
     assert float(g1) == 0.5 and float(g2) == 4.0
 
 
-def test_mrstft_loss_and_per_bin_magnitudes():
+@pytest.mark.parametrize("via_frames", [True, False])
+def test_mrstft_loss_and_per_bin_magnitudes(via_frames):
     """north_star: 'per-bin STFT checked element-wise'."""
     from oracle import eben_oracle as O
     from vibravox_b200 import ops
     from vibravox_b200.torch_modules.losses.mrstft_loss import MultiResolutionSTFTLoss
+    ops.STFT_VIA_FRAMES = via_frames
     torch.manual_seed(4)
     B, L = 2, 15840
     x = (0.3 * torch.randn(B, 1, L)).double().requires_grad_(True)      # fp32-representable values
@@ -206,8 +208,9 @@ def test_mrstft_loss_and_per_bin_magnitudes():
     assert torch.allclose(mod.fir_taps.cpu().view(-1), taps, atol=0, rtol=0)
     xc = x.detach().float().to(DEV).requires_grad_(True)
     got = mod(xc, y.float().to(DEV))
-    assert float(got) == pytest.approx(float(want), rel=2e-5)
+    assert float(got) == pytest.approx(float(want), rel=2e-5 if not via_frames else 1e-4)
     (gxc,) = torch.autograd.grad(got, xc)
+    ops.STFT_VIA_FRAMES = ops.TC_ENABLED
     err = (gxc.cpu().double() - gx).norm() / gx.norm()
     print("mrstft grad rel-L2 vs fp64:", float(err), "fp32 oracle:", float(noise))
     assert err < 2 * noise + 1e-4, (float(err), float(noise))
@@ -303,3 +306,22 @@ def test_tensor_core_conv_family_matches_fp64(case):
     dw = ops.tc_conv1d_wgrad(xc, dyc, geom)
     assert (dw.cpu().double() - gw).abs().max() < 2e-4 * float(gw.abs().max())
     assert (dw.cpu().double() - gw).norm() / gw.norm() < 1e-4
+
+
+def test_stft_framing_unfold_fold():
+    from vibravox_b200 import ops
+    import cpu_shim
+    torch.manual_seed(9)
+    for B, L, K, hop in ((2, 4000, 240, 50), (3, 15840, 1200, 240), (1, 700, 600, 120)):
+        pad = K // 2
+        x = torch.randn(B, 1, L)
+        want = cpu_shim.unfold_frames(x, K, hop, pad)
+        got = ops.unfold_frames(x.to(DEV), K, hop, pad)
+        assert got.shape == want.shape and torch.equal(got.cpu(), want)
+        dU = torch.randn_like(want)
+        gw = cpu_shim.fold_frames(dU.double(), L, hop, pad)
+        gg = ops.fold_frames(dU.to(DEV), L, hop, pad)
+        assert (gg.cpu().double() - gw).abs().max() < 1e-5
+        acc = torch.ones(B, 1, L, device=DEV)
+        ops.fold_frames(dU.to(DEV), L, hop, pad, dx=acc)
+        assert (acc.cpu().double() - (gw + 1)).abs().max() < 1e-5

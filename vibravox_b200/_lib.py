@@ -64,6 +64,8 @@ SIGNATURES = {
     "vbx_hinge_fwd": [c_p, c_i64, c_f, c_f, c_p, c_p],
     "vbx_hinge_bwd": [c_p, c_i64, c_f, c_f, c_p, c_p, c_p],
     "vbx_d2f": [c_p, c_p, c_int, c_f, c_p],
+    "vbx_unfold_frames": [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p],
+    "vbx_fold_frames": [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_f, c_p],
     "vbx_stft_stats": [c_p, c_p, c_int, c_int, c_int, c_f, c_p, c_p],
     "vbx_stft_finalize": [c_p, c_p, c_int, c_f, c_p, c_p],
     "vbx_stft_bwd": [c_p, c_p, c_int, c_int, c_int, c_f, c_p, c_d, c_p, c_f, c_p, c_p],

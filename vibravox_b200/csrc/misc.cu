@@ -386,6 +386,44 @@ __global__ void scalar_mul_kernel(const float* go, const float* lam, float* out,
   int i = threadIdx.x;
   if (i < n) out[i] = go[0] * (lam ? lam[i] : 1.f);
 }
+// STFT framing: U[b,k,f] = x[b, map(f*hop + k - pad)] (reflect halo), and its adjoint.
+__global__ void unfold_frames_kernel(const float* __restrict__ x, float* __restrict__ U, int L, int K, int F,
+                                     int hop, int pad) {
+  const int b = blockIdx.z, k = blockIdx.y;
+  const float* xb = x + (long long)b * L;
+  float* out = U + ((long long)b * K + k) * F;
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) {
+    int p = f * hop + k - pad;
+    if (p < 0) p = -p;
+    else if (p >= L) p = 2 * (L - 1) - p;
+    out[f] = (p >= 0 && p < L) ? xb[p] : 0.f;
+  }
+}
+// dx[b,p] (+)= sum over the (f,k) whose (mirrored) position is p of dU[b,k,f]; gather form, no atomics
+__global__ void fold_frames_kernel(const float* __restrict__ dU, float* __restrict__ dx, int L, int K, int F,
+                                   int hop, int pad, float beta) {
+  const int b = blockIdx.y;
+  const float* ub = dU + (long long)b * K * F;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < L; p += gridDim.x * blockDim.x) {
+    float acc = 0.f;
+#pragma unroll
+    for (int img = 0; img < 3; ++img) {
+      int q;
+      if (img == 0) q = p;
+      else if (img == 1) { if (p < 1 || p > pad) continue; q = -p; }
+      else { if (p > L - 2 || p < L - 1 - pad) continue; q = 2 * (L - 1) - p; }
+      const int a = q + pad;                                  // = f*hop + k
+      int f_hi = a / hop;
+      if (f_hi > F - 1) f_hi = F - 1;
+      int f_lo = (a - K + 1 + hop - 1) / hop;
+      if (a - K + 1 <= 0) f_lo = 0;
+      for (int f = f_lo; f <= f_hi; ++f) acc += ub[(long long)(a - f * hop) * F + f];
+    }
+    float* o = dx + (long long)b * L + p;
+    *o = beta != 0.f ? beta * *o + acc : acc;
+  }
+}
+
 // ------------------------------------------------------------------ reductions / optimiser
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, long long n, double* __restrict__ acc) {
   __shared__ double sh[32];
@@ -613,6 +651,26 @@ extern "C" int vbx_stft_bwd(const float* X, const float* Y, int32_t B, int32_t b
   VBX_REQUIRE(B > 0 && bins > 0 && F > 0, VBX_BAD_SHAPE, "stft_bwd: bad shape");
   stft_bwd_kernel<<<stream_blocks((long long)B * bins * F, 1024), 256, 0, ST>>>(X, Y, B, bins, F, eps, stats, count, go, w, dX);
   return launched("stft_bwd_kernel");
+}
+extern "C" int vbx_unfold_frames(const float* x, float* U, int32_t B, int32_t L, int32_t K, int32_t hop,
+                                 int32_t pad, void* stream) {
+  VBX_REQUIRE(x && U, VBX_BAD_POINTER, "unfold_frames: null tensor");
+  VBX_REQUIRE(B > 0 && L > 1 && K > 0 && hop > 0 && pad >= 0 && pad <= L - 1 && K <= 65535 && B <= 65535 &&
+                  L + 2 * pad >= K, VBX_BAD_SHAPE, "unfold_frames: bad shape");
+  const int F = (L + 2 * pad - K) / hop + 1;
+  dim3 grid(cdiv(F, 256), K, B);
+  unfold_frames_kernel<<<grid, 256, 0, ST>>>(x, U, L, K, F, hop, pad);
+  return launched("unfold_frames_kernel");
+}
+extern "C" int vbx_fold_frames(const float* dU, float* dx, int32_t B, int32_t L, int32_t K, int32_t hop,
+                               int32_t pad, float beta, void* stream) {
+  VBX_REQUIRE(dU && dx, VBX_BAD_POINTER, "fold_frames: null tensor");
+  VBX_REQUIRE(B > 0 && L > 1 && K > 0 && hop > 0 && pad >= 0 && pad <= L - 1 && B <= 65535 && L + 2 * pad >= K,
+              VBX_BAD_SHAPE, "fold_frames: bad shape");
+  const int F = (L + 2 * pad - K) / hop + 1;
+  dim3 grid(cdiv(L, 256), B);
+  fold_frames_kernel<<<grid, 256, 0, ST>>>(dU, dx, L, K, F, hop, pad, beta);
+  return launched("fold_frames_kernel");
 }
 extern "C" int vbx_weighted_sum(const float* x0, const float* x1, const float* x2, const float* x3, int32_t n,
                                 const float* lam, float* terms, float* total, void* stream) {

@@ -314,8 +314,15 @@ class MRSTFTFn(Function):
         counts = []
         saved = []
         for r, (geom, basis, _) in enumerate(spec.res):
-            X = ops.conv1d_fwd(xf, basis, geom)
-            Y = ops.conv1d_fwd(yf, basis, geom)
+            if ops.STFT_VIA_FRAMES:
+                # framing + DFT as a pointwise conv over the frame axis on the tensor-core kernel
+                pw = ConvGeom(geom.K, geom.Cout, 1)
+                wpw = basis.view(geom.Cout, geom.K, 1)
+                X = ops.conv_fwd(ops.unfold_frames(xf, geom.K, geom.stride, geom.pad), wpw, pw)
+                Y = ops.conv_fwd(ops.unfold_frames(yf, geom.K, geom.stride, geom.pad), wpw, pw)
+            else:
+                X = ops.conv1d_fwd(xf, basis, geom)
+                Y = ops.conv1d_fwd(yf, basis, geom)
             ops.stft_stats(X, Y, spec.eps, stats[3 * r:3 * r + 3])
             counts.append(float(X.numel() // 2))
             saved += [X, Y]
@@ -344,7 +351,12 @@ class MRSTFTFn(Function):
         for r, (geom, _, basis_k) in enumerate(spec.res):
             X, Y = ctx.saved_tensors[2 * r], ctx.saved_tensors[2 * r + 1]
             dX = ops.stft_bwd(X, Y, spec.eps, stats[3 * r:3 * r + 3], counts[r], go, 1.0 / nres)
-            ops.conv1d_dgrad_scatter(dX, basis_k, geom, L, dxf)
+            if ops.STFT_VIA_FRAMES:
+                pw = ConvGeom(geom.K, geom.Cout, 1)
+                dU = ops.conv_dgrad(dX, spec.res[r][1].view(geom.Cout, geom.K, 1), None, pw, dX.shape[2])
+                ops.fold_frames(dU, L, geom.stride, geom.pad, dx=dxf)
+            else:
+                ops.conv1d_dgrad_scatter(dX, basis_k, geom, L, dxf)
         dx = ops.conv1d_dgrad(dxf, spec.taps, spec.fir_geom, L) if spec.taps is not None else dxf
         return dx.view(B, C, L), None, None
 

@@ -319,6 +319,26 @@ def d2f(src: Tensor, scale: float = 1.0) -> Tensor:
     return dst
 
 
+def unfold_frames(x: Tensor, K: int, hop: int, pad: int) -> Tensor:
+    """(B,1,L) -> (B,K,F) frame matrix, reflect halo `pad` (STFT framing)."""
+    B, C, L = x.shape
+    assert C == 1
+    F = (L + 2 * pad - K) // hop + 1
+    U = torch.empty((B, K, F), device=x.device, dtype=torch.float32)
+    check(_lib.load().vbx_unfold_frames(_p(x), _p(U), B, L, K, hop, pad, _stream()), "vbx_unfold_frames")
+    return U
+
+
+def fold_frames(dU: Tensor, L: int, hop: int, pad: int, dx: Optional[Tensor] = None) -> Tensor:
+    """Adjoint of unfold_frames; accumulates into dx when given."""
+    B, K, F = dU.shape
+    beta = 1.0 if dx is not None else 0.0
+    if dx is None:
+        dx = torch.empty((B, 1, L), device=dU.device, dtype=torch.float32)
+    check(_lib.load().vbx_fold_frames(_p(dU), _p(dx), B, L, K, hop, pad, beta, _stream()), "vbx_fold_frames")
+    return dx
+
+
 def stft_stats(X: Tensor, Y: Tensor, eps: float, stats: Tensor) -> None:
     B, C2, F = X.shape
     assert X.shape == Y.shape and C2 % 2 == 0
@@ -394,6 +414,9 @@ def noise_mix_crop(body: Tensor, air: Tensor, noise: Tensor, start: Tensor, off:
 # kernels.  VBX_TC=0 forces the fp32 FMA kernels everywhere.
 TC_ENABLED = os.environ.get("VBX_TC", "1") != "0"
 TC_FWD, TC_DGRAD = 0, 1
+# STFT as framing (unfold) + a pointwise conv over the frame axis (so that it rides the tensor-core conv
+# kernels) instead of one strided conv with a 240..1200-tap kernel on the FMA path.
+STFT_VIA_FRAMES = TC_ENABLED
 
 
 def use_tc(g: ConvGeom, kind: str) -> bool:
@@ -401,7 +424,7 @@ def use_tc(g: ConvGeom, kind: str) -> bool:
         return False
     cin_g, cout_g = g.Cin // g.groups, g.Cout // g.groups
     if kind == "fwd":
-        return cout_g >= 8
+        return cout_g >= 8 or cin_g * g.K >= 512      # incl. the 1-channel certainty convs (K*Cin = 2-3k)
     if kind == "dgrad":
         return cin_g >= 4
     return cout_g >= 16 and cin_g * g.K >= 8          # wgrad
