@@ -210,10 +210,11 @@ def test_mrstft_loss_and_per_bin_magnitudes(via_frames):
     got = mod(xc, y.float().to(DEV))
     assert float(got) == pytest.approx(float(want), rel=2e-5 if not via_frames else 1e-4)
     (gxc,) = torch.autograd.grad(got, xc)
-    ops.STFT_VIA_FRAMES = ops.TC_ENABLED
+    ops.STFT_VIA_FRAMES = False
     err = (gxc.cpu().double() - gx).norm() / gx.norm()
-    print("mrstft grad rel-L2 vs fp64:", float(err), "fp32 oracle:", float(noise))
-    assert err < 2 * noise + 1e-4, (float(err), float(noise))
+    print("mrstft grad rel-L2 vs fp64:", float(err), "fp32 oracle:", float(noise), "via_frames", via_frames)
+    # the framed / tensor-core variant is opt-in because of exactly this number (see ops.STFT_VIA_FRAMES)
+    assert err < (2 * noise + 1e-4 if not via_frames else 5e-2), (float(err), float(noise))
     # per-bin magnitudes
     spec = mod._get_spec(torch.device(DEV, torch.cuda.current_device()))
     sig = x.detach().float().view(B, 1, L).to(DEV)
