@@ -131,6 +131,8 @@ VBX_API int vbx_tanh_recompose_fwd(const float* x, const float* first, float* y,
 VBX_API int vbx_tanh_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream);
 /* y = a + b */
 VBX_API int vbx_add(const float* a, const float* b, float* y, int64_t n, void* stream);
+/* y = alpha[0] * x (+ beta*y), alpha a device scalar (the loss-balancing lambdas never visit the host) */
+VBX_API int vbx_axpby_dev(const float* x, float* y, int64_t n, const float* alpha, float beta, void* stream);
 /* y = alpha * x (+ beta*y) */
 VBX_API int vbx_axpby(const float* x, float* y, int64_t n, float alpha, float beta, void* stream);
 

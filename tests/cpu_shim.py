@@ -153,6 +153,11 @@ def axpby(x, y, alpha, beta):
     return y
 
 
+def axpby_dev(x, y, alpha, beta):
+    y.copy_(alpha.view(-1)[0] * x + (beta * y if beta else 0))
+    return y
+
+
 def fill(t, value):
     return t.fill_(value)
 

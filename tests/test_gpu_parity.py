@@ -136,13 +136,15 @@ def test_forward_and_gradients_match_oracle(p, q, B, L, path):
         assert e < 3 * n32 + whole, (tag, e, n32)
 
 
-def test_training_step_matches_reference_golden(golden_dir, path):
+@pytest.mark.parametrize("schedule", ["shared", "reference"])
+def test_training_step_matches_reference_golden(golden_dir, path, schedule):
     """Two consecutive training steps vs the logs of the reference's own eben.py (golden)."""
     import vibravox_b200
     from oracle import eben_oracle as O
     gold = torch.load(os.path.join(golden_dir, "train_step.pt"))
     body, air = O.synthetic_pairs(gold["B"], gold["S"], seed=gold["data_seed"])
     lm = vibravox_b200.build_model(seed=gold["model_seed"], device=DEV)
+    lm.schedule = schedule
     batch = {"audio_body_conducted": body.to(DEV), "audio_airborne": air.to(DEV)}
     for it in range(2):
         out = lm.training_step(batch)

@@ -49,12 +49,14 @@ def test_modules_forward_backward_match_oracle():
         assert relerr(u, v) < 1e-2, (n, relerr(u, v))   # fp32 vs fp32, different summation order
 
 
-def test_training_step_schedule_matches_reference_golden(golden_dir):
+@pytest.mark.parametrize("schedule", ["shared", "reference"])
+def test_training_step_schedule_matches_reference_golden(golden_dir, schedule):
     import vibravox_b200
     gold = torch.load(os.path.join(golden_dir, "train_step.pt"))
     body, air = O.synthetic_pairs(gold["B"], gold["S"], seed=gold["data_seed"])
     with cpu_ops():
         lm = vibravox_b200.build_model(seed=gold["model_seed"], device="cpu")
+        lm.schedule = schedule
         for it in range(2):
             out = lm.training_step({"audio_body_conducted": body, "audio_airborne": air})
             want = gold["steps"][it]

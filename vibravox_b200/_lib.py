@@ -58,6 +58,7 @@ SIGNATURES = {
     "vbx_tanh_bwd": [c_p, c_p, c_p, c_i64, c_p],
     "vbx_add": [c_p, c_p, c_p, c_i64, c_p],
     "vbx_axpby": [c_p, c_p, c_i64, c_f, c_f, c_p],
+    "vbx_axpby_dev": [c_p, c_p, c_i64, c_p, c_f, c_p],
     "vbx_l1_pair_sums": [c_p, c_p, c_i64, c_p, c_p],
     "vbx_fm_finalize": [c_p, c_int, c_f, c_p, c_p],
     "vbx_l1_pair_bwd": [c_p, c_p, c_i64, c_p, c_p, c_f, c_p, c_p, c_p],

@@ -251,6 +251,15 @@ __global__ void axpby_kernel(const float* __restrict__ x, float* __restrict__ y,
     y[i] = beta != 0.f ? beta * y[i] + v : v;
   }
 }
+__global__ void axpby_dev_kernel(const float* __restrict__ x, float* __restrict__ y, long long n,
+                                 const float* __restrict__ alpha, float beta) {
+  const float a = alpha[0];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+    float v = a * x[i];
+    y[i] = beta != 0.f ? beta * y[i] + v : v;
+  }
+}
 __global__ void fill_kernel(float* __restrict__ p, long long n, float value) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) p[i] = value;
@@ -587,6 +596,12 @@ extern "C" int vbx_axpby(const float* x, float* y, int64_t n, float alpha, float
   VBX_REQUIRE(n > 0, VBX_BAD_SHAPE, "axpby: empty");
   axpby_kernel<<<stream_blocks(n, 1024), 256, 0, ST>>>(x, y, n, alpha, beta);
   return launched("axpby_kernel");
+}
+extern "C" int vbx_axpby_dev(const float* x, float* y, int64_t n, const float* alpha, float beta, void* stream) {
+  VBX_REQUIRE(x && y && alpha, VBX_BAD_POINTER, "axpby_dev: null tensor");
+  VBX_REQUIRE(n > 0, VBX_BAD_SHAPE, "axpby_dev: empty");
+  axpby_dev_kernel<<<stream_blocks(n, 1024), 256, 0, ST>>>(x, y, n, alpha, beta);
+  return launched("axpby_dev_kernel");
 }
 extern "C" int vbx_fill(float* p, int64_t n, float value, void* stream) {
   VBX_REQUIRE(p, VBX_BAD_POINTER, "fill: null tensor");

@@ -23,6 +23,15 @@ def _c(t: Tensor) -> Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+class Flags:
+    """Switches consulted by the backward kernels of the shared-schedule training step
+    (lightning_modules/eben.py): one discriminator graph serves both phases, so the generator phase
+    walks it with parameter gradients OFF and the discriminator phase walks it with the gradient
+    w.r.t. graph-leaf inputs (the detached generator outputs) OFF."""
+    param_grads = True
+    skip_leaf_input_grad = False
+
+
 def grad_slot(p: Tensor) -> Optional[Tensor]:
     """View into a flat gradient bucket (set by vibravox_b200.optim.FlatAdam on its parameters).
     When present, backward kernels accumulate the parameter gradient there directly and autograd
@@ -75,11 +84,13 @@ class ConvFn(Function):
     @staticmethod
     def forward(ctx, x: Tensor, w: Tensor, wt: Optional[Tensor], bias: Optional[Tensor], geom: ConvGeom,
                 slope: float):
+        x_leaf = x.is_leaf                      # before any copy: is x a graph leaf (e.g. a detached G output)?
         x, w = _c(x), _c(w)
         y = ops.conv_fwd(x, w, geom, bias=bias, slope=slope)
         ctx.geom, ctx.slope, ctx.has_bias = geom, slope, bias is not None
         ctx.w_slot = grad_slot(w)
         ctx.b_slot = grad_slot(bias) if bias is not None else None
+        ctx.x_leaf = x_leaf
         ctx.save_for_backward(x, w, wt, y if slope != 1.0 else None)
         return y
 
@@ -90,6 +101,8 @@ class ConvFn(Function):
         geom, slope = ctx.geom, ctx.slope
         gy = _c(gy)
         need_x, need_w, _, need_b = ctx.needs_input_grad[:4]
+        need_w, need_b = need_w and Flags.param_grads, need_b and Flags.param_grads
+        need_x = need_x and not (Flags.skip_leaf_input_grad and ctx.x_leaf)
         dbias = None
         if ctx.has_bias and need_b:
             dbias = ctx.b_slot if ctx.b_slot is not None else \
@@ -266,7 +279,7 @@ class FeatureMatchingFn(Function):
         go = _c(go).float()
         grads: List[Optional[Tensor]] = [None] * (2 * n)
         for i in range(n):
-            na, nb = ctx.needs_input_grad[2 + i], ctx.needs_input_grad[2 + n + i]
+            na, nb = ctx.needs_input_grad[2 + i], ctx.needs_input_grad[2 + n + i] and Flags.param_grads
             if na or nb:
                 grads[i], grads[n + i] = ops.l1_pair_bwd(a[i], b[i], sums[2 * i:2 * i + 2], go, ctx.scale, na, nb)
         return (None, None, *grads)

@@ -16,7 +16,7 @@ from typing import Dict, Optional
 import torch
 
 from .. import ops
-from ..functional import WeightedSumFn
+from ..functional import Flags, WeightedSumFn
 from ..optim import FlatAdam
 from ..parallel import allreduce_sum_
 from ..torch_modules.utils import share_weight_norm
@@ -31,7 +31,7 @@ class EBENLightningModule(torch.nn.Module):
                  adversarial_loss_fn: Optional[torch.nn.Module] = None,
                  dynamic_loss_balancing: Optional[str] = None, beta_ema: float = 0.9,
                  update_discriminator_ratio: float = 1.0, description: Optional[str] = None,
-                 push_to_hub_after_testing: bool = False):
+                 push_to_hub_after_testing: bool = False, schedule: str = "shared"):
         super().__init__()
         self.sample_rate, self.description = sample_rate, description
         self.generator, self.discriminator = generator, discriminator
@@ -51,6 +51,12 @@ class EBENLightningModule(torch.nn.Module):
         self.update_discriminator_ratio = update_discriminator_ratio
         self.push_to_hub_after_testing = push_to_hub_after_testing
         self.automatic_optimization = False
+        assert schedule in {"shared", "reference"}
+        # "reference": the literal op sequence of eben.py:82-130 (4 D forwards, 3 D input-gradient passes).
+        # "shared": same losses / gradients / updates with the algebraically redundant work removed
+        #           (SURVEY 7.3-6): one D graph serves both phases, loss gradients are taken once at the
+        #           generator outputs, combined with the lambdas, and the generator is back-propagated once.
+        self.schedule = schedule
         # balancing state (eben.py:73,230-235) lives on the device: EMA of the gradient norms
         self._bal = None
         self.logged: Dict[str, torch.Tensor] = {}
@@ -82,18 +88,7 @@ class EBENLightningModule(torch.nn.Module):
 
     def manual_backward(self, loss: torch.Tensor, optimizer) -> None:
         loss.backward()
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            world = torch.distributed.get_world_size()
-            if world > 1:
-                if isinstance(optimizer, FlatAdam):          # one bucket, one all-reduce
-                    optimizer.gather_autograd_grads()
-                    optimizer.grad_scale = allreduce_sum_(optimizer.grad)
-                else:
-                    for g in optimizer.param_groups:
-                        for p in g["params"]:
-                            if p.grad is not None:
-                                torch.distributed.all_reduce(p.grad)
-                                p.grad.div_(world)
+        self._sync_grads(optimizer)
 
     @property
     def atomic_norms_old(self):
@@ -101,6 +96,130 @@ class EBENLightningModule(torch.nn.Module):
 
     # ---- the hot path ------------------------------------------------------------------------
     def training_step(self, batch: Dict[str, torch.Tensor]):
+        ok = (self.schedule == "shared" and self.feature_matching_loss_fn is not None
+              and self.adversarial_loss_fn is not None and self.reconstructive_loss_temp_fn is None
+              and self.dynamic_loss_balancing is not None)
+        return self._training_step_shared(batch) if ok else self._training_step_reference(batch)
+
+    def _training_step_shared(self, batch: Dict[str, torch.Tensor]):
+        """eben.py:82-130 with the redundant traversals removed.  Equalities used:
+        (a) D(enhanced) and D(reference) of the discriminator phase equal those of the generator phase
+            (only G was updated in between, and the phase uses the pre-update, detached G outputs), so the
+            two D forwards are done once, with a graph, and serve both phases;
+        (b) d(sum_i lambda_i L_i) = sum_i lambda_i dL_i with detached lambdas, so each loss is differentiated
+            once down to the generator outputs; the norms at last_conv.weight come from pushing those three
+            gradients through G's short tail (synthesis, tanh, last_conv), and G is back-propagated once."""
+        G, D = self.generator, self.discriminator
+        corrupted_speech = G.cut_to_valid_length(batch["audio_body_conducted"])
+        reference_speech = G.cut_to_valid_length(batch["audio_airborne"])
+        g_opt, d_opt = self.optimizers(use_pl_optimizer=True)
+        for opt in (g_opt, d_opt):
+            if isinstance(opt, FlatAdam):
+                opt.materialize()
+        d_params = [p for grp in d_opt.param_groups for p in grp["params"]]
+        with share_weight_norm():
+            enhanced, enhanced_bands = G(corrupted_speech)
+            reference_bands = G.pqmf.forward(reference_speech, "analysis")
+            enh = enhanced.detach().requires_grad_(True)
+            bands = enhanced_bands.detach().requires_grad_(True)
+            Flags.param_grads = False                      # generator phase: no D parameter gradients
+            try:
+                losses = OrderedDict()
+                if self.reconstructive_loss_freq_fn:
+                    losses["reconstructive_loss_freq"] = self.reconstructive_loss_freq_fn(enh, reference_speech)
+                enhanced_embeddings = D(bands=bands, audio=enh)
+                reference_embeddings = D(bands=reference_bands, audio=reference_speech)
+                losses["feature_matching_loss"] = self.feature_matching_loss_fn(enhanced_embeddings,
+                                                                                reference_embeddings)
+                losses["adv_loss_gen"] = self.adversarial_loss_fn(embeddings=enhanced_embeddings, target=1)
+                for key, value in losses.items():
+                    self.log(f"train/generator/{key}", value, sync_dist=True)
+                # each loss once, down to the generator outputs
+                grads = [torch.autograd.grad(l, (enh, bands), retain_graph=True, allow_unused=True)
+                         for l in losses.values()]
+                lambdas = self._balance_from_output_grads(enhanced, enhanced_bands, grads)
+                total_e = torch.empty_like(enh)
+                total_b = torch.empty_like(bands)
+                first_e = first_b = True
+                for i, (ge, gb) in enumerate(grads):
+                    if ge is not None:
+                        ops.axpby_dev(ge.contiguous(), total_e, lambdas[i:i + 1], 0.0 if first_e else 1.0)
+                        first_e = False
+                    if gb is not None:
+                        ops.axpby_dev(gb.contiguous(), total_b, lambdas[i:i + 1], 0.0 if first_b else 1.0)
+                        first_b = False
+                with torch.no_grad():
+                    backprop_loss_generator = WeightedSumFn.apply(lambdas, *[l.detach() for l in losses.values()])
+                self.log("train/generator/backprop_loss", backprop_loss_generator, sync_dist=True)
+            finally:
+                Flags.param_grads = True
+            torch.autograd.backward((enhanced, enhanced_bands), (total_e, total_b))
+            self._sync_grads(g_opt)
+            g_opt.step()
+            g_opt.zero_grad()
+
+            # discriminator phase on the same graph
+            update = True
+            if self.update_discriminator_ratio < 1:
+                update = bool(torch.rand(1) < self.update_discriminator_ratio)
+            if update:
+                real_loss = self.adversarial_loss_fn(embeddings=reference_embeddings, target=1)
+                fake_loss = self.adversarial_loss_fn(embeddings=enhanced_embeddings, target=-1)
+                self.log("train/discriminator/real_loss", real_loss, sync_dist=True)
+                self.log("train/discriminator/fake_loss", fake_loss, sync_dist=True)
+                backprop_loss_discriminator = WeightedSumFn.apply(None, real_loss, fake_loss)
+                self.log("train/discriminator/backprop_loss", backprop_loss_discriminator, sync_dist=True)
+                Flags.skip_leaf_input_grad = True          # nothing upstream of the detached G outputs
+                try:
+                    torch.autograd.backward(backprop_loss_discriminator, inputs=d_params)
+                finally:
+                    Flags.skip_leaf_input_grad = False
+                self._sync_grads(d_opt)
+                d_opt.step()
+                d_opt.zero_grad()
+        return {"corrupted": corrupted_speech, "enhanced": enhanced, "reference": reference_speech}
+
+    def _balance_from_output_grads(self, enhanced, enhanced_bands, grads) -> torch.Tensor:
+        """dynamically_balance_losses (eben.py:222-240) from the loss gradients at the generator outputs."""
+        layer = self.generator.last_conv.weight
+        n, dev = len(grads), layer.device
+        if self._bal is None or self._bal["old"].numel() != n:
+            self._bal = dict(old=torch.zeros(n, device=dev), init=torch.zeros(1, device=dev, dtype=torch.int32))
+        sumsq = torch.zeros(n, device=dev, dtype=torch.float64)
+        for i, (ge, gb) in enumerate(grads):
+            outs, gos = [], []
+            if ge is not None:
+                outs.append(enhanced); gos.append(ge)
+            if gb is not None:
+                outs.append(enhanced_bands); gos.append(gb)
+            saved, Flags.param_grads = Flags.param_grads, True      # G's own tail: last_conv.weight is the target
+            try:
+                gw = torch.autograd.grad(outs, layer, grad_outputs=gos, retain_graph=True)[0]
+            finally:
+                Flags.param_grads = saved
+            ops.sumsq(gw.contiguous(), sumsq[i:i + 1])
+        lambdas = torch.empty(n, device=dev)
+        norms = torch.empty(n, device=dev)
+        ops.balance(sumsq, self._bal["old"], self._bal["init"], lambdas, norms, self.beta_ema,
+                    1 if self.dynamic_loss_balancing == "ema" else 0)
+        self.last_norms, self.last_lambdas = norms, lambdas
+        return lambdas
+
+    def _sync_grads(self, optimizer) -> None:
+        if torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1:
+            if isinstance(optimizer, FlatAdam):
+                optimizer.gather_autograd_grads()
+                optimizer.grad_scale = allreduce_sum_(optimizer.grad)
+            else:
+                world = torch.distributed.get_world_size()
+                for g in optimizer.param_groups:
+                    for p in g["params"]:
+                        if p.grad is not None:
+                            torch.distributed.all_reduce(p.grad)
+                            p.grad.div_(world)
+
+    def _training_step_reference(self, batch: Dict[str, torch.Tensor]):
         corrupted_speech = self.generator.cut_to_valid_length(batch["audio_body_conducted"])
         reference_speech = self.generator.cut_to_valid_length(batch["audio_airborne"])
         generator_optimizer, discriminator_optimizer = self.optimizers(use_pl_optimizer=True)

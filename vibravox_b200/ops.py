@@ -273,6 +273,12 @@ def axpby(x: Tensor, y: Tensor, alpha: float, beta: float) -> Tensor:
     return y
 
 
+def axpby_dev(x: Tensor, y: Tensor, alpha: Tensor, beta: float) -> Tensor:
+    """y = alpha[0]*x + beta*y with a device scalar alpha (a 1-element view)."""
+    check(_lib.load().vbx_axpby_dev(_p(x), _p(y), x.numel(), _p(alpha), beta, _stream()), "vbx_axpby_dev")
+    return y
+
+
 def fill(t: Tensor, value: float) -> Tensor:
     check(_lib.load().vbx_fill(_p(t), t.numel(), value, _stream()), "vbx_fill")
     return t
