@@ -65,7 +65,10 @@ inline int pow2_cols(int n) { int c = 32; while (c < n) c <<= 1; return c; }
 // overlaps the other's main loop.
 static const int kSmemMax = 225 * 1024;
 inline int pick_stages_for(int stage_sz, int nchunks) {
-  const int budget = 108 * 1024;
+  // shared-memory budget per CTA: three CTAs per SM (more producer warps in flight) unless a single stage
+  // is already > 36 KB (N = 256 tiles), where two CTAs per SM is the most that fits
+  static const int small_kb = getenv("VBX_TC_BUDGET_KB") ? atoi(getenv("VBX_TC_BUDGET_KB")) : 72;
+  const int budget = (2 * stage_sz > small_kb * 1024 ? 108 : small_kb) * 1024;
   int s = budget / stage_sz;
   const int cap = 4;
   s = s > cap ? cap : s;
@@ -85,7 +88,7 @@ __device__ __forceinline__ float finish(const GemmP& P, float v, int ch, long lo
 // MODE FWD  : rows (b,t),  cols co, reduction (ci,k):  A = x[b,ci,map(t*s + k*d - pad)]
 // MODE DGRAD: rows (b,u) of one phase, cols ci, reduction (co,j): A = dy[b,co,(u+pad-k*d)/s]
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 2) tc_conv_kernel(const TcP P) {
+__global__ void __launch_bounds__(kThreads, 3) tc_conv_kernel(const TcP P) {
   extern __shared__ __align__(128) unsigned char smem[];
   const GemmP& G = P.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -447,7 +450,7 @@ struct TcW {
 __host__ __device__ inline int lbo_wb(int NT) { return NT * 16 + 16; }
 __host__ __device__ inline int wstage_bytes(int NT) { return 2 * 4 * kLboW + 2 * 4 * lbo_wb(NT); }
 
-__global__ void __launch_bounds__(kThreads, 2) tc_wgrad_kernel(const TcW P) {
+__global__ void __launch_bounds__(kThreads, 3) tc_wgrad_kernel(const TcW P) {
   extern __shared__ __align__(128) unsigned char smem[];
   const GemmP& G = P.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
