@@ -218,7 +218,7 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
         "config": {"workload": f"EBEN BWE full train step (gen+disc+MR-STFT/FM/hinge, EMA balancing, 2x Adam) "
                                f"bs={B}x{args.seconds:g}s@16kHz per GPU (L={L} after cut_to_valid_length), "
-                               f"m=4 n=32 p=2 q=4 min_channels=24, reference schedule",
+                               f"m=4 n=32 p=2 q=4 min_channels=24, schedule={lm.schedule}",
                    "batch_per_gpu": B, "samples": L, "parallelism": f"dp{world}",
                    "l2": "per-step working set (activations ~ GBs) >> 126 MB L2; no explicit flush"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
@@ -227,6 +227,13 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, bounded=True)
     print(json.dumps(line), flush=True)
+
+
+def _shutdown():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def cpu_baseline(args, bounded: bool):
@@ -291,6 +298,7 @@ def main():
         run_reference(args)
     else:
         run_ours(args)
+        _shutdown()
 
 
 if __name__ == "__main__":
