@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define VBX_ABI_VERSION 1
+#define VBX_ABI_VERSION 2
 #if defined(__GNUC__)
 #define VBX_API __attribute__((visibility("default")))
 #else
@@ -76,15 +76,18 @@ VBX_API int vbx_conv1d_dgrad_scatter(const vbx_conv_desc* d, const float* dy, co
                              void* stream);
 /* ---- tensor-core (tcgen05 / TMEM) variants of the same contractions, bf16x3 split operands, fp32
  * accumulate.  Weights are pre-packed once per weight update into K-major bf16 hi/lo tiles
- * (vbx_tc_*_pack_bytes gives the buffer size, -1 on a bad descriptor); activations stay fp32 (B,C,T). */
-/* mode 0 = forward pack (columns = output channels), 1 = dgrad pack (columns = input channels, one
- * tile set per stride phase).  w is the plain W[co][ci_g][k]. */
-VBX_API int64_t vbx_tc_pack_bytes(const vbx_conv_desc* d, int32_t mode);
-VBX_API int vbx_tc_pack(const vbx_conv_desc* d, int32_t mode, const float* w, void* packed, void* stream);
+ * (vbx_tc_pack_bytes gives the buffer size, -1 on a bad descriptor); activations stay fp32 (B,C,T).
+ * mode 0 = forward pack (columns = output channels), 1 = dgrad pack (columns = input channels, one
+ * tile set per stride phase).  w is the plain W[co][ci_g][k].
+ * nsplit = bf16 components per operand: 2 -> hi+lo, 3 MMAs per product ("bf16x3", 16 mantissa bits);
+ * 3 -> hi+mid+lo, 6 MMAs ("bf16x6", 24 bits = fp32-grade; used where a log / division amplifies rounding). */
+VBX_API int64_t vbx_tc_pack_bytes(const vbx_conv_desc* d, int32_t mode, int32_t nsplit);
+VBX_API int vbx_tc_pack(const vbx_conv_desc* d, int32_t mode, int32_t nsplit, const float* w, void* packed,
+                void* stream);
 VBX_API int vbx_tc_conv1d_fwd(const vbx_conv_desc* d, const float* x, const void* packed, const vbx_epilogue* e,
-                      float* y, void* stream);
+                      float* y, int32_t nsplit, void* stream);
 VBX_API int vbx_tc_conv1d_dgrad(const vbx_conv_desc* d, const float* dy, const void* packed, const vbx_epilogue* e,
-                        float* dx, void* stream);
+                        float* dx, int32_t nsplit, void* stream);
 /* dw += sum dy*x on tensor cores (both operands gathered from the fp32 activations; nothing packed) */
 VBX_API int vbx_tc_conv1d_wgrad(const vbx_conv_desc* d, const float* x, const float* dy, float* dw, void* stream);
 /* W[co][ci_g][k] -> Wt[g][ci_g][co_g][k]  (layout for vbx_conv1d_dgrad) */

@@ -35,7 +35,7 @@ def _epi(v, bias, res, slope, want_mask, out, beta):
     return (v, mask) if want_mask else v
 
 
-def conv1d_fwd(x, w, g, bias=None, res=None, slope=1.0, want_mask=False, out=None, beta=0.0):
+def conv1d_fwd(x, w, g, bias=None, res=None, slope=1.0, want_mask=False, out=None, beta=0.0, nsplit=2):
     return _epi(_conv(x, w, g), bias, res, slope, want_mask, out, beta)
 
 
@@ -44,7 +44,7 @@ def _untranspose(wt, g):
     return wt.reshape(g.groups, Cin_g, Cout_g, g.K).permute(0, 2, 1, 3).reshape(g.Cout, Cin_g, g.K)
 
 
-def conv1d_dgrad(dy, wt, g, Tin, res=None, slope=1.0, out=None, beta=0.0, bias=None):
+def conv1d_dgrad(dy, wt, g, Tin, res=None, slope=1.0, out=None, beta=0.0, bias=None, nsplit=2):
     with torch.enable_grad():
         x0 = torch.zeros(dy.shape[0], g.Cin, Tin, requires_grad=True)
         (dx,) = torch.autograd.grad(_conv(x0, _untranspose(wt, g), g), x0, dy)

@@ -21,10 +21,10 @@ def path(request):
     """Run every parity test on both contraction paths: tcgen05 tensor cores with bf16x3 split operands
     (the default) and the fp32 FMA kernels (VBX_TC=0)."""
     from vibravox_b200 import ops
-    old = ops.TC_ENABLED
-    ops.TC_ENABLED = request.param == "tc"
+    old = ops.TC_ENABLED, ops.STFT_VIA_FRAMES
+    ops.TC_ENABLED = ops.STFT_VIA_FRAMES = request.param == "tc"
     yield request.param
-    ops.TC_ENABLED = old
+    ops.TC_ENABLED, ops.STFT_VIA_FRAMES = old
 
 
 def build(seed=42, p=2, q=4):

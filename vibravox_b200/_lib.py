@@ -14,7 +14,7 @@ import torch  # noqa: F401  (must precede the CDLL load, see module docstring)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvbx_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 c_int, c_i64, c_f, c_d, c_p = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double, ctypes.c_void_p
 
@@ -42,10 +42,10 @@ SIGNATURES = {
     "vbx_conv1d_dgrad": [_PD, c_p, c_p, _PE, c_p, c_p],
     "vbx_conv1d_wgrad": [_PD, c_p, c_p, c_p, c_p],
     "vbx_conv1d_dgrad_scatter": [_PD, c_p, c_p, c_p, c_p],
-    "vbx_tc_pack_bytes": [_PD, c_int],
-    "vbx_tc_pack": [_PD, c_int, c_p, c_p, c_p],
-    "vbx_tc_conv1d_fwd": [_PD, c_p, c_p, _PE, c_p, c_p],
-    "vbx_tc_conv1d_dgrad": [_PD, c_p, c_p, _PE, c_p, c_p],
+    "vbx_tc_pack_bytes": [_PD, c_int, c_int],
+    "vbx_tc_pack": [_PD, c_int, c_int, c_p, c_p, c_p],
+    "vbx_tc_conv1d_fwd": [_PD, c_p, c_p, _PE, c_p, c_int, c_p],
+    "vbx_tc_conv1d_dgrad": [_PD, c_p, c_p, _PE, c_p, c_int, c_p],
     "vbx_tc_conv1d_wgrad": [_PD, c_p, c_p, c_p, c_p],
     "vbx_transpose_weight": [c_p, c_p, c_int, c_int, c_int, c_int, c_p],
     "vbx_weight_norm_fwd": [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p],

@@ -41,6 +41,7 @@ struct TcP {
   int NT, ntiles_n, nchunks, tmem_cols, stages;
   int nphase;       // DGRAD: packed tiles are indexed [g][nt][phase][chunk], nchunks = chunks per phase
   int cpad;         // reduction channels padded to a multiple of 8 (or to 1/2/4): kk = tap*cpad + channel
+  int nsplit;       // bf16 components per operand: 2 = hi+lo, 3 MMAs (16 mantissa bits); 3 = hi+mid+lo, 6 MMAs (24 bits)
 };
 
 // one reduction segment of a tile: FWD has one; DGRAD has one per mirror image it touches
@@ -50,7 +51,7 @@ struct Seg {
 };
 
 __host__ __device__ inline int plane_b(int NT) { return NT * 64; }                 // NT rows x 32 bf16
-__host__ __device__ inline int stage_bytes(int NT) { return 2 * kPlaneA + 2 * plane_b(NT); }
+__host__ __device__ inline int stage_bytes(int NT, int nsplit = 2) { return nsplit * (kPlaneA + plane_b(NT)); }
 
 inline int pick_nt(int Cn) {
   int r = (Cn + 15) / 16 * 16;
@@ -92,8 +93,8 @@ __global__ void __launch_bounds__(kThreads, 3) tc_conv_kernel(const TcP P) {
   extern __shared__ __align__(128) unsigned char smem[];
   const GemmP& G = P.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int S = P.stages, NT = P.NT;
-  const int stage_sz = stage_bytes(NT);
+  const int S = P.stages, NT = P.NT, NS = P.nsplit;
+  const int stage_sz = stage_bytes(NT, NS);
   unsigned char* stage0 = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_sz);
   uint64_t* full_a = bars;
@@ -228,9 +229,14 @@ __global__ void __launch_bounds__(kThreads, 3) tc_conv_kernel(const TcP P) {
         for (int i = 0; i < 8; ++i) {
           const __nv_bfloat162 hi2 = __floats2bfloat162_rn(xa[i], xb[i]);      // .x = row r0, .y = row r0+1
           const float2 hf = __bfloat1622float2(hi2);
-          const __nv_bfloat162 lo2 = __floats2bfloat162_rn(xa[i] - hf.x, xb[i] - hf.y);
+          const float ra = xa[i] - hf.x, rb = xb[i] - hf.y;
+          const __nv_bfloat162 lo2 = __floats2bfloat162_rn(ra, rb);
           *reinterpret_cast<__nv_bfloat162*>(a_hi + i * 16) = hi2;
           *reinterpret_cast<__nv_bfloat162*>(a_lo + i * 16) = lo2;
+          if (NS == 3) {
+            const float2 mf = __bfloat1622float2(lo2);
+            *reinterpret_cast<__nv_bfloat162*>(a_lo + kPlaneA + i * 16) = __floats2bfloat162_rn(ra - mf.x, rb - mf.y);
+          }
         }
         fence_proxy_async();
         mbar_arrive(&full_a[s]);
@@ -286,18 +292,26 @@ __global__ void __launch_bounds__(kThreads, 3) tc_conv_kernel(const TcP P) {
           mbar_wait(&full_a[s], use & 1);
           mbar_wait(&full_b[s], use & 1);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(stage0 + (size_t)s * stage_sz), a_lo = a_hi + kPlaneA;
-          const uint32_t b_hi = a_hi + 2 * kPlaneA, b_lo = b_hi + plane_b(NT);
+          const uint32_t a0 = smem_u32(stage0 + (size_t)s * stage_sz);
+          const uint32_t b0 = a0 + NS * kPlaneA;
 #pragma unroll
           for (int ks = 0; ks < kKC / 16; ++ks) {
-            const uint64_t da_hi = make_desc(a_hi + ks * 2 * kLboA, kLboA, kSboA);
-            const uint64_t da_lo = make_desc(a_lo + ks * 2 * kLboA, kLboA, kSboA);
-            const uint64_t db_hi = make_desc(b_hi + ks * 2 * lbo_b, lbo_b, 128);
-            const uint64_t db_lo = make_desc(b_lo + ks * 2 * lbo_b, lbo_b, 128);
-            mma_bf16_ss(tmem_base, da_hi, db_hi, idesc, accumulate);
+            uint64_t da[3], db[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              da[i] = make_desc(a0 + i * kPlaneA + ks * 2 * kLboA, kLboA, kSboA);
+              db[i] = make_desc(b0 + i * plane_b(NT) + ks * 2 * lbo_b, lbo_b, 128);
+            }
+            // all component products a_i * b_j with i + j < NS (the dropped ones are below 2^-8NS relative)
+            mma_bf16_ss(tmem_base, da[0], db[0], idesc, accumulate);
             accumulate = 1;
-            mma_bf16_ss(tmem_base, da_hi, db_lo, idesc, 1);
-            mma_bf16_ss(tmem_base, da_lo, db_hi, idesc, 1);
+            mma_bf16_ss(tmem_base, da[0], db[1], idesc, 1);
+            mma_bf16_ss(tmem_base, da[1], db[0], idesc, 1);
+            if (NS == 3) {
+              mma_bf16_ss(tmem_base, da[0], db[2], idesc, 1);
+              mma_bf16_ss(tmem_base, da[2], db[0], idesc, 1);
+              mma_bf16_ss(tmem_base, da[1], db[1], idesc, 1);
+            }
           }
           mma_commit(&empty[s]);       // frees the stage once these MMAs have read it
         }
@@ -308,7 +322,7 @@ __global__ void __launch_bounds__(kThreads, 3) tc_conv_kernel(const TcP P) {
   } else {
     // ===================== weight tiles: linear bulk copies (TMA engine) =====================
     if (lane == 0) {
-      const uint32_t bytes = 2u * (uint32_t)plane_b(NT);
+      const uint32_t bytes = (uint32_t)NS * (uint32_t)plane_b(NT);
       int c = 0;
       for (int sg = 0; sg < nseg; ++sg) {
         const Seg seg = segs[sg];
@@ -318,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, 3) tc_conv_kernel(const TcP P) {
           const int s = c % S, use = c / S;
           mbar_wait(&empty[s], (use & 1) ^ 1);
           mbar_expect_tx(&full_b[s], bytes);
-          bulk_copy_g2s(stage0 + (size_t)s * stage_sz + 2 * kPlaneA, src + (size_t)cs * bytes, bytes, &full_b[s]);
+          bulk_copy_g2s(stage0 + (size_t)s * stage_sz + NS * kPlaneA, src + (size_t)cs * bytes, bytes, &full_b[s]);
         }
       }
     }
@@ -349,7 +363,7 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, unsigned char* __res
     const int col = nt * NT + n;
     const int kk0 = c * kKC + ku * 8;
     DgradImg im = dgrad_taps(G, MODE == FWD ? 0 : ph);
-    __align__(16) __nv_bfloat16 hi[8], lo[8];
+    __align__(16) __nv_bfloat16 hi[8], lo[8], lo3[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float v = 0.f;
@@ -364,20 +378,24 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, unsigned char* __res
         }
       }
       split_bf16(v, hi[j], lo[j]);
+      lo3[j] = __float2bfloat16_rn((v - __bfloat162float(hi[j])) - __bfloat162float(lo[j]));
     }
     unsigned char* base =
-        out + ((((size_t)(g * P.ntiles_n + nt) * P.nphase + ph) * P.nchunks + c)) * 2 * plane_b(NT);
+        out + ((((size_t)(g * P.ntiles_n + nt) * P.nphase + ph) * P.nchunks + c)) * P.nsplit * plane_b(NT);
     const size_t off = ((size_t)ku * NT + n) * 16;
     *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<const uint4*>(hi);
     *reinterpret_cast<uint4*>(base + plane_b(NT) + off) = *reinterpret_cast<const uint4*>(lo);
+    if (P.nsplit == 3) *reinterpret_cast<uint4*>(base + 2 * plane_b(NT) + off) = *reinterpret_cast<const uint4*>(lo3);
   }
 }
 
-static int fill_tc(TcP& P, const vbx_conv_desc* d, int mode) {
+static int fill_tc(TcP& P, const vbx_conv_desc* d, int mode, int nsplit) {
   int code = 0;
   const char* msg = check_desc_msg(d, &code);
   if (msg) return fail(code, msg);
+  if (nsplit != 2 && nsplit != 3) return fail(VBX_UNSUPPORTED, "tc: nsplit must be 2 (bf16x3) or 3 (bf16x6)");
   fill(P.g, d);
+  P.nsplit = nsplit;
   const int Ccol = mode == FWD ? P.g.Cout_g : P.g.Cin_g;
   P.NT = pick_nt(Ccol);
   P.ntiles_n = (Ccol + P.NT - 1) / P.NT;
@@ -394,12 +412,12 @@ static int fill_tc(TcP& P, const vbx_conv_desc* d, int mode) {
     P.nchunks = (P.cpad * max_taps + kKC - 1) / kKC;
   }
   P.tmem_cols = pow2_cols(P.NT);
-  P.stages = pick_stages_for(stage_bytes(P.NT), P.nchunks);
+  P.stages = pick_stages_for(stage_bytes(P.NT, P.nsplit), P.nchunks);
   return 0;
 }
 
 static size_t smem_bytes(const TcP& P) {
-  return (size_t)P.stages * stage_bytes(P.NT) + (3 * P.stages + 1) * sizeof(uint64_t) + 16 + 3 * sizeof(Seg) + 16;
+  return (size_t)P.stages * stage_bytes(P.NT, P.nsplit) + (3 * P.stages + 1) * sizeof(uint64_t) + 16 + 3 * sizeof(Seg) + 16;
 }
 
 template <int MODE>
@@ -623,20 +641,21 @@ __global__ void __launch_bounds__(kThreads, 3) tc_wgrad_kernel(const TcW P) {
 }
 
 static int64_t pack_bytes(const TcP& P) {
-  return (int64_t)P.g.groups * P.ntiles_n * P.nphase * P.nchunks * 2 * plane_b(P.NT);
+  return (int64_t)P.g.groups * P.ntiles_n * P.nphase * P.nchunks * P.nsplit * plane_b(P.NT);
 }
 
-extern "C" int64_t vbx_tc_pack_bytes(const vbx_conv_desc* d, int32_t mode) {
+extern "C" int64_t vbx_tc_pack_bytes(const vbx_conv_desc* d, int32_t mode, int32_t nsplit) {
   TcP P;
   if (mode != FWD && mode != DGRAD) return -1;
-  if (fill_tc(P, d, mode)) return -1;
+  if (fill_tc(P, d, mode, nsplit)) return -1;
   return pack_bytes(P);
 }
 
-extern "C" int vbx_tc_pack(const vbx_conv_desc* d, int32_t mode, const float* w, void* packed, void* stream) {
+extern "C" int vbx_tc_pack(const vbx_conv_desc* d, int32_t mode, int32_t nsplit, const float* w, void* packed,
+                           void* stream) {
   TcP P;
   VBX_REQUIRE(mode == FWD || mode == DGRAD, VBX_UNSUPPORTED, "tc_pack: mode must be 0 (fwd) or 1 (dgrad)");
-  if (int r = fill_tc(P, d, mode)) return r;
+  if (int r = fill_tc(P, d, mode, nsplit)) return r;
   VBX_REQUIRE(w && packed, VBX_BAD_POINTER, "tc_pack: null tensor");
   VBX_REQUIRE(((uintptr_t)packed & 15) == 0, VBX_BAD_POINTER, "tc_pack: packed buffer must be 16-byte aligned");
   return mode == FWD ? pack_tc<FWD>(P, w, packed, (cudaStream_t)stream)
@@ -644,9 +663,9 @@ extern "C" int vbx_tc_pack(const vbx_conv_desc* d, int32_t mode, const float* w,
 }
 
 extern "C" int vbx_tc_conv1d_fwd(const vbx_conv_desc* d, const float* x, const void* packed,
-                                 const vbx_epilogue* e, float* y, void* stream) {
+                                 const vbx_epilogue* e, float* y, int32_t nsplit, void* stream) {
   TcP P;
-  if (int r = fill_tc(P, d, FWD)) return r;
+  if (int r = fill_tc(P, d, FWD, nsplit)) return r;
   VBX_REQUIRE(x && packed && y, VBX_BAD_POINTER, "tc_conv1d_fwd: null tensor");
   VBX_REQUIRE(((uintptr_t)packed & 15) == 0, VBX_BAD_POINTER, "tc_conv1d_fwd: packed weights must be 16-byte aligned");
   fill_epi(P.g, e);
@@ -656,9 +675,9 @@ extern "C" int vbx_tc_conv1d_fwd(const vbx_conv_desc* d, const float* x, const v
 }
 
 extern "C" int vbx_tc_conv1d_dgrad(const vbx_conv_desc* d, const float* dy, const void* packed,
-                                   const vbx_epilogue* e, float* dx, void* stream) {
+                                   const vbx_epilogue* e, float* dx, int32_t nsplit, void* stream) {
   TcP P;
-  if (int r = fill_tc(P, d, DGRAD)) return r;
+  if (int r = fill_tc(P, d, DGRAD, nsplit)) return r;
   VBX_REQUIRE(dy && packed && dx, VBX_BAD_POINTER, "tc_conv1d_dgrad: null tensor");
   VBX_REQUIRE(((uintptr_t)packed & 15) == 0, VBX_BAD_POINTER, "tc_conv1d_dgrad: packed weights must be 16-byte aligned");
   fill_epi(P.g, e);

@@ -331,8 +331,8 @@ class MRSTFTFn(Function):
                 # framing + DFT as a pointwise conv over the frame axis on the tensor-core kernel
                 pw = ConvGeom(geom.K, geom.Cout, 1)
                 wpw = basis.view(geom.Cout, geom.K, 1)
-                X = ops.conv_fwd(ops.unfold_frames(xf, geom.K, geom.stride, geom.pad), wpw, pw)
-                Y = ops.conv_fwd(ops.unfold_frames(yf, geom.K, geom.stride, geom.pad), wpw, pw)
+                X = ops.conv_fwd(ops.unfold_frames(xf, geom.K, geom.stride, geom.pad), wpw, pw, nsplit=3)
+                Y = ops.conv_fwd(ops.unfold_frames(yf, geom.K, geom.stride, geom.pad), wpw, pw, nsplit=3)
             else:
                 X = ops.conv1d_fwd(xf, basis, geom)
                 Y = ops.conv1d_fwd(yf, basis, geom)
@@ -366,7 +366,7 @@ class MRSTFTFn(Function):
             dX = ops.stft_bwd(X, Y, spec.eps, stats[3 * r:3 * r + 3], counts[r], go, 1.0 / nres)
             if ops.STFT_VIA_FRAMES:
                 pw = ConvGeom(geom.K, geom.Cout, 1)
-                dU = ops.conv_dgrad(dX, spec.res[r][1].view(geom.Cout, geom.K, 1), None, pw, dX.shape[2])
+                dU = ops.conv_dgrad(dX, spec.res[r][1].view(geom.Cout, geom.K, 1), None, pw, dX.shape[2], nsplit=3)
                 ops.fold_frames(dU, L, geom.stride, geom.pad, dx=dxf)
             else:
                 ops.conv1d_dgrad_scatter(dX, basis_k, geom, L, dxf)

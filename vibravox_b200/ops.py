@@ -125,19 +125,19 @@ def _geom_only_desc(g: ConvGeom) -> ConvDesc:
     return g.desc(1, tin + (-(tin + 2 * g.pad - g.dil * (g.K - 1) - 1)) % g.stride)
 
 
-def tc_pack(w: Tensor, g: ConvGeom, mode: int) -> Tensor:
-    """bf16 hi/lo K-major weight tiles for the tensor-core kernels (mode 0 = fwd, 1 = dgrad)."""
+def tc_pack(w: Tensor, g: ConvGeom, mode: int, nsplit: int = 2) -> Tensor:
+    """bf16 hi/lo(/lo2) K-major weight tiles for the tensor-core kernels (mode 0 = fwd, 1 = dgrad)."""
     d = _geom_only_desc(g)
-    nbytes = _lib.load().vbx_tc_pack_bytes(ctypes.byref(d), mode)
+    nbytes = _lib.load().vbx_tc_pack_bytes(ctypes.byref(d), mode, nsplit)
     if nbytes <= 0:
         raise _lib.VbxError("vbx_tc_pack_bytes: " + _lib.load().vbx_last_error().decode())
     packed = torch.empty((nbytes,), device=w.device, dtype=torch.uint8)
-    check(_lib.load().vbx_tc_pack(ctypes.byref(d), mode, _p(w), packed.data_ptr(), _stream()), "vbx_tc_pack")
+    check(_lib.load().vbx_tc_pack(ctypes.byref(d), mode, nsplit, _p(w), packed.data_ptr(), _stream()), "vbx_tc_pack")
     return packed
 
 
 def tc_conv1d_fwd(x: Tensor, packed: Tensor, g: ConvGeom, bias: Optional[Tensor] = None,
-                  res: Optional[Tensor] = None, slope: float = 1.0, want_mask: bool = False):
+                  res: Optional[Tensor] = None, slope: float = 1.0, want_mask: bool = False, nsplit: int = 2):
     B, Cin, Tin = x.shape
     assert Cin == g.Cin
     d = g.desc(B, Tin)
@@ -146,13 +146,13 @@ def tc_conv1d_fwd(x: Tensor, packed: Tensor, g: ConvGeom, bias: Optional[Tensor]
     if res is not None:
         assert res.shape == y.shape
     e = _epi(bias, res, mask, slope, 0.0)
-    check(_lib.load().vbx_tc_conv1d_fwd(ctypes.byref(d), _p(x), packed.data_ptr(), ctypes.byref(e), _p(y), _stream()),
-          "vbx_tc_conv1d_fwd")
+    check(_lib.load().vbx_tc_conv1d_fwd(ctypes.byref(d), _p(x), packed.data_ptr(), ctypes.byref(e), _p(y), nsplit,
+                                        _stream()), "vbx_tc_conv1d_fwd")
     return (y, mask) if want_mask else y
 
 
 def tc_conv1d_dgrad(dy: Tensor, packed: Tensor, g: ConvGeom, Tin: int, res: Optional[Tensor] = None,
-                    slope: float = 1.0) -> Tensor:
+                    slope: float = 1.0, nsplit: int = 2) -> Tensor:
     B, Cout, Tout = dy.shape
     d = g.desc(B, Tin)
     assert Cout == g.Cout and Tout == d.Tout, (dy.shape, g, Tin, d.Tout)
@@ -161,7 +161,7 @@ def tc_conv1d_dgrad(dy: Tensor, packed: Tensor, g: ConvGeom, Tin: int, res: Opti
         assert res.shape == dx.shape
     e = _epi(None, res, None, slope, 0.0)
     check(_lib.load().vbx_tc_conv1d_dgrad(ctypes.byref(d), _p(dy), packed.data_ptr(), ctypes.byref(e), _p(dx),
-                                          _stream()), "vbx_tc_conv1d_dgrad")
+                                          nsplit, _stream()), "vbx_tc_conv1d_dgrad")
     return dx
 
 
@@ -425,7 +425,7 @@ TC_FWD, TC_DGRAD = 0, 1
 # log-magnitude term divides by bins that sit 60-100 dB under the frame energy (A-weighting), which turns the
 # 2^-17 operand rounding of bf16x3 into a 1.8e-2 gradient error / +1 % gradient-norm bias (measured, fp32
 # arithmetic: 4e-3 / <1e-4), and that norm drives the loss balancing.  The FMA path keeps fp32 there.
-STFT_VIA_FRAMES = os.environ.get("VBX_STFT_VIA_FRAMES", "0") == "1"
+STFT_VIA_FRAMES = os.environ.get("VBX_STFT_VIA_FRAMES", "1" if TC_ENABLED else "0") == "1"
 
 
 def use_tc(g: ConvGeom, kind: str) -> bool:
@@ -439,28 +439,32 @@ def use_tc(g: ConvGeom, kind: str) -> bool:
     return cout_g >= 16 and cin_g * g.K >= 8          # wgrad
 
 
-def get_pack(w: Tensor, g: ConvGeom, mode: int) -> Tensor:
+def get_pack(w: Tensor, g: ConvGeom, mode: int, nsplit: int = 2) -> Tensor:
     """Packed bf16 hi/lo tiles of `w`, cached on the tensor object (an effective weight lives for one
     phase of one step; parameters used directly are keyed by their version counter)."""
     cache = w.__dict__.setdefault("_vbx_packs", {})
-    key = (g, mode, w._version)
+    key = (g, mode, nsplit, w._version)
     pk = cache.get(key)
     if pk is None:
-        pk = tc_pack(w if w.is_contiguous() else w.contiguous(), g, mode)
-        cache.clear()
+        pk = tc_pack(w if w.is_contiguous() else w.contiguous(), g, mode, nsplit)
+        for k in [k for k in cache if k[3] != w._version]:
+            del cache[k]
         cache[key] = pk
     return pk
 
 
-def conv_fwd(x: Tensor, w: Tensor, g: ConvGeom, bias=None, res=None, slope: float = 1.0, want_mask: bool = False):
+def conv_fwd(x: Tensor, w: Tensor, g: ConvGeom, bias=None, res=None, slope: float = 1.0, want_mask: bool = False,
+             nsplit: int = 2):
     if use_tc(g, "fwd"):
-        return tc_conv1d_fwd(x, get_pack(w, g, TC_FWD), g, bias=bias, res=res, slope=slope, want_mask=want_mask)
+        return tc_conv1d_fwd(x, get_pack(w, g, TC_FWD, nsplit), g, bias=bias, res=res, slope=slope,
+                             want_mask=want_mask, nsplit=nsplit)
     return conv1d_fwd(x, w, g, bias=bias, res=res, slope=slope, want_mask=want_mask)
 
 
-def conv_dgrad(dy: Tensor, w: Tensor, wt: Optional[Tensor], g: ConvGeom, Tin: int, res=None, slope: float = 1.0):
+def conv_dgrad(dy: Tensor, w: Tensor, wt: Optional[Tensor], g: ConvGeom, Tin: int, res=None, slope: float = 1.0,
+               nsplit: int = 2):
     if use_tc(g, "dgrad"):
-        return tc_conv1d_dgrad(dy, get_pack(w, g, TC_DGRAD), g, Tin, res=res, slope=slope)
+        return tc_conv1d_dgrad(dy, get_pack(w, g, TC_DGRAD, nsplit), g, Tin, res=res, slope=slope, nsplit=nsplit)
     if wt is None:
         wt = transpose_weight(w, g.groups)
     return conv1d_dgrad(dy, wt, g, Tin, res=res, slope=slope)
