@@ -5,6 +5,7 @@ MelGAN discriminator on the waveform; element 0 of every list is the input, inte
 entries are post-LeakyReLU(0.2), the last is the raw certainty map."""
 from __future__ import annotations
 
+import os
 from typing import List
 
 import torch
@@ -61,6 +62,33 @@ class DiscriminatorEBENMultiScales(nn.Module, PyTorchModelHubMixin):
         selected = bands[:, -self.q:, :]
         if not selected.is_contiguous():
             selected = selected.contiguous()
-        embeddings = [dis(selected) for dis in self.pqmf_discriminators]
-        embeddings.append(self.melgan_discriminator(audio))
+        nets = list(self.pqmf_discriminators) + [self.melgan_discriminator]
+        inputs = [selected, selected, selected, audio]
+        if not (selected.is_cuda and _SIDE_STREAMS):
+            return [net(x) for net, x in zip(nets, inputs)]
+        # The four sub-discriminators are independent chains of small / medium kernels: run each on its own
+        # stream so that they fill the 148 SMs together (autograd replays each chain's backward on the stream
+        # its forward ran on and inserts the cross-stream waits itself).
+        cur = torch.cuda.current_stream()
+        streams = self._streams(selected.device)
+        embeddings = []
+        for net, x, st in zip(nets, inputs, streams):
+            st.wait_stream(cur)
+            x.record_stream(st)
+            with torch.cuda.stream(st):
+                emb = net(x)
+            for t in emb[1:]:
+                t.record_stream(cur)                    # consumed by the losses on the caller's stream
+            embeddings.append(emb)
+        for st in streams:
+            cur.wait_stream(st)
         return embeddings
+
+    def _streams(self, device):
+        cache = self.__dict__.setdefault("_vbx_streams", {})
+        if device not in cache:
+            cache[device] = [torch.cuda.Stream(device=device) for _ in range(4)]
+        return cache[device]
+
+
+_SIDE_STREAMS = os.environ.get("VBX_D_STREAMS", "1") != "0"
