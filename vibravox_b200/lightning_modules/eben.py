@@ -127,8 +127,12 @@ class EBENLightningModule(torch.nn.Module):
                 losses = OrderedDict()
                 if self.reconstructive_loss_freq_fn:
                     losses["reconstructive_loss_freq"] = self.reconstructive_loss_freq_fn(enh, reference_speech)
-                enhanced_embeddings = D(bands=bands, audio=enh)
-                reference_embeddings = D(bands=reference_bands, audio=reference_speech)
+                if hasattr(D, "forward_multi"):
+                    enhanced_embeddings, reference_embeddings = D.forward_multi(
+                        [(bands, enh), (reference_bands, reference_speech)])
+                else:
+                    enhanced_embeddings = D(bands=bands, audio=enh)
+                    reference_embeddings = D(bands=reference_bands, audio=reference_speech)
                 losses["feature_matching_loss"] = self.feature_matching_loss_fn(enhanced_embeddings,
                                                                                 reference_embeddings)
                 losses["adv_loss_gen"] = self.adversarial_loss_fn(embeddings=enhanced_embeddings, target=1)

@@ -59,36 +59,51 @@ class DiscriminatorEBENMultiScales(nn.Module, PyTorchModelHubMixin):
         self.melgan_discriminator = DiscriminatorMelGAN(alpha_leaky_relu=0.2)
 
     def forward(self, bands: torch.Tensor, audio: torch.Tensor) -> List[List[torch.Tensor]]:
-        selected = bands[:, -self.q:, :]
-        if not selected.is_contiguous():
-            selected = selected.contiguous()
-        nets = list(self.pqmf_discriminators) + [self.melgan_discriminator]
-        inputs = [selected, selected, selected, audio]
-        if not (selected.is_cuda and _SIDE_STREAMS):
-            return [net(x) for net, x in zip(nets, inputs)]
-        # The four sub-discriminators are independent chains of small / medium kernels: run each on its own
-        # stream so that they fill the 148 SMs together (autograd replays each chain's backward on the stream
-        # its forward ran on and inserts the cross-stream waits itself).
-        cur = torch.cuda.current_stream()
-        streams = self._streams(selected.device)
-        embeddings = []
-        for net, x, st in zip(nets, inputs, streams):
-            st.wait_stream(cur)
-            x.record_stream(st)
-            with torch.cuda.stream(st):
-                emb = net(x)
-            for t in emb[1:]:
-                t.record_stream(cur)                    # consumed by the losses on the caller's stream
-            embeddings.append(emb)
-        for st in streams:
-            cur.wait_stream(st)
-        return embeddings
+        return self.forward_multi([(bands, audio)])[0]
 
-    def _streams(self, device):
+    def forward_multi(self, pairs) -> List[List[List[torch.Tensor]]]:
+        """forward() for several independent (bands, audio) pairs at once (e.g. enhanced and reference).
+        The 4 x len(pairs) sub-discriminator passes are independent chains of small / medium kernels: each
+        runs on its own stream so that together they fill the 148 SMs; autograd replays each chain's backward
+        on the stream its forward ran on and inserts the cross-stream waits itself."""
+        nets = list(self.pqmf_discriminators) + [self.melgan_discriminator]
+        jobs = []
+        for bands, audio in pairs:
+            selected = bands[:, -self.q:, :]
+            if not selected.is_contiguous():
+                selected = selected.contiguous()
+            jobs.append([selected, selected, selected, audio])
+        if not (jobs[0][0].is_cuda and _SIDE_STREAMS):
+            return [[net(x) for net, x in zip(nets, inputs)] for inputs in jobs]
+        cur = torch.cuda.current_stream()
+        streams = self._streams(jobs[0][0].device, 4 * len(jobs))
+        out, used = [], []
+        for j, inputs in enumerate(jobs):
+            embeddings = []
+            for i, (net, x) in enumerate(zip(nets, inputs)):
+                st = streams[4 * j + i]
+                st.wait_stream(cur)
+                x.record_stream(st)
+                with torch.cuda.stream(st):
+                    emb = net(x)
+                for t in emb[1:]:
+                    t.record_stream(cur)                # consumed by the losses on the caller's stream
+                embeddings.append(emb)
+                used.append(st)
+            out.append(embeddings)
+        for st in used:
+            cur.wait_stream(st)
+        return out
+
+    def _streams(self, device, n):
         cache = self.__dict__.setdefault("_vbx_streams", {})
-        if device not in cache:
-            cache[device] = [torch.cuda.Stream(device=device) for _ in range(4)]
-        return cache[device]
+        pool = cache.setdefault(device, [])
+        while len(pool) < n:
+            pool.append(torch.cuda.Stream(device=device))
+        return pool
 
 
 _SIDE_STREAMS = os.environ.get("VBX_D_STREAMS", "1") != "0"
+if _SIDE_STREAMS and hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+    # leaves created on the caller's stream (detached generator outputs) receive gradients from side streams
+    torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
