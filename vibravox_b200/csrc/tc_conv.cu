@@ -69,7 +69,8 @@ inline int pick_stages_for(int stage_sz, int nchunks) {
   // shared-memory budget per CTA: three CTAs per SM (more producer warps in flight) unless a single stage
   // is already > 36 KB (N = 256 tiles), where two CTAs per SM is the most that fits
   static const int small_kb = getenv("VBX_TC_BUDGET_KB") ? atoi(getenv("VBX_TC_BUDGET_KB")) : 72;
-  const int budget = (2 * stage_sz > small_kb * 1024 ? 108 : small_kb) * 1024;
+  static const int tiny_kb = getenv("VBX_TC_TINY_KB") ? atoi(getenv("VBX_TC_TINY_KB")) : 54;
+  const int budget = (2 * stage_sz <= tiny_kb * 1024 ? tiny_kb : 2 * stage_sz > small_kb * 1024 ? 108 : small_kb) * 1024;
   int s = budget / stage_sz;
   const int cap = 4;
   s = s > cap ? cap : s;
@@ -88,8 +89,10 @@ __device__ __forceinline__ float finish(const GemmP& P, float v, int ch, long lo
 
 // MODE FWD  : rows (b,t),  cols co, reduction (ci,k):  A = x[b,ci,map(t*s + k*d - pad)]
 // MODE DGRAD: rows (b,u) of one phase, cols ci, reduction (co,j): A = dy[b,co,(u+pad-k*d)/s]
-template <int MODE>
-__global__ void __launch_bounds__(kThreads, 3) tc_conv_kernel(const TcP P) {
+// MINB = CTAs per SM the register budget is sized for (3: 64 registers, 4: 48 registers for N <= 64 tiles,
+// whose short reductions are latency bound and want as many tiles in flight as possible)
+template <int MODE, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const TcP P) {
   extern __shared__ __align__(128) unsigned char smem[];
   const GemmP& G = P.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -424,7 +427,9 @@ template <int MODE>
 static int launch_tc(const TcP& P, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t ce = cudaFuncSetAttribute(tc_conv_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+    cudaError_t ce = cudaFuncSetAttribute(tc_conv_kernel<MODE, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+    if (ce == cudaSuccess)
+      ce = cudaFuncSetAttribute(tc_conv_kernel<MODE, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
     if (ce != cudaSuccess) return fail((int)ce, "tc_conv: cannot raise the dynamic shared memory limit");
     attr_set = true;
   }
@@ -433,7 +438,10 @@ static int launch_tc(const TcP& P, cudaStream_t st) {
   dim3 grid((unsigned)((rows + kRows - 1) / kRows), (unsigned)(P.ntiles_n * P.g.groups),
             (unsigned)(MODE == FWD ? 1 : P.g.stride));
   if (grid.y > 65535 || grid.z > 65535) return fail(VBX_UNSUPPORTED, "tc_conv: grid too large");
-  tc_conv_kernel<MODE><<<grid, kThreads, smem_bytes(P), st>>>(P);
+  if (smem_bytes(P) <= 56 * 1024 && P.tmem_cols <= 128)
+    tc_conv_kernel<MODE, 4><<<grid, kThreads, smem_bytes(P), st>>>(P);
+  else
+    tc_conv_kernel<MODE, 3><<<grid, kThreads, smem_bytes(P), st>>>(P);
   return launched("tc_conv_kernel");
 }
 
@@ -532,6 +540,16 @@ __global__ void __launch_bounds__(kThreads, 3) tc_wgrad_kernel(const TcW P) {
     const int rows_a = min(kRows, G.Cout_g - co_base);
     const uint32_t lbo_b = (uint32_t)lbo_wb(NT);
     const int kmin = kspan[0], kmax = kspan[1];          // range of k*d - pad over this tile's columns
+    // Rows beyond the layer's channel / column count stay zero for the whole kernel: clear the stages once
+    // (generic-proxy writes, published by the fence that precedes every arrive) and never touch them again.
+    const int ncols_tile = min(NT, Ncols - nt * NT);
+    const int rows_a16 = (rows_a + 15) & ~15, rows_b16 = (ncols_tile + 15) & ~15;
+    if (rows_a16 < kRows || rows_b16 < NT) {
+      uint4* z = reinterpret_cast<uint4*>(stage0);
+      const int n16 = S * stage_sz / 16;
+      for (int i = tid; i < n16; i += kProducers) z[i] = make_uint4(0u, 0u, 0u, 0u);
+      asm volatile("bar.sync 1, 256;" ::: "memory");     // producer warps only
+    }
     for (int c = 0; c < nchunks; ++c) {
       const int s = c % S, use = c / S;
       // the two reduction elements of this lane: r, r+1 (may straddle a batch boundary)
@@ -558,9 +576,8 @@ __global__ void __launch_bounds__(kThreads, 3) tc_wgrad_kernel(const TcW P) {
         *reinterpret_cast<__nv_bfloat162*>(hi_p) = hi2;
         *reinterpret_cast<__nv_bfloat162*>(lo_p) = __floats2bfloat162_rn(a - hf.x, b - hf.y);
       };
-#pragma unroll
-      for (int j = 0; j < kRows / 16; ++j) {
-        const int m = j * 16 + rl;
+#pragma unroll 8
+      for (int m = rl; m < rows_a16; m += 16) {
         const float a = (v0 && m < rows_a) ? dy0[m * G.Tout] : 0.f;
         const float b = (v1 && m < rows_a) ? dy1[m * G.Tout] : 0.f;
         put(a_hi + m * 16, a_lo + m * 16, a, b);
@@ -569,7 +586,7 @@ __global__ void __launch_bounds__(kThreads, 3) tc_wgrad_kernel(const TcW P) {
         const float* xt0 = x0 + ts0;
         const float* xt1 = x1 + ts1;
 #pragma unroll 4
-        for (int n = rl; n < NT; n += 16) {
+        for (int n = rl; n < rows_b16; n += 16) {
           const int ro = roff[n];
           const float a = ro != INT_MIN ? xt0[ro] : 0.f;
           const float b = ro != INT_MIN ? xt1[ro] : 0.f;
@@ -577,7 +594,7 @@ __global__ void __launch_bounds__(kThreads, 3) tc_wgrad_kernel(const TcW P) {
         }
       } else {
 #pragma unroll 2
-        for (int n = rl; n < NT; n += 16) {
+        for (int n = rl; n < rows_b16; n += 16) {
           const int2 ri = rowinfo[n];
           float a = 0.f, b = 0.f;
           if (ri.y != INT_MIN) {

@@ -436,7 +436,7 @@ def use_tc(g: ConvGeom, kind: str) -> bool:
         return cout_g >= 8 or cin_g * g.K >= 512      # incl. the 1-channel certainty convs (K*Cin = 2-3k)
     if kind == "dgrad":
         return cin_g >= 4
-    return cout_g >= 16 and cin_g * g.K >= 8          # wgrad
+    return cout_g >= 4 and cin_g * g.K >= 3           # wgrad
 
 
 def get_pack(w: Tensor, g: ConvGeom, mode: int, nsplit: int = 2) -> Tensor:
