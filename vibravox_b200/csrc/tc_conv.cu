@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(kThreads, 3) tc_wgrad_kernel(const TcW P) {
   const int nchunks = (red_hi - red_lo + kKC - 1) / kKC;
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&full[s], kProducers); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], kProducers / 2); mbar_init(&empty[s], 1); }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -531,9 +531,11 @@ __global__ void __launch_bounds__(kThreads, 3) tc_wgrad_kernel(const TcW P) {
   if (warp < 8) {
     // ===================== producers: dy rows and im2col'd x rows, lanes walk t =====================
     // A half-warp covers the 32 reduction positions of one row (16 lanes x 2 consecutive t); the two
-    // halves take rows 4 apart so that their 4-byte stores land in different banks.  16 rows per pass.
+    // halves take rows 4 apart so that their 4-byte stores land in different banks.  The 8 warps form two
+    // groups that fill alternate stages, so two chunks' worth of loads are in flight per CTA.
     const int tp = lane & 15, hw = lane >> 4;
-    const int rl = (warp & 3) + 4 * hw + 8 * (warp >> 2);          // row within a 16-row pass
+    const int grp2 = warp >> 2;
+    const int rl = (warp & 3) + 4 * hw;                              // row within an 8-row pass
     const int ku = tp >> 2;
     const uint32_t lane_off = (uint32_t)(tp & 3) * 4;
     const int co_base = mt * kRows;
@@ -543,14 +545,14 @@ __global__ void __launch_bounds__(kThreads, 3) tc_wgrad_kernel(const TcW P) {
     // Rows beyond the layer's channel / column count stay zero for the whole kernel: clear the stages once
     // (generic-proxy writes, published by the fence that precedes every arrive) and never touch them again.
     const int ncols_tile = min(NT, Ncols - nt * NT);
-    const int rows_a16 = (rows_a + 15) & ~15, rows_b16 = (ncols_tile + 15) & ~15;
+    const int rows_a16 = (rows_a + 7) & ~7, rows_b16 = (ncols_tile + 7) & ~7;
     if (rows_a16 < kRows || rows_b16 < NT) {
       uint4* z = reinterpret_cast<uint4*>(stage0);
       const int n16 = S * stage_sz / 16;
       for (int i = tid; i < n16; i += kProducers) z[i] = make_uint4(0u, 0u, 0u, 0u);
       asm volatile("bar.sync 1, 256;" ::: "memory");     // producer warps only
     }
-    for (int c = 0; c < nchunks; ++c) {
+    for (int c = grp2; c < nchunks; c += 2) {
       const int s = c % S, use = c / S;
       // the two reduction elements of this lane: r, r+1 (may straddle a batch boundary)
       const int r = red_lo + c * kKC + 2 * tp;
@@ -577,7 +579,7 @@ __global__ void __launch_bounds__(kThreads, 3) tc_wgrad_kernel(const TcW P) {
         *reinterpret_cast<__nv_bfloat162*>(lo_p) = __floats2bfloat162_rn(a - hf.x, b - hf.y);
       };
 #pragma unroll 8
-      for (int m = rl; m < rows_a16; m += 16) {
+      for (int m = rl; m < rows_a16; m += 8) {
         const float a = (v0 && m < rows_a) ? dy0[m * G.Tout] : 0.f;
         const float b = (v1 && m < rows_a) ? dy1[m * G.Tout] : 0.f;
         put(a_hi + m * 16, a_lo + m * 16, a, b);
@@ -585,8 +587,8 @@ __global__ void __launch_bounds__(kThreads, 3) tc_wgrad_kernel(const TcW P) {
       if (interior) {
         const float* xt0 = x0 + ts0;
         const float* xt1 = x1 + ts1;
-#pragma unroll 4
-        for (int n = rl; n < rows_b16; n += 16) {
+#pragma unroll 8
+        for (int n = rl; n < rows_b16; n += 8) {
           const int ro = roff[n];
           const float a = ro != INT_MIN ? xt0[ro] : 0.f;
           const float b = ro != INT_MIN ? xt1[ro] : 0.f;
@@ -594,7 +596,7 @@ __global__ void __launch_bounds__(kThreads, 3) tc_wgrad_kernel(const TcW P) {
         }
       } else {
 #pragma unroll 2
-        for (int n = rl; n < rows_b16; n += 16) {
+        for (int n = rl; n < rows_b16; n += 8) {
           const int2 ri = rowinfo[n];
           float a = 0.f, b = 0.f;
           if (ri.y != INT_MIN) {
