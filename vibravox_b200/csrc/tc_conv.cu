@@ -530,14 +530,15 @@ __global__ void __launch_bounds__(kThreads, 3) tc_wgrad_kernel(const TcW P) {
 
   if (warp < 8) {
     // ===================== producers: dy rows and im2col'd x rows, lanes walk t =====================
-    // A half-warp covers the 32 reduction positions of one row (16 lanes x 2 consecutive t); the two
-    // halves take rows 4 apart so that their 4-byte stores land in different banks.  The 8 warps form two
-    // groups that fill alternate stages, so two chunks' worth of loads are in flight per CTA.
-    const int tp = lane & 15, hw = lane >> 4;
+    // A lane owns FOUR consecutive reduction positions of a row (8 lanes = the 32 positions of a stage), so the
+    // address / halo / batch-boundary logic is paid once per four values, the split uses packed converts and a
+    // row costs one 8-byte store per plane.  A warp covers 4 rows per pass (rows 4 apart: disjoint banks); the
+    // 8 warps form two groups that fill alternate stages, so two stages' loads are in flight per CTA.
+    const int tq = lane & 7, rsel = lane >> 3;
     const int grp2 = warp >> 2;
-    const int rl = (warp & 3) + 4 * hw;                              // row within an 8-row pass
-    const int ku = tp >> 2;
-    const uint32_t lane_off = (uint32_t)(tp & 3) * 4;
+    const int rl = (warp & 3) + 4 * rsel;                            // row within a 16-row pass
+    const uint32_t lane_off = (uint32_t)(tq >> 1) * 0 + (uint32_t)(tq & 1) * 8;
+    const int ku = tq >> 1;
     const int co_base = mt * kRows;
     const int rows_a = min(kRows, G.Cout_g - co_base);
     const uint32_t lbo_b = (uint32_t)lbo_wb(NT);
@@ -545,65 +546,91 @@ __global__ void __launch_bounds__(kThreads, 3) tc_wgrad_kernel(const TcW P) {
     // Rows beyond the layer's channel / column count stay zero for the whole kernel: clear the stages once
     // (generic-proxy writes, published by the fence that precedes every arrive) and never touch them again.
     const int ncols_tile = min(NT, Ncols - nt * NT);
-    const int rows_a16 = (rows_a + 7) & ~7, rows_b16 = (ncols_tile + 7) & ~7;
+    const int rows_a16 = (rows_a + 15) & ~15, rows_b16 = (ncols_tile + 15) & ~15;
     if (rows_a16 < kRows || rows_b16 < NT) {
       uint4* z = reinterpret_cast<uint4*>(stage0);
       const int n16 = S * stage_sz / 16;
       for (int i = tid; i < n16; i += kProducers) z[i] = make_uint4(0u, 0u, 0u, 0u);
       asm volatile("bar.sync 1, 256;" ::: "memory");     // producer warps only
     }
+    auto put4 = [](unsigned char* hi_p, unsigned char* lo_p, const float (&v)[4]) {
+      const __nv_bfloat162 h01 = __floats2bfloat162_rn(v[0], v[1]), h23 = __floats2bfloat162_rn(v[2], v[3]);
+      const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+      const __nv_bfloat162 l01 = __floats2bfloat162_rn(v[0] - f01.x, v[1] - f01.y);
+      const __nv_bfloat162 l23 = __floats2bfloat162_rn(v[2] - f23.x, v[3] - f23.y);
+      uint2 h, l;
+      h.x = *reinterpret_cast<const uint32_t*>(&h01); h.y = *reinterpret_cast<const uint32_t*>(&h23);
+      l.x = *reinterpret_cast<const uint32_t*>(&l01); l.y = *reinterpret_cast<const uint32_t*>(&l23);
+      *reinterpret_cast<uint2*>(hi_p) = h;
+      *reinterpret_cast<uint2*>(lo_p) = l;
+    };
     for (int c = grp2; c < nchunks; c += 2) {
       const int s = c % S, use = c / S;
-      // the two reduction elements of this lane: r, r+1 (may straddle a batch boundary)
-      const int r = red_lo + c * kKC + 2 * tp;
-      const bool v0 = r < red_hi, v1 = r + 1 < red_hi;
-      const int b0 = v0 ? r / G.Tout : 0, t0 = v0 ? r % G.Tout : 0;
-      int b1 = b0, t1 = t0 + 1;
-      if (t1 >= G.Tout) { t1 = 0; ++b1; }
-      if (!v1) { b1 = 0; t1 = 0; }
-      const float* dy0 = G.DY + ((long long)b0 * G.Cout + grp * G.Cout_g + co_base) * G.Tout + t0;
-      const float* dy1 = G.DY + ((long long)b1 * G.Cout + grp * G.Cout_g + co_base) * G.Tout + t1;
-      const float* x0 = G.X + ((long long)b0 * G.Cin + grp * G.Cin_g) * G.Tin;
-      const float* x1 = G.X + ((long long)b1 * G.Cin + grp * G.Cin_g) * G.Tin;
-      const int ts0 = t0 * G.stride, ts1 = t1 * G.stride;
-      const bool interior = v0 && v1 && ts0 + kmin >= 0 && ts0 + kmax < G.Tin && ts1 + kmin >= 0 && ts1 + kmax < G.Tin;
+      const int r0 = red_lo + c * kKC + 4 * tq;          // this lane's four reduction elements r0 .. r0+3
+      const int nval = max(0, min(4, red_hi - r0));
+      const int b0 = nval > 0 ? r0 / G.Tout : 0, t0 = nval > 0 ? r0 % G.Tout : 0;
+      const bool fast = nval == 4 && t0 + 3 < G.Tout;    // all four valid and inside one batch item
+      const float* dyp = G.DY + ((long long)b0 * G.Cout + grp * G.Cout_g + co_base) * G.Tout + t0;
+      const float* xp = G.X + ((long long)b0 * G.Cin + grp * G.Cin_g) * G.Tin;
+      const int ts0 = t0 * G.stride;
+      const bool interior = fast && ts0 + kmin >= 0 && ts0 + 3 * G.stride + kmax < G.Tin;
+      // generic per-element decode (lanes that straddle a batch boundary or the end of the slice)
+      int eb[4], et[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        int t = t0 + e, b = b0;
+        if (t >= G.Tout) { t -= G.Tout; ++b; }           // 4 consecutive positions cross at most one boundary
+        eb[e] = b; et[e] = e < nval ? t : -1;
+      }
       mbar_wait(&empty[s], (use & 1) ^ 1);
       unsigned char* a_hi = stage0 + (size_t)s * stage_sz + (uint32_t)ku * kLboW + lane_off;
       unsigned char* a_lo = a_hi + plane_a;
       unsigned char* b_hi = stage0 + (size_t)s * stage_sz + 2 * plane_a + (uint32_t)ku * lbo_b + lane_off;
       unsigned char* b_lo = b_hi + plane_bw;
-      auto put = [](unsigned char* hi_p, unsigned char* lo_p, float a, float b) {
-        const __nv_bfloat162 hi2 = __floats2bfloat162_rn(a, b);
-        const float2 hf = __bfloat1622float2(hi2);
-        *reinterpret_cast<__nv_bfloat162*>(hi_p) = hi2;
-        *reinterpret_cast<__nv_bfloat162*>(lo_p) = __floats2bfloat162_rn(a - hf.x, b - hf.y);
-      };
-#pragma unroll 8
-      for (int m = rl; m < rows_a16; m += 8) {
-        const float a = (v0 && m < rows_a) ? dy0[m * G.Tout] : 0.f;
-        const float b = (v1 && m < rows_a) ? dy1[m * G.Tout] : 0.f;
-        put(a_hi + m * 16, a_lo + m * 16, a, b);
+#pragma unroll 4
+      for (int m = rl; m < rows_a16; m += 16) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (m < rows_a) {
+          if (fast) {
+            const float* q = dyp + (long long)m * G.Tout;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = q[e];
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (et[e] >= 0)
+                v[e] = G.DY[((long long)eb[e] * G.Cout + grp * G.Cout_g + co_base + m) * G.Tout + et[e]];
+          }
+        }
+        put4(a_hi + m * 16, a_lo + m * 16, v);
       }
       if (interior) {
-        const float* xt0 = x0 + ts0;
-        const float* xt1 = x1 + ts1;
-#pragma unroll 8
-        for (int n = rl; n < rows_b16; n += 8) {
+        const float* xt = xp + ts0;
+        const int st = G.stride;
+#pragma unroll 4
+        for (int n = rl; n < rows_b16; n += 16) {
           const int ro = roff[n];
-          const float a = ro != INT_MIN ? xt0[ro] : 0.f;
-          const float b = ro != INT_MIN ? xt1[ro] : 0.f;
-          put(b_hi + n * 16, b_lo + n * 16, a, b);
+          float v[4] = {0.f, 0.f, 0.f, 0.f};
+          if (ro != INT_MIN) {
+            const float* q = xt + ro;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = q[e * st];
+          }
+          put4(b_hi + n * 16, b_lo + n * 16, v);
         }
       } else {
-#pragma unroll 2
-        for (int n = rl; n < rows_b16; n += 8) {
+        for (int n = rl; n < rows_b16; n += 16) {
           const int2 ri = rowinfo[n];
-          float a = 0.f, b = 0.f;
+          float v[4] = {0.f, 0.f, 0.f, 0.f};
           if (ri.y != INT_MIN) {
-            if (v0) { const int p = map_pos(ts0 + ri.y, G.Tin, G.refl); if (p >= 0) a = x0[ri.x + p]; }
-            if (v1) { const int p = map_pos(ts1 + ri.y, G.Tin, G.refl); if (p >= 0) b = x1[ri.x + p]; }
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (et[e] >= 0) {
+                const int p = map_pos(et[e] * G.stride + ri.y, G.Tin, G.refl);
+                if (p >= 0) v[e] = G.X[((long long)eb[e] * G.Cin + grp * G.Cin_g) * G.Tin + ri.x + p];
+              }
           }
-          put(b_hi + n * 16, b_lo + n * 16, a, b);
+          put4(b_hi + n * 16, b_lo + n * 16, v);
         }
       }
       fence_proxy_async();
