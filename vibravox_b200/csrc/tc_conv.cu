@@ -476,7 +476,10 @@ struct TcW {
 __host__ __device__ inline int lbo_wb(int NT) { return NT * 16 + 16; }
 __host__ __device__ inline int wstage_bytes(int NT) { return 2 * 4 * kLboW + 2 * 4 * lbo_wb(NT); }
 
-__global__ void __launch_bounds__(kThreads, 3) tc_wgrad_kernel(const TcW P) {
+// MINB / UNR: CTAs per SM the register budget allows and the row-loop unroll (loads in flight per lane).
+// N = 256 tiles own 256 TMEM columns, so only two CTAs fit per SM anyway: they get 96 registers and unroll 8.
+template <int MINB, int UNR>
+__global__ void __launch_bounds__(kThreads, MINB) tc_wgrad_kernel(const TcW P) {
   extern __shared__ __align__(128) unsigned char smem[];
   const GemmP& G = P.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -587,7 +590,7 @@ __global__ void __launch_bounds__(kThreads, 3) tc_wgrad_kernel(const TcW P) {
       unsigned char* a_lo = a_hi + plane_a;
       unsigned char* b_hi = stage0 + (size_t)s * stage_sz + 2 * plane_a + (uint32_t)ku * lbo_b + lane_off;
       unsigned char* b_lo = b_hi + plane_bw;
-#pragma unroll 4
+#pragma unroll (UNR)
       for (int m = rl; m < rows_a16; m += 16) {
         float v[4] = {0.f, 0.f, 0.f, 0.f};
         if (m < rows_a) {
@@ -607,7 +610,7 @@ __global__ void __launch_bounds__(kThreads, 3) tc_wgrad_kernel(const TcW P) {
       if (interior) {
         const float* xt = xp + ts0;
         const int st = G.stride;
-#pragma unroll 4
+#pragma unroll (UNR)
         for (int n = rl; n < rows_b16; n += 16) {
           const int ro = roff[n];
           float v[4] = {0.f, 0.f, 0.f, 0.f};
@@ -763,10 +766,13 @@ extern "C" int vbx_tc_conv1d_wgrad(const vbx_conv_desc* d, const float* x, const
                       (size_t)P.NT * (sizeof(int2) + sizeof(int)) + 2 * sizeof(int) + 16;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t ce = cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+    cudaError_t ce = cudaFuncSetAttribute(tc_wgrad_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+    if (ce == cudaSuccess)
+      ce = cudaFuncSetAttribute(tc_wgrad_kernel<3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
     if (ce != cudaSuccess) return fail((int)ce, "tc_conv1d_wgrad: cannot raise the dynamic shared memory limit");
     attr_set = true;
   }
-  tc_wgrad_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(P);
+  if (P.tmem_cols > 128) tc_wgrad_kernel<2, 8><<<grid, kThreads, smem, (cudaStream_t)stream>>>(P);
+  else tc_wgrad_kernel<3, 4><<<grid, kThreads, smem, (cudaStream_t)stream>>>(P);
   return launched("tc_wgrad_kernel");
 }
