@@ -63,9 +63,9 @@ class DiscriminatorEBENMultiScales(nn.Module, PyTorchModelHubMixin):
 
     def forward_multi(self, pairs) -> List[List[List[torch.Tensor]]]:
         """forward() for several independent (bands, audio) pairs at once (e.g. enhanced and reference).
-        The 4 x len(pairs) sub-discriminator passes are independent chains of small / medium kernels: each
-        runs on its own stream so that together they fill the 148 SMs; autograd replays each chain's backward
-        on the stream its forward ran on and inserts the cross-stream waits itself."""
+        The four sub-discriminators are independent chains of small / medium kernels: each runs on its own
+        stream so that together they fill the 148 SMs; autograd replays each chain's backward on the stream
+        its forward ran on and inserts the cross-stream waits itself."""
         nets = list(self.pqmf_discriminators) + [self.melgan_discriminator]
         jobs = []
         for bands, audio in pairs:
@@ -75,23 +75,23 @@ class DiscriminatorEBENMultiScales(nn.Module, PyTorchModelHubMixin):
             jobs.append([selected, selected, selected, audio])
         if not (jobs[0][0].is_cuda and _SIDE_STREAMS):
             return [[net(x) for net, x in zip(nets, inputs)] for inputs in jobs]
+        # One stream per SUB-DISCRIMINATOR (not per pass): every pass of network i runs on stream i, so its
+        # effective weights and packed tiles - created lazily by the first pass and shared by the others -
+        # are produced and consumed in one stream's order, and their allocator lifetime is that stream's.
         cur = torch.cuda.current_stream()
-        streams = self._streams(jobs[0][0].device, 4 * len(jobs))
-        out, used = [], []
-        for j, inputs in enumerate(jobs):
-            embeddings = []
-            for i, (net, x) in enumerate(zip(nets, inputs)):
-                st = streams[4 * j + i]
-                st.wait_stream(cur)
-                x.record_stream(st)
-                with torch.cuda.stream(st):
+        streams = self._streams(jobs[0][0].device, len(nets))
+        out = [[None] * len(nets) for _ in jobs]
+        for i, (net, st) in enumerate(zip(nets, streams)):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                for j, inputs in enumerate(jobs):
+                    x = inputs[i]
+                    x.record_stream(st)
                     emb = net(x)
-                for t in emb[1:]:
-                    t.record_stream(cur)                # consumed by the losses on the caller's stream
-                embeddings.append(emb)
-                used.append(st)
-            out.append(embeddings)
-        for st in used:
+                    for t in emb[1:]:
+                        t.record_stream(cur)            # consumed by the losses on the caller's stream
+                    out[j][i] = emb
+        for st in streams:
             cur.wait_stream(st)
         return out
 
