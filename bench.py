@@ -203,7 +203,10 @@ def run_ours(args):
     wall = parallel.max_over_ranks(wall, dev)
     e2e = {"value": audio_s * args.steps / wall, "unit": "audio-s/s",
            "h2d_bytes_per_step": int(2 * body_h.numel() * 4), "d2h_bytes_per_step": 8,
-           "losses": [float(loss_h[0]), float(loss_h[1])]}
+           "losses": [float(loss_h[0]), float(loss_h[1])],
+           "losses_finite": bool(torch.isfinite(loss_h).all())}
+    if not e2e["losses_finite"]:
+        sys.stderr.write("WARNING: non-finite training losses at the end of the e2e loop - this run is not valid\n")
 
     if rank != 0:
         return

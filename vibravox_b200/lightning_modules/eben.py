@@ -86,8 +86,14 @@ class EBENLightningModule(torch.nn.Module):
             p.requires_grad = True
         self._toggled = []
 
+    @staticmethod
+    def _join(module) -> None:
+        if hasattr(module, "join_streams"):
+            module.join_streams()
+
     def manual_backward(self, loss: torch.Tensor, optimizer) -> None:
         loss.backward()
+        self._join(self.discriminator)
         self._sync_grads(optimizer)
 
     @property
@@ -141,6 +147,7 @@ class EBENLightningModule(torch.nn.Module):
                 # each loss once, down to the generator outputs
                 grads = [torch.autograd.grad(l, (enh, bands), retain_graph=True, allow_unused=True)
                          for l in losses.values()]
+                self._join(D)
                 lambdas = self._balance_from_output_grads(enhanced, enhanced_bands, grads)
                 total_e = torch.empty_like(enh)
                 total_b = torch.empty_like(bands)
@@ -178,6 +185,7 @@ class EBENLightningModule(torch.nn.Module):
                     torch.autograd.backward(backprop_loss_discriminator, inputs=d_params)
                 finally:
                     Flags.skip_leaf_input_grad = False
+                self._join(D)
                 self._sync_grads(d_opt)
                 d_opt.step()
                 d_opt.zero_grad()
@@ -313,6 +321,7 @@ class EBENLightningModule(torch.nn.Module):
         sumsq = torch.zeros(n, device=dev, dtype=torch.float64)
         for i, loss in enumerate(atomic_losses.values()):
             grad = torch.autograd.grad(loss, layer, retain_graph=True)[0]
+            self._join(self.discriminator)
             ops.sumsq(grad.contiguous(), sumsq[i:i + 1])
         lambdas = torch.empty(n, device=dev)
         norms = torch.empty(n, device=dev)

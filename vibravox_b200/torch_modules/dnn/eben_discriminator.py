@@ -95,6 +95,17 @@ class DiscriminatorEBENMultiScales(nn.Module, PyTorchModelHubMixin):
             cur.wait_stream(st)
         return out
 
+    def join_streams(self) -> None:
+        """Make the caller's stream wait for everything queued on the side streams.  Needed after a backward
+        pass whose parameter gradients were accumulated straight into a flat bucket (functional.grad_slot):
+        those writes are invisible to autograd, so its end-of-backward synchronisation does not cover them."""
+        if not torch.cuda.is_available():
+            return
+        cur = torch.cuda.current_stream()
+        for pool in self.__dict__.get("_vbx_streams", {}).values():
+            for st in pool:
+                cur.wait_stream(st)
+
     def _streams(self, device, n):
         cache = self.__dict__.setdefault("_vbx_streams", {})
         pool = cache.setdefault(device, [])
