@@ -48,9 +48,10 @@ def test_discriminator_structure_and_losses(sample):
         assert HingeLossForDiscriminatorMelganMultiScales()(emb_a, target).shape == torch.Size([])
 
 
-@pytest.mark.parametrize("p,q,B,L", [(1, 3, 1, 224), (2, 4, 1, 480), (4, 4, 3, 1000), (2, 3, 5, 4001)])
+@pytest.mark.parametrize("p,q,B,L", [(1, 3, 1, 2600), (2, 4, 1, 2559), (4, 4, 3, 3000), (2, 3, 5, 4001)])
 def test_edge_shapes_match_oracle(p, q, B, L):
-    """batch 1, the shortest valid lengths (one latent frame), odd lengths, every p / q the configs use."""
+    """batch 1, the shortest length the reference's discriminator accepts (2528 samples: below that its
+    dilation-3 branch runs out of samples and PyTorch raises), odd lengths, every p / q the configs use."""
     from oracle import eben_oracle as O
     from vibravox_b200.torch_modules.dnn.eben_discriminator import DiscriminatorEBENMultiScales
     from vibravox_b200.torch_modules.dnn.eben_generator import EBENGenerator
@@ -60,8 +61,6 @@ def test_edge_shapes_match_oracle(p, q, B, L):
     ds = {k: v.detach().clone() for k, v in D.state_dict().items()}
     x = 0.3 * torch.randn(B, 1, L)
     xc = O.cut_to_valid_length(x, 32, 4)
-    if xc.shape[2] < 224:
-        pytest.skip("shorter than one latent frame")
     with torch.no_grad():
         y0, b0 = O.generator_forward(gs, xc, p)
         e0 = O.discriminator_forward(ds, b0, y0, q, 24)
@@ -88,3 +87,18 @@ def test_cpu_tensors_are_refused_not_silently_computed():
         PseudoQMFBanks(4, 32)(torch.randn(1, 1, 1000), "analysis")
     with pytest.raises(ValueError):
         PseudoQMFBanks(4, 32).to(DEV)(torch.randn(1, 1, 1000, device=DEV), "decompose")
+
+
+def test_too_short_input_raises_like_the_reference():
+    """Below 2528 samples the reference raises inside conv1d ("Kernel size can't be greater than actual input
+    size"); the drop-in raises VbxError from the descriptor check instead of computing garbage."""
+    from vibravox_b200 import _lib
+    from vibravox_b200.torch_modules.dnn.eben_discriminator import DiscriminatorEBENMultiScales
+    from vibravox_b200.torch_modules.dnn.eben_generator import EBENGenerator
+    G, D = EBENGenerator(m=4, n=32, p=2).to(DEV), DiscriminatorEBENMultiScales(q=4, min_channels=24).to(DEV)
+    x = G.cut_to_valid_length(torch.randn(1, 1, 1000, device=DEV))
+    with torch.no_grad():
+        y, b = G(x)
+        with pytest.raises((_lib.VbxError, AssertionError)):
+            D(bands=b, audio=y)
+            torch.cuda.synchronize()
