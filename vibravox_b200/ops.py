@@ -52,7 +52,14 @@ class ConvGeom:
     groups: int = 1
 
     def tout(self, Tin: int) -> int:
-        return (Tin + 2 * self.pad - self.dil * (self.K - 1) - 1) // self.stride + 1
+        span = Tin + 2 * self.pad - self.dil * (self.K - 1) - 1
+        if span < 0:      # same condition (and wording) as ATen's conv shape check
+            raise _lib.VbxError(f"Calculated padded input size per channel: ({Tin + 2 * self.pad}). Kernel size: "
+                                f"({self.dil * (self.K - 1) + 1}). Kernel size can't be greater than actual input size")
+        if self.refl > Tin - 1:
+            raise _lib.VbxError(f"Padding size should be less than the corresponding input dimension, but got: "
+                                f"padding ({self.refl}, {self.refl}) at dimension 2 of input of length {Tin}")
+        return span // self.stride + 1
 
     def desc(self, B: int, Tin: int) -> ConvDesc:
         return ConvDesc(B, self.Cin, self.Cout, Tin, self.tout(Tin), self.K, self.stride, self.dil,
