@@ -42,6 +42,14 @@ struct TcP {
   int nphase;       // DGRAD: packed tiles are indexed [g][nt][phase][chunk], nchunks = chunks per phase
   int cpad;         // reduction channels padded to a multiple of 8 (or to 1/2/4): kk = tap*cpad + channel
   int nsplit;       // bf16 components per operand: 2 = hi+lo, 3 MMAs (16 mantissa bits); 3 = hi+mid+lo, 6 MMAs (24 bits)
+  // Merged-phase ("sub-pixel") input gradient of a strided conv (dil = 1, zero halo): all `stride` phases of
+  // dx share the same dy window, so they become COLUMNS of one stride-1 forward-style GEMM
+  //   D[(b,v), (ph,ci)] = sum_{co,m'} dy[b,co, v + m' - padp] * Wm[(ph,ci), (co,m')],   dx[b,ci, r(ph) + s*v] = D
+  // -> dy is gathered once instead of once per phase and the MMA is `stride` times wider.  The kernel then runs
+  // in FWD mode on a re-labelled geometry (g) and only the output indexing differs.
+  int merged;
+  int mg_s, mg_Tx, mg_Cin, mg_Cing;           // stride, dx length, dx channels, dx channels per group
+  int mg_r[8];                                // first position u of each phase
 };
 
 // one reduction segment of a tile: FWD has one; DGRAD has one per mirror image it touches
@@ -272,6 +280,25 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const TcP P) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[j] = 0.f;
       }
+      if (MODE == FWD && P.merged) {
+        // rows are (b, v); column = phase * Cin_g + ci  ->  dx[b, ci, r(phase) + s*v]
+        const int eb = ev ? en / G.Tout : 0, v = ev ? en % G.Tout : 0;
+        int col = nt * NT + blk * 16;
+        int ph = col / P.mg_Cing, ci = col % P.mg_Cing;
+#pragma unroll
+        for (int j = 0; j < 16; ++j, ++col) {
+          if (ev && col < Ccol) {
+            const int u = P.mg_r[ph] + P.mg_s * v;
+            if (u < P.mg_Tx) {
+              const int ch = grp * P.mg_Cing + ci;
+              const long long idx = ((long long)eb * P.mg_Cin + ch) * P.mg_Tx + u;
+              G.Y[idx] = finish(G, acc[j], ch, idx);
+            }
+          }
+          if (++ci == P.mg_Cing) { ci = 0; ++ph; }
+        }
+        continue;
+      }
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int col = nt * NT + blk * 16 + j;
@@ -392,6 +419,72 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, unsigned char* __res
   }
 }
 
+// per-phase tap bookkeeping of the merged-phase dgrad (host side, stride <= 8)
+struct MergedPlan {
+  int c[8], k0[8], nt[8], r[8];
+  int cmax, J;
+};
+static MergedPlan merged_plan(const GemmP& G) {
+  MergedPlan M;
+  M.cmax = -(1 << 30);
+  for (int ph = 0; ph < G.stride; ++ph) {
+    DgradImg im = dgrad_taps(G, ph);
+    M.r[ph] = mod_pos(ph - G.pad, G.stride);
+    M.c[ph] = (M.r[ph] + G.pad) / G.stride - im.kd0_hi;
+    M.k0[ph] = im.k0; M.nt[ph] = im.ntaps;
+    if (im.ntaps > 0 && M.c[ph] > M.cmax) M.cmax = M.c[ph];
+  }
+  M.J = 1;
+  for (int ph = 0; ph < G.stride; ++ph)
+    if (M.nt[ph] > 0 && M.nt[ph] + M.cmax - M.c[ph] > M.J) M.J = M.nt[ph] + M.cmax - M.c[ph];
+  return M;
+}
+struct MergedDev { int c[8], k0[8], nt[8], cmax, J, s, Cin_g, Cout_g, K; };
+
+// Wm[(ph,ci), (m', co)] = W[co][ci][k0(ph) + jj*s],  jj = (J-1-m') - (cmax - c(ph)),  zero outside the phase's taps
+__global__ void tc_pack_merged_kernel(const float* __restrict__ w, unsigned char* __restrict__ out, const TcP P,
+                                      const MergedDev M) {
+  const int NT = P.NT;
+  const int Ccol = M.s * M.Cin_g;
+  const long long units = (long long)P.g.groups * P.ntiles_n * P.nchunks * 4 * NT;
+  for (long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x; u < units;
+       u += (long long)gridDim.x * blockDim.x) {
+    int n = (int)(u % NT);
+    long long r = u / NT;
+    int ku = (int)(r % 4); r /= 4;
+    int c = (int)(r % P.nchunks); r /= P.nchunks;
+    int nt = (int)(r % P.ntiles_n);
+    int g = (int)(r / P.ntiles_n);
+    const int col = nt * NT + n;
+    const int ph = col / M.Cin_g, ci = col % M.Cin_g;
+    const int kk0 = c * kKC + ku * 8;
+    __align__(16) __nv_bfloat16 hi[8], lo[8], lo3[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = 0.f;
+      const int kk = kk0 + j;
+      const int mp = kk / P.cpad, cr = kk % P.cpad;
+      if (col < Ccol && cr < M.Cout_g && mp < M.J) {
+        const int jj = (M.J - 1 - mp) - (M.cmax - M.c[ph]);
+        if (jj >= 0 && jj < M.nt[ph])
+          v = w[(((long long)g * M.Cout_g + cr) * M.Cin_g + ci) * M.K + M.k0[ph] + jj * M.s];
+      }
+      split_bf16(v, hi[j], lo[j]);
+      lo3[j] = __float2bfloat16_rn((v - __bfloat162float(hi[j])) - __bfloat162float(lo[j]));
+    }
+    unsigned char* base = out + ((((size_t)(g * P.ntiles_n + nt)) * P.nchunks + c)) * P.nsplit * plane_b(NT);
+    const size_t off = ((size_t)ku * NT + n) * 16;
+    *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(base + plane_b(NT) + off) = *reinterpret_cast<const uint4*>(lo);
+    if (P.nsplit == 3) *reinterpret_cast<uint4*>(base + 2 * plane_b(NT) + off) = *reinterpret_cast<const uint4*>(lo3);
+  }
+}
+
+static bool use_merged(const GemmP& G) {
+  static const bool off = getenv("VBX_TC_MERGED") && atoi(getenv("VBX_TC_MERGED")) == 0;
+  return !off && G.stride > 1 && G.stride <= 8 && G.dil == 1 && G.refl == 0;
+}
+
 static int fill_tc(TcP& P, const vbx_conv_desc* d, int mode, int nsplit) {
   int code = 0;
   const char* msg = check_desc_msg(d, &code);
@@ -399,6 +492,20 @@ static int fill_tc(TcP& P, const vbx_conv_desc* d, int mode, int nsplit) {
   if (nsplit != 2 && nsplit != 3) return fail(VBX_UNSUPPORTED, "tc: nsplit must be 2 (bf16x3) or 3 (bf16x6)");
   fill(P.g, d);
   P.nsplit = nsplit;
+  P.merged = 0;
+  if (mode == DGRAD && use_merged(P.g)) {
+    // re-label the geometry: a stride-1 forward conv dy (Cout ch, Tout long) -> D (s*Cin ch, V long)
+    const GemmP o = P.g;
+    const MergedPlan M = merged_plan(o);
+    P.merged = 1;
+    P.mg_s = o.stride; P.mg_Tx = o.Tin; P.mg_Cin = o.Cin; P.mg_Cing = o.Cin_g;
+    for (int ph = 0; ph < 8; ++ph) P.mg_r[ph] = ph < o.stride ? M.r[ph] : 0;
+    P.g.Cin = o.Cout; P.g.Cin_g = o.Cout_g;
+    P.g.Cout = o.stride * o.Cin; P.g.Cout_g = o.stride * o.Cin_g;
+    P.g.Tin = o.Tout; P.g.Tout = (o.Tin + o.stride - 1) / o.stride;
+    P.g.K = M.J; P.g.stride = 1; P.g.dil = 1; P.g.pad = M.J - 1 - M.cmax; P.g.refl = 0;
+    mode = FWD;
+  }
   const int Ccol = mode == FWD ? P.g.Cout_g : P.g.Cin_g;
   P.NT = pick_nt(Ccol);
   P.ntiles_n = (Ccol + P.NT - 1) / P.NT;
@@ -707,6 +814,18 @@ extern "C" int vbx_tc_pack(const vbx_conv_desc* d, int32_t mode, int32_t nsplit,
   if (int r = fill_tc(P, d, mode, nsplit)) return r;
   VBX_REQUIRE(w && packed, VBX_BAD_POINTER, "tc_pack: null tensor");
   VBX_REQUIRE(((uintptr_t)packed & 15) == 0, VBX_BAD_POINTER, "tc_pack: packed buffer must be 16-byte aligned");
+  if (P.merged) {
+    GemmP o; fill(o, d);
+    const MergedPlan M = merged_plan(o);
+    MergedDev D;
+    for (int i = 0; i < 8; ++i) { D.c[i] = M.c[i]; D.k0[i] = M.k0[i]; D.nt[i] = i < o.stride ? M.nt[i] : 0; }
+    D.cmax = M.cmax; D.J = M.J; D.s = o.stride; D.Cin_g = o.Cin_g; D.Cout_g = o.Cout_g; D.K = o.K;
+    long long units = (long long)P.g.groups * P.ntiles_n * P.nchunks * 4 * P.NT;
+    int blocks = (int)((units + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    tc_pack_merged_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (unsigned char*)packed, P, D);
+    return launched("tc_pack_merged_kernel");
+  }
   return mode == FWD ? pack_tc<FWD>(P, w, packed, (cudaStream_t)stream)
                      : pack_tc<DGRAD>(P, w, packed, (cudaStream_t)stream);
 }
@@ -732,6 +851,7 @@ extern "C" int vbx_tc_conv1d_dgrad(const vbx_conv_desc* d, const float* dy, cons
   fill_epi(P.g, e);
   P.g.X = dy; P.g.Y = dx;
   P.packed = (const unsigned char*)packed;
+  if (P.merged) return launch_tc<FWD>(P, (cudaStream_t)stream);
   return launch_tc<DGRAD>(P, (cudaStream_t)stream);
 }
 
