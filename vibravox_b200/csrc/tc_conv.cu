@@ -482,7 +482,8 @@ __global__ void tc_pack_merged_kernel(const float* __restrict__ w, unsigned char
 
 static bool use_merged(const GemmP& G) {
   static const bool off = getenv("VBX_TC_MERGED") && atoi(getenv("VBX_TC_MERGED")) == 0;
-  return !off && G.stride > 1 && G.stride <= 8 && G.dil == 1 && G.refl == 0;
+  // (with >= 256 channels per group every phase already fills a 256-wide tile: nothing to merge)
+  return !off && G.stride > 1 && G.stride <= 8 && G.dil == 1 && G.refl == 0 && G.Cin_g < 256;
 }
 
 static int fill_tc(TcP& P, const vbx_conv_desc* d, int mode, int nsplit) {
