@@ -170,7 +170,9 @@ def run_ours(args):
     if args.profile:
         step()
         torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()     # ncu --profile-from-start off sees exactly --steps steps
         t_dev, _ = timed(step, args.steps)
+        torch.cuda.cudart().cudaProfilerStop()
         if rank == 0:
             print(json.dumps({"profile_run": True, "ms_per_step": t_dev / args.steps * 1e3}))
         return

@@ -584,6 +584,24 @@ struct TcW {
 __host__ __device__ inline int lbo_wb(int NT) { return NT * 16 + 16; }
 __host__ __device__ inline int wstage_bytes(int NT) { return 2 * 4 * kLboW + 2 * 4 * lbo_wb(NT); }
 
+// Row loops of the wgrad producers: U rows' loads are issued back to back, then the U converts + stores; the tail
+// goes through 4 / 2 / 1-row batches so short tiles also keep several loads in flight.
+template <int U, class L, class St>
+__device__ __forceinline__ void row_batch(int m, L& load, St& store) {
+  float v[U][4];
+#pragma unroll
+  for (int u = 0; u < U; ++u) load(m + 16 * u, v[u]);
+#pragma unroll
+  for (int u = 0; u < U; ++u) store(m + 16 * u, v[u]);
+}
+template <int UNR, class L, class St>
+__device__ __forceinline__ void row_loop(int m, int end, L load, St store) {
+  for (; m + 16 * (UNR - 1) < end; m += 16 * UNR) row_batch<UNR>(m, load, store);
+  if (UNR > 4 && m + 48 < end) { row_batch<4>(m, load, store); m += 64; }
+  if (UNR > 2 && m + 16 < end) { row_batch<2>(m, load, store); m += 32; }
+  if (m < end) row_batch<1>(m, load, store);
+}
+
 // MINB / UNR: CTAs per SM the register budget allows and the row-loop unroll (loads in flight per lane).
 // N = 256 tiles own 256 TMEM columns, so only two CTAs fit per SM anyway: they get 96 registers and unroll 8.
 template <int MINB, int UNR>
@@ -693,56 +711,77 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_wgrad_kernel(const TcW P) {
         if (t >= G.Tout) { t -= G.Tout; ++b; }           // 4 consecutive positions cross at most one boundary
         eb[e] = b; et[e] = e < nval ? t : -1;
       }
+      // The row loops below contain no control flow (out-of-range rows / elements load a safe address and are
+      // zeroed by selects), so the unrolled iterations' loads are all issued before the first convert waits.
+      // A warp with any boundary lane takes the masked form for all its lanes (cost = max, not sum, of the two).
+      const bool wfast = __all_sync(0xffffffffu, fast);
+      const bool wint = __all_sync(0xffffffffu, interior);
       mbar_wait(&empty[s], (use & 1) ^ 1);
       unsigned char* a_hi = stage0 + (size_t)s * stage_sz + (uint32_t)ku * kLboW + lane_off;
       unsigned char* a_lo = a_hi + plane_a;
       unsigned char* b_hi = stage0 + (size_t)s * stage_sz + 2 * plane_a + (uint32_t)ku * lbo_b + lane_off;
       unsigned char* b_lo = b_hi + plane_bw;
-#pragma unroll (UNR)
-      for (int m = rl; m < rows_a16; m += 16) {
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (m < rows_a) {
-          if (fast) {
-            const float* q = dyp + (long long)m * G.Tout;
+      auto store_a = [&](int m, const float (&v)[4]) { put4(a_hi + m * 16, a_lo + m * 16, v); };
+      auto store_b = [&](int n, const float (&v)[4]) { put4(b_hi + n * 16, b_lo + n * 16, v); };
+      if (wfast) {
+        row_loop<UNR>(rl, rows_a16, [&](int m, float (&v)[4]) {
+          const bool ok = m < rows_a;
+          const float* q = dyp + (long long)(ok ? m : 0) * G.Tout;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = q[e];
-          } else {
+          for (int e = 0; e < 4; ++e) v[e] = q[e];
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (et[e] >= 0)
-                v[e] = G.DY[((long long)eb[e] * G.Cout + grp * G.Cout_g + co_base + m) * G.Tout + et[e]];
-          }
-        }
-        put4(a_hi + m * 16, a_lo + m * 16, v);
+          for (int e = 0; e < 4; ++e) v[e] = ok ? v[e] : 0.f;
+        }, store_a);
+      } else {
+        const float* pa[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          pa[e] = et[e] >= 0 ? G.DY + ((long long)eb[e] * G.Cout + grp * G.Cout_g + co_base) * G.Tout + et[e] : G.DY;
+        row_loop<UNR>(rl, rows_a16, [&](int m, float (&v)[4]) {
+          const bool ok = m < rows_a;
+          const long long mo = ok ? (long long)m * G.Tout : 0;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = pa[e][et[e] >= 0 ? mo : 0];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = (ok && et[e] >= 0) ? v[e] : 0.f;
+        }, store_a);
       }
-      if (interior) {
+      if (wint) {
         const float* xt = xp + ts0;
         const int st = G.stride;
-#pragma unroll (UNR)
-        for (int n = rl; n < rows_b16; n += 16) {
+        const int ro0 = roff[0];                         // column 0 of a tile always exists: the safe address
+        row_loop<UNR>(rl, rows_b16, [&](int n, float (&v)[4]) {
           const int ro = roff[n];
-          float v[4] = {0.f, 0.f, 0.f, 0.f};
-          if (ro != INT_MIN) {
-            const float* q = xt + ro;
+          const bool ok = ro != INT_MIN;
+          const float* q = xt + (ok ? ro : ro0);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = q[e * st];
-          }
-          put4(b_hi + n * 16, b_lo + n * 16, v);
-        }
+          for (int e = 0; e < 4; ++e) v[e] = q[e * st];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = ok ? v[e] : 0.f;
+        }, store_b);
       } else {
-        for (int n = rl; n < rows_b16; n += 16) {
-          const int2 ri = rowinfo[n];
-          float v[4] = {0.f, 0.f, 0.f, 0.f};
-          if (ri.y != INT_MIN) {
+        const float* xb[4];
+        int ets[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (et[e] >= 0) {
-                const int p = map_pos(et[e] * G.stride + ri.y, G.Tin, G.refl);
-                if (p >= 0) v[e] = G.X[((long long)eb[e] * G.Cin + grp * G.Cin_g) * G.Tin + ri.x + p];
-              }
-          }
-          put4(b_hi + n * 16, b_lo + n * 16, v);
+        for (int e = 0; e < 4; ++e) {
+          xb[e] = G.X + (et[e] >= 0 ? ((long long)eb[e] * G.Cin + grp * G.Cin_g) * G.Tin : 0);
+          ets[e] = et[e] * G.stride;
         }
+        row_loop<UNR>(rl, rows_b16, [&](int n, float (&v)[4]) {
+          const int2 ri = rowinfo[n];
+          const bool ok = ri.y != INT_MIN;
+          const int ky = ok ? ri.y : 0;
+          bool val[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int pp = ets[e] + ky;                  // map_pos as selects (no branches between the loads)
+            const int p = pp < 0 ? -pp : (pp >= G.Tin ? 2 * (G.Tin - 1) - pp : pp);
+            val[e] = ok & (et[e] >= 0) & (pp >= -G.refl) & (pp < G.Tin + G.refl);
+            v[e] = xb[e][val[e] ? ri.x + p : 0];
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = val[e] ? v[e] : 0.f;
+        }, store_b);
       }
       fence_proxy_async();
       mbar_arrive(&full[s]);
