@@ -150,8 +150,11 @@ def run_ours(args):
     body_d, air_d = body_h.to(dev), air_h.to(dev)
     batch = {"audio_body_conducted": body_d, "audio_airborne": air_d}
 
+    graphed = (not args.no_graph) and (not args.profile) and lm.graph_capturable()
+
     def step():
-        lm.training_step(batch)
+        # the public call: replays the captured step (after 2 eager calls + 1 capture, all inside the warm-up)
+        (lm.training_step_graphed if graphed else lm.training_step)(batch)
 
     def timed(fn, k):
         parallel.barrier()
@@ -176,7 +179,8 @@ def run_ours(args):
         if rank == 0:
             print(json.dumps({"profile_run": True, "ms_per_step": t_dev / args.steps * 1e3}))
         return
-    for _ in range(max(args.warmup, 3)):
+    n_warm = max(args.warmup, 3) + (3 if graphed else 0)   # graph mode: 2 eager calls + the capture come first
+    for _ in range(n_warm):
         step()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -184,6 +188,9 @@ def run_ours(args):
     n0 = _lib.launch_count()
     t_dev, _ = timed(step, args.steps)
     launches = _lib.launch_count() - n0
+    if graphed:
+        assert lm.graph_launches() > 0, "the step was not captured during the warm-up"
+        launches = lm.graph_launches() * args.steps     # kernel nodes of the replayed graph, counted at capture
     clocks = sampler.stop() if rank == 0 else None
     audio_s = world * B * L / SR
     value = audio_s * args.steps / t_dev
@@ -191,11 +198,15 @@ def run_ours(args):
     # e2e: the public call with HOST buffers; H2D of the step's inputs and D2H of its losses inside the timed region
     stage_body, stage_air = torch.empty_like(body_d), torch.empty_like(air_d)
     loss_h = torch.empty(2, dtype=torch.float32).pin_memory()
+    host_batch = {"audio_body_conducted": body_h, "audio_airborne": air_h}
 
     def e2e_step():
-        stage_body.copy_(body_h, non_blocking=True)
-        stage_air.copy_(air_h, non_blocking=True)
-        lm.training_step({"audio_body_conducted": stage_body, "audio_airborne": stage_air})
+        if graphed:
+            lm.training_step_graphed(host_batch)          # H2D straight into the captured step's input buffers
+        else:
+            stage_body.copy_(body_h, non_blocking=True)
+            stage_air.copy_(air_h, non_blocking=True)
+            lm.training_step({"audio_body_conducted": stage_body, "audio_airborne": stage_air})
         loss_h[0:1].copy_(lm.logged["train/generator/backprop_loss"].view(1), non_blocking=True)
         loss_h[1:2].copy_(lm.logged["train/discriminator/backprop_loss"].view(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -219,12 +230,13 @@ def run_ours(args):
     roof = dict(kernels[0]) if kernels else None
     line = {
         "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
+        "warmup": n_warm, "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
         "config": {"workload": f"EBEN BWE full train step (gen+disc+MR-STFT/FM/hinge, EMA balancing, 2x Adam) "
                                f"bs={B}x{args.seconds:g}s@16kHz per GPU (L={L} after cut_to_valid_length), "
                                f"m=4 n=32 p=2 q=4 min_channels=24, schedule={lm.schedule}",
                    "batch_per_gpu": B, "samples": L, "parallelism": f"dp{world}",
+                   "launch": "one CUDA graph replay per step" if graphed else "eager launches",
                    "l2": "per-step working set (activations ~ GBs) >> 126 MB L2; no explicit flush"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roof, "kernel_rooflines": kernels,
@@ -288,6 +300,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--seconds", type=float, default=3.0)
     ap.add_argument("--cpu-batch", type=int, default=4)

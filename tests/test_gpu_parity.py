@@ -225,3 +225,38 @@ def test_full_size_properties(path):
         e5 = D(bands=bands[5:6].contiguous(), audio=y[5:6].contiguous())
         for sa, sb in zip(emb, e5):
             assert (sa[-1][5:6] - sb[-1]).abs().max() < 1e-4
+
+
+def test_graphed_step_matches_eager_and_golden(golden_dir):
+    """training_step_graphed (2 eager calls, capture, replays) walks the same trajectory as training_step:
+    the first two steps match the reference's golden logs, and over 6 steps the captured replay stays with an
+    eager twin to within the drift two eager runs show between themselves (fp32 atomics in the split-K sums)."""
+    import vibravox_b200
+    from oracle import eben_oracle as O
+    gold = torch.load(os.path.join(golden_dir, "train_step.pt"))
+    body, air = O.synthetic_pairs(gold["B"], gold["S"], seed=gold["data_seed"])
+    batch = {"audio_body_conducted": body.to(DEV), "audio_airborne": air.to(DEV)}
+    host_batch = {"audio_body_conducted": body.pin_memory(), "audio_airborne": air.pin_memory()}
+    keys = ("train/generator/backprop_loss", "train/discriminator/backprop_loss")
+
+    def run(graphed):
+        lm = vibravox_b200.build_model(seed=gold["model_seed"], device=DEV)
+        assert lm.graph_capturable()
+        tr = []
+        for it in range(6):
+            out = lm.training_step_graphed(host_batch) if graphed else lm.training_step(batch)
+            tr.append([float(lm.logged[k]) for k in keys] + [float(out["enhanced"].abs().mean())])
+        return lm, tr
+
+    lm_g, tr_g = run(True)
+    assert lm_g.graph_launches() > 500                      # the whole step was captured
+    assert int(lm_g.generator_optimizer.step_count) == 6    # one Adam tick per call, eager or replayed
+    _, tr_e = run(False)
+    _, tr_e2 = run(False)
+    for it in range(2):
+        for k, got in zip(keys, tr_g[it]):
+            want = gold["steps"][it]["logs"][k[len("train/"):]]
+            assert got == pytest.approx(want, rel=3e-3), (it, k)
+    for it in range(6):
+        for a, b, c in zip(tr_g[it], tr_e[it], tr_e2[it]):
+            assert abs(a - b) <= 5 * abs(b - c) + 2e-3 * abs(b), (it, tr_g[it], tr_e[it], tr_e2[it])

@@ -60,6 +60,8 @@ class EBENLightningModule(torch.nn.Module):
         # balancing state (eben.py:73,230-235) lives on the device: EMA of the gradient norms
         self._bal = None
         self.logged: Dict[str, torch.Tensor] = {}
+        self._graphs: Dict[tuple, dict] = {}      # training_step_graphed: one captured step per batch shape
+        self.graph_warmup_steps = 2
 
     # ---- Lightning services, restated --------------------------------------------------------
     def optimizers(self, use_pl_optimizer: bool = True):
@@ -106,6 +108,55 @@ class EBENLightningModule(torch.nn.Module):
               and self.adversarial_loss_fn is not None and self.reconstructive_loss_temp_fn is None
               and self.dynamic_loss_balancing is not None)
         return self._training_step_shared(batch) if ok else self._training_step_reference(batch)
+
+    def graph_capturable(self) -> bool:
+        """The step replays as one CUDA graph when nothing in it is decided on the host per step."""
+        single = not (torch.distributed.is_available() and torch.distributed.is_initialized()
+                      and torch.distributed.get_world_size() > 1)
+        flat = all(isinstance(o, FlatAdam) for o in self.configure_optimizers())
+        return single and flat and self.update_discriminator_ratio >= 1
+
+    def training_step_graphed(self, batch: Dict[str, torch.Tensor]):
+        """`training_step` replayed from a CUDA graph (all streams of the step included): the ~1300 kernel launches
+        of a step cost one cudaGraphLaunch, so the step no longer depends on how fast the host can issue them.
+        Every call performs exactly one training step: the first `graph_warmup_steps` calls for a batch shape run
+        eagerly (they fill the weight / filter caches that outlive a step), the next call captures the step and
+        replays it, later calls copy the batch into the captured input buffers and replay.  `batch` tensors may
+        live on the host (pinned) or the device.  The returned tensors and `self.logged` are the graph's static
+        outputs: valid until the next call.  Learning rates are baked in at capture time."""
+        if not self.graph_capturable():
+            dev = self.generator.last_conv.weight.device
+            return self.training_step({k: v.to(dev, non_blocking=True) for k, v in batch.items()
+                                       if isinstance(v, torch.Tensor)})
+        names = ("audio_body_conducted", "audio_airborne")
+        key = tuple(tuple(batch[n].shape) for n in names)
+        st = self._graphs.get(key)
+        if st is None:
+            dev = self.generator.last_conv.weight.device
+            st = self._graphs[key] = dict(calls=0, graph=None, out=None, logged=None, launches=0,
+                                          inputs={n: torch.empty(batch[n].shape, device=dev, dtype=torch.float32)
+                                                  for n in names})
+        for n in names:
+            st["inputs"][n].copy_(batch[n], non_blocking=True)
+        if st["graph"] is None:
+            st["calls"] += 1
+            if st["calls"] <= self.graph_warmup_steps:
+                return self.training_step(st["inputs"])
+            from .. import _lib
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(graph):
+                st["out"] = self.training_step(st["inputs"])
+            st["launches"] = _lib.launch_count() - n0
+            st["graph"], st["logged"] = graph, dict(self.logged)
+        self.logged = st["logged"]
+        st["graph"].replay()
+        return st["out"]
+
+    def graph_launches(self) -> int:
+        """Kernels of this library inside one captured step (0 before capture)."""
+        return max([st["launches"] for st in self._graphs.values()], default=0)
 
     def _training_step_shared(self, batch: Dict[str, torch.Tensor]):
         """eben.py:82-130 with the redundant traversals removed.  Equalities used:

@@ -10,8 +10,8 @@ from . import parallel
 
 
 class Trainer:
-    def __init__(self, max_steps: int = 100, log_every_n_steps: int = 10, **_ignored):
-        self.max_steps, self.log_every = max_steps, log_every_n_steps
+    def __init__(self, max_steps: int = 100, log_every_n_steps: int = 10, use_cuda_graph: bool = True, **_ignored):
+        self.max_steps, self.log_every, self.use_cuda_graph = max_steps, log_every_n_steps, use_cuda_graph
 
     def fit(self, module, datamodule):
         rank, local_rank, world = parallel.init_from_env("nccl")
@@ -21,7 +21,10 @@ class Trainer:
         it = datamodule.batches(dev, rank)
         t0 = time.perf_counter()
         for step in range(1, self.max_steps + 1):
-            module.training_step(next(it))
+            if self.use_cuda_graph and hasattr(module, "training_step_graphed"):
+                module.training_step_graphed(next(it))      # falls back to eager launches when not capturable
+            else:
+                module.training_step(next(it))
             if rank == 0 and step % self.log_every == 0:
                 torch.cuda.synchronize()
                 logs = {k.replace("train/", ""): round(float(v), 5) for k, v in module.logged.items()}
