@@ -134,19 +134,28 @@ class EBENLightningModule(torch.nn.Module):
         if st is None:
             dev = self.generator.last_conv.weight.device
             st = self._graphs[key] = dict(calls=0, graph=None, out=None, logged=None, launches=0,
+                                          stream=torch.cuda.Stream(dev),
                                           inputs={n: torch.empty(batch[n].shape, device=dev, dtype=torch.float32)
                                                   for n in names})
         for n in names:
             st["inputs"][n].copy_(batch[n], non_blocking=True)
         if st["graph"] is None:
             st["calls"] += 1
+            side = st["stream"]
             if st["calls"] <= self.graph_warmup_steps:
-                return self.training_step(st["inputs"])
+                # eager, but on the stream the capture will use: autograd's cached gradient-accumulation nodes
+                # remember the stream they were created on, and one created on the legacy default stream
+                # cannot take part in a capture
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    out = self.training_step(st["inputs"])
+                torch.cuda.current_stream().wait_stream(side)
+                return out
             from .. import _lib
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=side):
                 st["out"] = self.training_step(st["inputs"])
             st["launches"] = _lib.launch_count() - n0
             st["graph"], st["logged"] = graph, dict(self.logged)
@@ -240,7 +249,7 @@ class EBENLightningModule(torch.nn.Module):
                 self._sync_grads(d_opt)
                 d_opt.step()
                 d_opt.zero_grad()
-        return {"corrupted": corrupted_speech, "enhanced": enhanced, "reference": reference_speech}
+        return {"corrupted": corrupted_speech, "enhanced": enhanced.detach(), "reference": reference_speech}
 
     def _balance_from_output_grads(self, enhanced, enhanced_bands, grads) -> torch.Tensor:
         """dynamically_balance_losses (eben.py:222-240) from the loss gradients at the generator outputs."""
@@ -330,7 +339,7 @@ class EBENLightningModule(torch.nn.Module):
                 discriminator_optimizer.zero_grad()
         self.untoggle_optimizer(discriminator_optimizer)
 
-        return {"corrupted": corrupted_speech, "enhanced": enhanced_speech, "reference": reference_speech}
+        return {"corrupted": corrupted_speech, "enhanced": enhanced_speech.detach(), "reference": reference_speech}
 
     def compute_atomic_losses(self, network: str, enhanced_speech, reference_speech, decomposed_enhanced_speech,
                               decomposed_reference_speech) -> "OrderedDict[str, torch.Tensor]":
