@@ -27,6 +27,8 @@
 namespace vbx {
 namespace tc {
 
+template <int V> struct IntC { static constexpr int value = V; };
+
 static const int kRows = 128;               // MMA M
 static const int kKC = 32;                  // reduction elements per stage (2 MMA k-steps of 16)
 static const int kSboA = 144;               // bytes between consecutive 8-row units of A (padded: conflict-free stores)
@@ -172,7 +174,8 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const TcP P) {
     const uint32_t st_off = (uint32_t)kq * kLboA + (uint32_t)(r0 >> 3) * kSboA + (uint32_t)(r0 & 7) * 2;
     const int cpad = P.cpad;
     const int chan_stride = MODE == FWD ? G.Tin : G.Tout;
-    int c = 0;                                           // global chunk counter (pipeline position)
+    int s = 0;                                           // pipeline position: stage and parity of its use count
+    uint32_t par = 0;
     for (int sg = 0; sg < nseg; ++sg) {
       const Seg seg = segs[sg];
       const int Kmod = MODE == FWD ? G.K : seg.ntaps;    // taps walked by the reduction
@@ -208,7 +211,7 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const TcP P) {
       };
       int tap = 0, c0 = kq * 8;                          // cpad % 8 == 0 walk: (tap, first channel) of this thread's run
       if ((cpad & 7) == 0) { tap = c0 / cpad; c0 %= cpad; }
-      for (int cs = 0; cs < seg.nchunks; ++cs, ++c) {
+      for (int cs = 0; cs < seg.nchunks; ++cs) {
         float xa[8], xb[8];
         if ((cpad & 7) == 0) {
           const int pa = tap_pos(0, tap), pb = tap_pos(1, tap);
@@ -224,16 +227,27 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const TcP P) {
           while (c0 >= cpad) { c0 -= cpad; ++tap; }
         } else {                                         // cpad in {1,2,4}: a run spans 8/cpad taps
           const int kk0 = cs * kKC + kq * 8;
+          auto small = [&](auto CP_) {
+            constexpr int CP = decltype(CP_)::value;
+            const int tp0 = kk0 / CP;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int kk = kk0 + i, tp = kk / cpad, ci = kk % cpad;
-            const int pa = tap_pos(0, tp), pb = tap_pos(1, tp);
-            xa[i] = (pa >= 0 && ci < Cred) ? srcr[0][ci * chan_stride + pa] : 0.f;
-            xb[i] = (pb >= 0 && ci < Cred) ? srcr[1][ci * chan_stride + pb] : 0.f;
-          }
+            for (int ti = 0; ti < 8 / CP; ++ti) {
+              const int pa = tap_pos(0, tp0 + ti), pb = tap_pos(1, tp0 + ti);
+#pragma unroll
+              for (int ci = 0; ci < CP; ++ci) {
+                const bool cv = ci < Cred;
+                const float va = srcr[0][(cv ? ci : 0) * chan_stride + (pa >= 0 ? pa : 0)];
+                const float vb = srcr[1][(cv ? ci : 0) * chan_stride + (pb >= 0 ? pb : 0)];
+                xa[ti * CP + ci] = (pa >= 0 && cv) ? va : 0.f;
+                xb[ti * CP + ci] = (pb >= 0 && cv) ? vb : 0.f;
+              }
+            }
+          };
+          if (cpad == 4) small(IntC<4>{});
+          else if (cpad == 2) small(IntC<2>{});
+          else small(IntC<1>{});
         }
-        const int s = c % S, use = c / S;
-        mbar_wait(&empty[s], (use & 1) ^ 1);
+        mbar_wait(&empty[s], par ^ 1u);
         unsigned char* a_hi = stage0 + (size_t)s * stage_sz + st_off;
         unsigned char* a_lo = a_hi + kPlaneA;
 #pragma unroll
@@ -251,6 +265,7 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const TcP P) {
         }
         fence_proxy_async();
         mbar_arrive(&full_a[s]);
+        if (++s == S) { s = 0; par ^= 1u; }
       }
     }
     // ===================== epilogue: TMEM -> registers -> fused output stage -> (B,C,T) =====================
@@ -299,10 +314,43 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const TcP P) {
         }
         continue;
       }
+      const int cb = nt * NT + blk * 16;
+      if (!ev) continue;                                 // (the TMEM load above is warp-collective)
+      if (cb + 16 <= Ccol && G.beta == 0.f) {
+        // full block: uniform option branches outside the column loops, 16 independent loads / stores each
+        const long long o = out_base + (long long)cb * Tlen;
+        if (G.bias) {
+          const float* bp = G.bias + grp * Ccol + cb;
 #pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] += __ldg(bp + j);
+        }
+        if (G.mask) {
+          unsigned char* mp = G.mask + o;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) mp[(long long)j * Tlen] = acc[j] > 0.f ? 1 : 0;
+        }
+        if (G.slope != 1.f) {
+          const float sl = G.slope;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = acc[j] > 0.f ? acc[j] : acc[j] * sl;
+        }
+        if (G.res) {
+          const float* rp = G.res + o;
+          float r[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] = rp[(long long)j * Tlen];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] += r[j];
+        }
+        float* yp = G.Y + o;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) yp[(long long)j * Tlen] = acc[j];
+        continue;
+      }
+#pragma unroll 1
       for (int j = 0; j < 16; ++j) {
-        const int col = nt * NT + blk * 16 + j;
-        if (ev && col < Ccol) {
+        const int col = cb + j;
+        if (col < Ccol) {
           const long long idx = out_base + (long long)col * Tlen;
           G.Y[idx] = finish(G, acc[j], grp * Ccol + col, idx);
         }
@@ -314,13 +362,13 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const TcP P) {
       const uint32_t idesc = make_idesc_bf16(NT, /*a_mn=*/true, /*b_mn=*/false);
       const uint32_t lbo_b = (uint32_t)NT * 16;
       uint32_t accumulate = 0;
-      int c = 0;
+      int s = 0;
+      uint32_t par = 0;
       for (int sg = 0; sg < nseg; ++sg) {
         const int nch = segs[sg].nchunks;
-        for (int cs = 0; cs < nch; ++cs, ++c) {
-          const int s = c % S, use = c / S;
-          mbar_wait(&full_a[s], use & 1);
-          mbar_wait(&full_b[s], use & 1);
+        for (int cs = 0; cs < nch; ++cs) {
+          mbar_wait(&full_a[s], par);
+          mbar_wait(&full_b[s], par);
           tc_fence_after();
           const uint32_t a0 = smem_u32(stage0 + (size_t)s * stage_sz);
           const uint32_t b0 = a0 + NS * kPlaneA;
@@ -344,6 +392,7 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const TcP P) {
             }
           }
           mma_commit(&empty[s]);       // frees the stage once these MMAs have read it
+          if (++s == S) { s = 0; par ^= 1u; }
         }
       }
       if (nseg > 0) mma_commit(acc_full);
@@ -353,16 +402,17 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const TcP P) {
     // ===================== weight tiles: linear bulk copies (TMA engine) =====================
     if (lane == 0) {
       const uint32_t bytes = (uint32_t)NS * (uint32_t)plane_b(NT);
-      int c = 0;
+      int s = 0;
+      uint32_t par = 0;
       for (int sg = 0; sg < nseg; ++sg) {
         const Seg seg = segs[sg];
         const unsigned char* src =
             P.packed + (((size_t)(grp * P.ntiles_n + nt) * P.nphase + seg.phase) * P.nchunks) * bytes;
-        for (int cs = 0; cs < seg.nchunks; ++cs, ++c) {
-          const int s = c % S, use = c / S;
-          mbar_wait(&empty[s], (use & 1) ^ 1);
+        for (int cs = 0; cs < seg.nchunks; ++cs) {
+          mbar_wait(&empty[s], par ^ 1u);
           mbar_expect_tx(&full_b[s], bytes);
           bulk_copy_g2s(stage0 + (size_t)s * stage_sz + NS * kPlaneA, src + (size_t)cs * bytes, bytes, &full_b[s]);
+          if (++s == S) { s = 0; par ^= 1u; }
         }
       }
     }
