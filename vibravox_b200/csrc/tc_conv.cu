@@ -596,7 +596,8 @@ static int launch_tc(const TcP& P, cudaStream_t st) {
   dim3 grid((unsigned)((rows + kRows - 1) / kRows), (unsigned)(P.ntiles_n * P.g.groups),
             (unsigned)(MODE == FWD ? 1 : P.g.stride));
   if (grid.y > 65535 || grid.z > 65535) return fail(VBX_UNSUPPORTED, "tc_conv: grid too large");
-  if (smem_bytes(P) <= 56 * 1024 && P.tmem_cols <= 128)
+  static const int max_chunks4 = getenv("VBX_TC_MINB4_CHUNKS") ? atoi(getenv("VBX_TC_MINB4_CHUNKS")) : 0;   // 0: the 48-register variant is off (it spills; measured slower on every layer)
+  if (smem_bytes(P) <= 56 * 1024 && P.tmem_cols <= 128 && P.nchunks <= max_chunks4)
     tc_conv_kernel<MODE, 4><<<grid, kThreads, smem_bytes(P), st>>>(P);
   else
     tc_conv_kernel<MODE, 3><<<grid, kThreads, smem_bytes(P), st>>>(P);
