@@ -15,7 +15,17 @@ def cuda(*ts):
     return [t.to(DEV) for t in ts]
 
 
-@pytest.mark.parametrize("case", CASES, ids=[str(c) for c in CASES])
+# one input channel per group -> direct_conv.cu (fwd and input gradient), several tiles per row
+DIRECT_CASES = [
+    (2, 4, 24, 1500, 3, 1, 2, 2, 1, 4),       # PQMF-disc L0 on all four bands
+    (2, 4, 24, 1111, 3, 1, 3, 3, 1, 4),
+    (2, 1, 16, 2500, 15, 1, 1, 7, 7, 1),      # MelGAN L0, 3 forward tiles / 5 gradient tiles
+    (3, 1, 1, 2100, 101, 1, 1, 50, 0, 1),     # A-weighting FIR
+    (2, 3, 12, 1100, 5, 2, 1, 2, 2, 3),       # strided: direct forward, GEMM input gradient
+]
+
+
+@pytest.mark.parametrize("case", CASES + DIRECT_CASES, ids=[str(c) for c in CASES + DIRECT_CASES])
 def test_conv_family_matches_torch(case):
     from vibravox_b200 import ops
     B, Cin, Cout, Tin, K, s, d, pad, refl, groups = case

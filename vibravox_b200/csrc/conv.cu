@@ -54,6 +54,12 @@ static int launch_cfg(const Plan& pl, const GemmP& P, cudaStream_t st) {
   return launched("gemm_conv_kernel");
 }
 
+// direct_conv.cu: one input channel per group
+bool direct_fwd_ok(const GemmP& P);
+bool direct_dgrad_ok(const GemmP& P);
+int direct_fwd(const GemmP& P, cudaStream_t st);
+int direct_dgrad(const GemmP& P, cudaStream_t st);
+
 static int check_desc(const vbx_conv_desc* d) {
   int code = 0;
   const char* msg = check_desc_msg(d, &code);
@@ -70,6 +76,7 @@ extern "C" int vbx_conv1d_fwd(const vbx_conv_desc* d, const float* x, const floa
   VBX_REQUIRE(x && w && y, VBX_BAD_POINTER, "conv1d_fwd: null tensor");
   GemmP P; fill(P, d); fill_epi(P, e);
   P.W = w; P.X = x; P.Y = y;
+  if (direct_fwd_ok(P)) return direct_fwd(P, (cudaStream_t)stream);
   Plan pl = plan_conv(FWD, P);
   if (pl.bk) return launch_cfg<FWD, true>(pl, P, (cudaStream_t)stream);
   return launch_cfg<FWD, false>(pl, P, (cudaStream_t)stream);
@@ -81,6 +88,7 @@ extern "C" int vbx_conv1d_dgrad(const vbx_conv_desc* d, const float* dy, const f
   VBX_REQUIRE(dy && wt && dx, VBX_BAD_POINTER, "conv1d_dgrad: null tensor");
   GemmP P; fill(P, d); fill_epi(P, e);
   P.W = wt; P.X = dy; P.Y = dx;
+  if (direct_dgrad_ok(P)) return direct_dgrad(P, (cudaStream_t)stream);
   Plan pl = plan_conv(DGRAD, P);
   return launch_cfg<DGRAD, false>(pl, P, (cudaStream_t)stream);
 }

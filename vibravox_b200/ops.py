@@ -439,6 +439,8 @@ def use_tc(g: ConvGeom, kind: str) -> bool:
     if not TC_ENABLED or g.stride > 8:
         return False
     cin_g, cout_g = g.Cin // g.groups, g.Cout // g.groups
+    if kind == "fwd" and cin_g == 1 and cout_g <= 16 and g.K <= 128 and g.stride <= 2:
+        return False                                  # one input channel per group: direct kernel (direct_conv.cu)
     if kind == "fwd":
         return cout_g >= 8 or cin_g * g.K >= 512      # incl. the 1-channel certainty convs (K*Cin = 2-3k)
     if kind == "dgrad":
