@@ -52,6 +52,13 @@ struct TcP {
   int merged;
   int mg_s, mg_Tx, mg_Cin, mg_Cing;           // stride, dx length, dx channels, dx channels per group
   int mg_r[8];                                // first position u of each phase
+  // "slab" form (tc_slab.cuh): no im2col replication; chosen by fill_tc from the geometry alone
+  int slab;
+  int sl_R;         // virtual output rows per batch item (Tout real ones + the tail the taps overhang)
+  int sl_ncg;       // 16-channel groups of the reduction
+  int sl_tpb;       // taps per weight stage
+  int sl_nbst;      // weight stages per channel group = ceil(K / sl_tpb)
+  int sl_SA, sl_SB; // ring depths: slab stages / weight stages
 };
 
 // one reduction segment of a tile: FWD has one; DGRAD has one per mirror image it touches
@@ -530,10 +537,44 @@ __global__ void tc_pack_merged_kernel(const float* __restrict__ w, unsigned char
   }
 }
 
+#include "tc_slab.cuh"
+
 static bool use_merged(const GemmP& G) {
   static const bool off = getenv("VBX_TC_MERGED") && atoi(getenv("VBX_TC_MERGED")) == 0;
   // (with >= 256 channels per group every phase already fills a 256-wide tile: nothing to merge)
   return !off && G.stride > 1 && G.stride <= 8 && G.dil == 1 && G.refl == 0 && G.Cin_g < 256;
+}
+
+// Slab form: forward-style problems (incl. merged-phase input gradients) with >= 2 taps whose reduction has enough
+// channels for 16-wide groups, when everything a producer thread indexes fits 32 bits and the rings fit shared memory.
+static size_t slab_smem_bytes(const TcP& P) {
+  return (size_t)P.sl_SA * slab_a_stage(P.g) + (size_t)P.sl_SB * slab_b_stage(P.NT, P.sl_tpb) +
+         (2 * P.sl_SA + 2 * P.sl_SB + 1) * sizeof(uint64_t) + 16 + (size_t)P.g.K * sizeof(int) + 16;
+}
+static void plan_slab(TcP& P, const vbx_conv_desc* d) {
+  static const int min_cin = getenv("VBX_TC_SLAB_MIN_CIN") ? atoi(getenv("VBX_TC_SLAB_MIN_CIN")) : 8;
+  static const int min_k = getenv("VBX_TC_SLAB_MIN_K") ? atoi(getenv("VBX_TC_SLAB_MIN_K")) : 2;
+  static const bool off = getenv("VBX_TC_SLAB") && atoi(getenv("VBX_TC_SLAB")) == 0;
+  const GemmP& G = P.g;
+  if (off || P.nsplit != 2 || G.K < min_k || G.K > 128 || G.Cin_g < min_cin || G.stride > 8) return;
+  if (slab_npos(G) > kSlabMaxU * kProducers) return;
+  const int R = G.Tout - 1 + ((G.K - 1) * G.dil + 1 + G.stride - 1) / G.stride;
+  if ((long long)d->B * R * G.stride + 2048 >= (1ll << 31) || (long long)d->B * G.Cin * G.Tin >= (1ll << 31)) return;
+  P.sl_R = R;
+  P.sl_ncg = (G.Cin_g + 15) / 16;
+  int tpb = 16384 / (P.NT * 64);
+  if (tpb < 1) tpb = 1;
+  if (tpb > G.K) tpb = G.K;
+  P.sl_tpb = tpb;
+  P.sl_nbst = (G.K + tpb - 1) / tpb;
+  P.sl_SA = P.sl_ncg >= 2 ? 2 : 1;
+  const int total_b = P.sl_ncg * P.sl_nbst;
+  P.sl_SB = total_b < 4 ? total_b : 4;
+  if (slab_smem_bytes(P) > 200 * 1024) {
+    P.sl_SB = total_b < 2 ? total_b : 2;
+    if (slab_smem_bytes(P) > 200 * 1024) return;
+  }
+  P.slab = 1;
 }
 
 static int fill_tc(TcP& P, const vbx_conv_desc* d, int mode, int nsplit) {
@@ -574,6 +615,8 @@ static int fill_tc(TcP& P, const vbx_conv_desc* d, int mode, int nsplit) {
   }
   P.tmem_cols = pow2_cols(P.NT);
   P.stages = pick_stages_for(stage_bytes(P.NT, P.nsplit), P.nchunks);
+  P.slab = 0;
+  if (mode == FWD) plan_slab(P, d);
   return 0;
 }
 
@@ -602,6 +645,20 @@ static int launch_tc(const TcP& P, cudaStream_t st) {
   else
     tc_conv_kernel<MODE, 3><<<grid, kThreads, smem_bytes(P), st>>>(P);
   return launched("tc_conv_kernel");
+}
+
+static int launch_slab(const TcP& P, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t ce = cudaFuncSetAttribute(tc_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+    if (ce != cudaSuccess) return fail((int)ce, "tc_slab: cannot raise the dynamic shared memory limit");
+    attr_set = true;
+  }
+  const long long rows = (long long)P.g.B * P.sl_R;
+  dim3 grid((unsigned)((rows + kRows - 1) / kRows), (unsigned)(P.ntiles_n * P.g.groups), 1);
+  if (grid.y > 65535) return fail(VBX_UNSUPPORTED, "tc_slab: grid too large");
+  tc_slab_kernel<<<grid, kThreads, slab_smem_bytes(P), st>>>(P);
+  return launched("tc_slab_kernel");
 }
 
 template <int MODE>
@@ -888,6 +945,8 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_wgrad_kernel(const TcW P) {
 }
 
 static int64_t pack_bytes(const TcP& P) {
+  if (P.slab)
+    return (int64_t)P.g.groups * P.ntiles_n * P.sl_ncg * P.sl_nbst * slab_b_stage(P.NT, P.sl_tpb);
   return (int64_t)P.g.groups * P.ntiles_n * P.nphase * P.nchunks * P.nsplit * plane_b(P.NT);
 }
 
@@ -905,12 +964,22 @@ extern "C" int vbx_tc_pack(const vbx_conv_desc* d, int32_t mode, int32_t nsplit,
   if (int r = fill_tc(P, d, mode, nsplit)) return r;
   VBX_REQUIRE(w && packed, VBX_BAD_POINTER, "tc_pack: null tensor");
   VBX_REQUIRE(((uintptr_t)packed & 15) == 0, VBX_BAD_POINTER, "tc_pack: packed buffer must be 16-byte aligned");
+  MergedDev D = {};
   if (P.merged) {
     GemmP o; fill(o, d);
     const MergedPlan M = merged_plan(o);
-    MergedDev D;
     for (int i = 0; i < 8; ++i) { D.c[i] = M.c[i]; D.k0[i] = M.k0[i]; D.nt[i] = i < o.stride ? M.nt[i] : 0; }
     D.cmax = M.cmax; D.J = M.J; D.s = o.stride; D.Cin_g = o.Cin_g; D.Cout_g = o.Cout_g; D.K = o.K;
+  }
+  if (P.slab) {
+    const long long units = (long long)P.g.groups * P.ntiles_n * P.sl_ncg * P.sl_nbst * P.sl_tpb * 2 * P.NT;
+    int blocks = (int)((units + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (P.merged) tc_pack_slab_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (unsigned char*)packed, P, D);
+    else tc_pack_slab_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (unsigned char*)packed, P, D);
+    return launched("tc_pack_slab_kernel");
+  }
+  if (P.merged) {
     long long units = (long long)P.g.groups * P.ntiles_n * P.nchunks * 4 * P.NT;
     int blocks = (int)((units + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
@@ -930,6 +999,7 @@ extern "C" int vbx_tc_conv1d_fwd(const vbx_conv_desc* d, const float* x, const v
   fill_epi(P.g, e);
   P.g.X = x; P.g.Y = y;
   P.packed = (const unsigned char*)packed;
+  if (P.slab) return launch_slab(P, (cudaStream_t)stream);
   return launch_tc<FWD>(P, (cudaStream_t)stream);
 }
 
@@ -942,6 +1012,7 @@ extern "C" int vbx_tc_conv1d_dgrad(const vbx_conv_desc* d, const float* dy, cons
   fill_epi(P.g, e);
   P.g.X = dy; P.g.Y = dx;
   P.packed = (const unsigned char*)packed;
+  if (P.slab) return launch_slab(P, (cudaStream_t)stream);
   if (P.merged) return launch_tc<FWD>(P, (cudaStream_t)stream);
   return launch_tc<DGRAD>(P, (cudaStream_t)stream);
 }
