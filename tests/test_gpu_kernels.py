@@ -286,6 +286,10 @@ TC_CASES = [
     (2, 24, 48, 131, 7, 2, 2, 3, 0, 4), (2, 24, 48, 131, 7, 2, 3, 3, 0, 4), (2, 16, 32, 257, 16, 8, 1, 7, 7, 1),
     (2, 128, 256, 64, 16, 8, 1, 4, 0, 1), (2, 2, 32, 100, 3, 1, 1, 1, 1, 1), (2, 256, 64, 62, 7, 1, 1, 3, 3, 1),
     (5, 40, 24, 97, 5, 3, 2, 4, 2, 2),
+    # slab-form kernel: several row tiles straddling batch items, partial 16-channel groups, strided + dilated
+    # zero-halo input gradients (merged phases on a unit or dilated tap lattice), stride-1 flipped-tap gradients
+    (3, 48, 96, 700, 7, 2, 3, 3, 0, 4), (3, 48, 96, 701, 7, 2, 2, 3, 0, 4), (2, 64, 64, 333, 5, 1, 3, 6, 0, 2),
+    (2, 40, 80, 500, 5, 3, 2, 4, 0, 2), (3, 512, 512, 187, 41, 4, 1, 20, 0, 2), (2, 36, 20, 450, 3, 1, 9, 9, 9, 1),
 ]
 
 

@@ -479,7 +479,8 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, unsigned char* __res
 // per-phase tap bookkeeping of the merged-phase dgrad (host side, stride <= 8)
 struct MergedPlan {
   int c[8], k0[8], nt[8], r[8];
-  int cmax, J;
+  int cmax, J, tstep;
+  int dilm, Kp;     // tap lattice of the re-labelled conv: Kp taps spaced dilm (J = (Kp-1)*dilm + 1 unit slots)
 };
 static MergedPlan merged_plan(const GemmP& G) {
   MergedPlan M;
@@ -491,12 +492,29 @@ static MergedPlan merged_plan(const GemmP& G) {
     M.k0[ph] = im.k0; M.nt[ph] = im.ntaps;
     if (im.ntaps > 0 && M.c[ph] > M.cmax) M.cmax = M.c[ph];
   }
+  // taps of a phase read dy at v + c(ph) - jj*tstep (tstep = dil / gcd(dil, stride)); the common tap grid has
+  // unit spacing and spans all of them: m' = (J-1) - (cmax - c(ph)) - jj*tstep
+  M.tstep = dgrad_taps(G, 0).tstep;
   M.J = 1;
+  for (int ph = 0; ph < G.stride; ++ph) {
+    const int span = (M.nt[ph] - 1) * M.tstep + 1 + M.cmax - M.c[ph];
+    if (M.nt[ph] > 0 && span > M.J) M.J = span;
+  }
+  // if every phase's taps fall on one lattice of spacing tstep (always so for stride 1), keep the dilation
+  M.dilm = M.tstep;
   for (int ph = 0; ph < G.stride; ++ph)
-    if (M.nt[ph] > 0 && M.nt[ph] + M.cmax - M.c[ph] > M.J) M.J = M.nt[ph] + M.cmax - M.c[ph];
+    if (M.nt[ph] > 0 && (M.cmax - M.c[ph]) % M.tstep != 0) M.dilm = 1;
+  M.Kp = (M.J - 1) / M.dilm + 1;
   return M;
 }
-struct MergedDev { int c[8], k0[8], nt[8], cmax, J, s, Cin_g, Cout_g, K; };
+struct MergedDev { int c[8], k0[8], nt[8], cmax, J, s, Cin_g, Cout_g, K, tstep, kstep, dilm; };
+// index jj of the phase's tap that sits at tap `mp` of the re-labelled conv (unit slot mp*dilm), or -1
+__device__ __forceinline__ int merged_tap(const MergedDev& M, int ph, int mp) {
+  const int num = (M.J - 1 - mp * M.dilm) - (M.cmax - M.c[ph]);
+  if (num < 0 || num % M.tstep != 0) return -1;
+  const int jj = num / M.tstep;
+  return jj < M.nt[ph] ? jj : -1;
+}
 
 // Wm[(ph,ci), (m', co)] = W[co][ci][k0(ph) + jj*s],  jj = (J-1-m') - (cmax - c(ph)),  zero outside the phase's taps
 __global__ void tc_pack_merged_kernel(const float* __restrict__ w, unsigned char* __restrict__ out, const TcP P,
@@ -521,10 +539,10 @@ __global__ void tc_pack_merged_kernel(const float* __restrict__ w, unsigned char
       float v = 0.f;
       const int kk = kk0 + j;
       const int mp = kk / P.cpad, cr = kk % P.cpad;
-      if (col < Ccol && cr < M.Cout_g && mp < M.J) {
-        const int jj = (M.J - 1 - mp) - (M.cmax - M.c[ph]);
-        if (jj >= 0 && jj < M.nt[ph])
-          v = w[(((long long)g * M.Cout_g + cr) * M.Cin_g + ci) * M.K + M.k0[ph] + jj * M.s];
+      if (col < Ccol && cr < M.Cout_g && mp * M.dilm < M.J) {
+        const int jj = merged_tap(M, ph, mp);
+        if (jj >= 0)
+          v = w[(((long long)g * M.Cout_g + cr) * M.Cin_g + ci) * M.K + M.k0[ph] + jj * M.kstep];
       }
       split_bf16(v, hi[j], lo[j]);
       lo3[j] = __float2bfloat16_rn((v - __bfloat162float(hi[j])) - __bfloat162float(lo[j]));
@@ -539,9 +557,10 @@ __global__ void tc_pack_merged_kernel(const float* __restrict__ w, unsigned char
 
 #include "tc_slab.cuh"
 
+// Merged-phase input gradient on the gather kernel: worth it only where the common tap grid has no holes
+// (dil = 1) and a phase does not already fill a 256-wide tile.  The slab kernel takes the general case.
 static bool use_merged(const GemmP& G) {
   static const bool off = getenv("VBX_TC_MERGED") && atoi(getenv("VBX_TC_MERGED")) == 0;
-  // (with >= 256 channels per group every phase already fills a 256-wide tile: nothing to merge)
   return !off && G.stride > 1 && G.stride <= 8 && G.dil == 1 && G.refl == 0 && G.Cin_g < 256;
 }
 
@@ -585,8 +604,12 @@ static int fill_tc(TcP& P, const vbx_conv_desc* d, int mode, int nsplit) {
   fill(P.g, d);
   P.nsplit = nsplit;
   P.merged = 0;
-  if (mode == DGRAD && use_merged(P.g)) {
-    // re-label the geometry: a stride-1 forward conv dy (Cout ch, Tout long) -> D (s*Cin ch, V long)
+  P.slab = 0;
+  if (mode == DGRAD && P.g.refl == 0 && P.g.stride <= 8) {
+    // Zero-halo input gradient as a stride-1 forward conv over dy (Cout ch, Tout long) -> D (s*Cin ch, V long):
+    // every stride phase of dx becomes a block of columns, the taps sit on a unit-spaced grid of J slots
+    // (for stride 1 this is just the flipped-tap correlation).  Kept if the slab kernel takes it, or - on the
+    // gather kernel - where use_merged() says it pays.
     const GemmP o = P.g;
     const MergedPlan M = merged_plan(o);
     P.merged = 1;
@@ -595,8 +618,16 @@ static int fill_tc(TcP& P, const vbx_conv_desc* d, int mode, int nsplit) {
     P.g.Cin = o.Cout; P.g.Cin_g = o.Cout_g;
     P.g.Cout = o.stride * o.Cin; P.g.Cout_g = o.stride * o.Cin_g;
     P.g.Tin = o.Tout; P.g.Tout = (o.Tin + o.stride - 1) / o.stride;
-    P.g.K = M.J; P.g.stride = 1; P.g.dil = 1; P.g.pad = M.J - 1 - M.cmax; P.g.refl = 0;
-    mode = FWD;
+    P.g.K = M.Kp; P.g.stride = 1; P.g.dil = M.dilm; P.g.pad = M.J - 1 - M.cmax; P.g.refl = 0;
+    P.NT = pick_nt(P.g.Cout_g);
+    P.ntiles_n = (P.g.Cout_g + P.NT - 1) / P.NT;
+    if (M.J >= 1 && P.g.pad >= 0) plan_slab(P, d);
+    if (P.slab || use_merged(o)) {
+      mode = FWD;
+    } else {
+      P.g = o;
+      P.merged = 0;
+    }
   }
   const int Ccol = mode == FWD ? P.g.Cout_g : P.g.Cin_g;
   P.NT = pick_nt(Ccol);
@@ -615,8 +646,7 @@ static int fill_tc(TcP& P, const vbx_conv_desc* d, int mode, int nsplit) {
   }
   P.tmem_cols = pow2_cols(P.NT);
   P.stages = pick_stages_for(stage_bytes(P.NT, P.nsplit), P.nchunks);
-  P.slab = 0;
-  if (mode == FWD) plan_slab(P, d);
+  if (mode == FWD && !P.slab) plan_slab(P, d);
   return 0;
 }
 
@@ -970,6 +1000,7 @@ extern "C" int vbx_tc_pack(const vbx_conv_desc* d, int32_t mode, int32_t nsplit,
     const MergedPlan M = merged_plan(o);
     for (int i = 0; i < 8; ++i) { D.c[i] = M.c[i]; D.k0[i] = M.k0[i]; D.nt[i] = i < o.stride ? M.nt[i] : 0; }
     D.cmax = M.cmax; D.J = M.J; D.s = o.stride; D.Cin_g = o.Cin_g; D.Cout_g = o.Cout_g; D.K = o.K;
+    D.tstep = M.tstep; D.kstep = dgrad_taps(o, 0).kstep; D.dilm = M.dilm;
   }
   if (P.slab) {
     const long long units = (long long)P.g.groups * P.ntiles_n * P.sl_ncg * P.sl_nbst * P.sl_tpb * 2 * P.NT;

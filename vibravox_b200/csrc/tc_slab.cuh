@@ -277,9 +277,9 @@ __global__ void tc_pack_slab_kernel(const float* __restrict__ w, unsigned char* 
           v = w[(((long long)g * G.Cout_g + col) * G.Cin_g + c) * G.K + tap];
         } else {
           const int ph = col / M.Cin_g, ci = col % M.Cin_g;
-          const int jj = (M.J - 1 - tap) - (M.cmax - M.c[ph]);
-          if (jj >= 0 && jj < M.nt[ph])
-            v = w[(((long long)g * M.Cout_g + c) * M.Cin_g + ci) * M.K + M.k0[ph] + jj * M.s];
+          const int jj = merged_tap(M, ph, tap);
+          if (jj >= 0)
+            v = w[(((long long)g * M.Cout_g + c) * M.Cin_g + ci) * M.K + M.k0[ph] + jj * M.kstep];
         }
       }
       split_bf16(v, hi[e], lo[e]);
