@@ -621,7 +621,10 @@ static int fill_tc(TcP& P, const vbx_conv_desc* d, int mode, int nsplit) {
     P.g.K = M.Kp; P.g.stride = 1; P.g.dil = M.dilm; P.g.pad = M.J - 1 - M.cmax; P.g.refl = 0;
     P.NT = pick_nt(P.g.Cout_g);
     P.ntiles_n = (P.g.Cout_g + P.NT - 1) / P.NT;
-    if (M.J >= 1 && P.g.pad >= 0) plan_slab(P, d);
+    // (a unit lattice under dilated taps multiplies the MMA work by Kp*stride / K: only worth it while the layer
+    //  is far from MMA-bound, i.e. for modest reductions)
+    const bool stuffed = (long long)M.Kp * o.stride * 2 > 3ll * o.K && o.Cout_g >= 128;
+    if (M.J >= 1 && P.g.pad >= 0 && !stuffed) plan_slab(P, d);
     if (P.slab || use_merged(o)) {
       mode = FWD;
     } else {
@@ -1048,12 +1051,21 @@ extern "C" int vbx_tc_conv1d_dgrad(const vbx_conv_desc* d, const float* dy, cons
   return launch_tc<DGRAD>(P, (cudaStream_t)stream);
 }
 
+#include "tc_wslab.cuh"
+
 extern "C" int vbx_tc_conv1d_wgrad(const vbx_conv_desc* d, const float* x, const float* dy, float* dw,
                                    void* stream) {
   int code = 0;
   const char* msg = check_desc_msg(d, &code);
   if (msg) return fail(code, msg);
   VBX_REQUIRE(x && dy && dw, VBX_BAD_POINTER, "tc_conv1d_wgrad: null tensor");
+  {
+    TcWS W;
+    if (plan_wslab(W, d)) {
+      W.g.X = x; W.g.DY = dy; W.g.Y = dw;
+      return launch_wslab(W, (cudaStream_t)stream);
+    }
+  }
   TcW P;
   fill(P.g, d);
   P.g.X = x; P.g.DY = dy; P.g.Y = dw;

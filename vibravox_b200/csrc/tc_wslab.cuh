@@ -1,0 +1,297 @@
+// Weight gradient on tensor cores WITHOUT im2col replication ("slab" form), included by tc_conv.cu (global scope,
+// after `using namespace vbx::tc`).
+//
+//   dW[co, ci, k] = sum_{(b,t)} dy[b, co, t] * x[b, ci, map(s*t + k*d - pad)]
+//
+// One MMA family per tap:  D_k[co (M = 128), ci (N = NCI)] += A[co, t] * B_k[ci, t]  with the reduction over time.
+// Both operands are staged MN-major - a 16-byte unit holds 8 consecutive CHANNELS of one time position and
+// consecutive positions are 16 bytes apart - so B_k is the SAME staged x slab for every tap, read through a
+// descriptor whose start address is advanced by the tap offset (k*d = s*j + rho -> phase plane rho, j units).
+// Every x / dy value is loaded, split into bf16 hi/lo and stored once per (co tile, ci tile, tap group) instead of
+// once per tap column.  TG taps accumulate side by side in TMEM (TG * NCI <= 512 columns); time runs over the
+// virtual timeline of tc_slab.cuh (period R rows per batch item; dy is zero on the rows that are not real) and is
+// split over blockIdx.z; partial results are added to dW with fp32 atomics.
+#pragma once
+
+static const int kWsTC = 32;                // time positions per stage (two MMA k-steps)
+
+struct TcWS {
+  GemmP g;
+  int NCI, TG, ntg, ci_tiles, co_tiles, tmem_cols, stages;
+  int R;            // virtual rows per batch item
+  int UB;           // x units per stride phase in a stage
+  int rows_per;     // virtual rows per blockIdx.z (multiple of kWsTC)
+};
+__host__ __device__ inline int ws_UB(const GemmP& G, int TG) { return kWsTC + ((TG - 1) * G.dil) / G.stride + 1; }
+// bytes between consecutive 8-channel groups of a slab: an odd number of 16-byte units, so that the 16 (or NCI/8)
+// units the tensor core fetches for one time position fall in different shared-memory banks
+__host__ __device__ inline int ws_sbo_a() { return kWsTC * 16 + 16; }
+__host__ __device__ inline int ws_sbo_b(const GemmP& G, int UB) { return (G.stride * UB | 1) * 16; }
+__host__ __device__ inline int ws_a_stage() { return 2 * (kRows / 8) * ws_sbo_a(); }                  // hi + lo
+__host__ __device__ inline int ws_b_stage(const GemmP& G, int NCI, int UB) { return 2 * (NCI / 8) * ws_sbo_b(G, UB); }
+// positions of x a tile with `ntap` taps stages per time chunk (its own tap span only)
+__host__ __device__ inline int ws_npos_taps(const GemmP& G, int ntap) {
+  return (kWsTC - 1) * G.stride + (ntap - 1) * G.dil + 1;
+}
+
+// PW producer warps (+ one MMA warp): 16 when the tile owns all 512 TMEM columns (one CTA per SM: the extra warps
+// are the memory-level parallelism), 8 with two CTAs per SM otherwise.
+template <int PW, int MINB>
+__global__ void __launch_bounds__(PW * 32 + 32, MINB) tc_wslab_kernel(const TcWS P) {
+  constexpr int kProd = PW * 32;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const GemmP& G = P.g;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = P.stages, NCI = P.NCI, s = G.stride, UB = P.UB;
+  const int a_stage = ws_a_stage(), b_stage = ws_b_stage(G, NCI, UB), stage_sz = a_stage + b_stage;
+  const int plane_a = a_stage / 2, plane_b = b_stage / 2;
+  const int sbo_a = ws_sbo_a(), sbo_b = ws_sbo_b(G, UB);            // bytes between 8-channel groups
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_sz);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + S;
+  uint64_t* acc_full = bars + 2 * S;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  int* tapoff = reinterpret_cast<int*>(tmem_slot + 2);          // per tap of this group: byte offset into the x slab
+
+  // blockIdx.x = tap group * ci_tiles + ci tile;  blockIdx.y = group * co_tiles + co tile;  blockIdx.z = time slice
+  const int tg = blockIdx.x / P.ci_tiles, cit = blockIdx.x % P.ci_tiles;
+  const int grp = blockIdx.y / P.co_tiles, cot = blockIdx.y % P.co_tiles;
+  const int tap0 = tg * P.TG, ntap = min(P.TG, G.K - tap0);
+  const int co0 = cot * kRows, ci0 = cit * NCI;
+  const int R = P.R, Ppos = R * s;
+  const int total = G.B * R;
+  const int rv_lo = blockIdx.z * P.rows_per, rv_hi = min(rv_lo + P.rows_per, total);
+  if (rv_lo >= rv_hi) return;
+  const int nstage = (rv_hi - rv_lo + kWsTC - 1) / kWsTC;
+
+  if (tid == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(&full[i], kProd); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  const int pos0 = tap0 * G.dil;                                // first x position (relative to s*rv) this tile reads
+  if (tid < ntap) {
+    const int off = tid * G.dil;                                // relative to pos0
+    tapoff[tid] = ((off % s) * UB + off / s) * 16;
+  }
+  if (warp == PW) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < PW) {
+    // ===================== producers =====================
+    // dy: one position x (16 / PW) 8-channel groups per thread.  x: TPP threads share a position and interleave its
+    // 8-channel groups, so all threads carry a similar number of loads.
+    constexpr int NA = 16 / PW;
+    constexpr int TPP = kProd / 128;                            // threads per x position (128 positions per round)
+    constexpr int NU = 8 / TPP;                                 // 8-channel groups per thread and position (NCI <= 64)
+    constexpr int MAXR = 3;                                     // position rounds (host: positions <= 384)
+    const int npos = ws_npos_taps(G, ntap);
+    const int ncg = NCI / 8;
+    const int tA = tid & 31, cogA = (tid >> 5) * NA;
+    const float* dyg = G.DY + (long long)(grp * G.Cout_g + co0) * G.Tout;
+    const float* xg = G.X + (long long)(grp * G.Cin_g + ci0) * G.Tin;
+    const int rows_a = min(kRows, G.Cout_g - co0), cols_b = min(NCI, G.Cin_g - ci0);
+    auto put16 = [](unsigned char* hi_p, unsigned char* lo_p, const float (&v)[8]) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+        const float2 hf = __bfloat1622float2(h2);
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+        hi[e] = *reinterpret_cast<const uint32_t*>(&h2);
+        lo[e] = *reinterpret_cast<const uint32_t*>(&l2);
+      }
+      *reinterpret_cast<uint4*>(hi_p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(lo_p) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    };
+    // 8 channels (rows `stride` apart) of one position; `nvalid` of them exist, the rest read as zero
+    auto load8 = [](const float* p, long long stride, int nvalid, float (&v)[8]) {
+      if (nvalid >= 8) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = __ldg(p + e * stride);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = e < nvalid ? __ldg(p + e * stride) : 0.f;
+      }
+    };
+    // running (batch item, offset) of this thread's dy row and x positions: advanced per stage, never divided again
+    int ba = (rv_lo + tA) / R, ta = (rv_lo + tA) % R;
+    int bx[MAXR], px[MAXR], sx[MAXR];
+#pragma unroll
+    for (int r = 0; r < MAXR; ++r) {
+      const int i = tid / TPP + 128 * r;
+      const unsigned q = (unsigned)rv_lo * (unsigned)s + (unsigned)(pos0 + i);
+      bx[r] = (int)(q / (unsigned)Ppos); px[r] = (int)(q % (unsigned)Ppos);
+      sx[r] = i < npos ? ((i % s) * UB + i / s) * 16 : -1;
+    }
+    const int cg0 = tid % TPP;
+    int st = 0;
+    uint32_t par = 0;
+    for (int c = 0; c < nstage; ++c) {
+      // ---- dy ----
+      const bool va = rv_lo + c * kWsTC + tA < rv_hi && ba < G.B && ta < G.Tout;
+      float a[NA][8];
+      {
+        const float* pa = dyg + ((long long)ba * G.Cout + (long long)cogA * 8) * G.Tout + ta;
+#pragma unroll
+        for (int h = 0; h < NA; ++h)
+          load8(pa + (long long)h * 8 * G.Tout, G.Tout, va ? rows_a - (cogA + h) * 8 : 0, a[h]);
+      }
+      mbar_wait(&empty[st], par ^ 1u);
+      unsigned char* sa = smem + (size_t)st * stage_sz;
+      unsigned char* sb = sa + a_stage;
+#pragma unroll
+      for (int h = 0; h < NA; ++h) {
+        unsigned char* d0 = sa + (cogA + h) * sbo_a + tA * 16;
+        put16(d0, d0 + plane_a, a[h]);
+      }
+      // ---- x ----
+#pragma unroll
+      for (int r = 0; r < MAXR; ++r) {
+        if (sx[r] >= 0) {
+          const int tau = map_pos(px[r] - G.pad, G.Tin, G.refl);
+          const bool vb = bx[r] < G.B && tau >= 0;
+          const float* pb = xg + ((long long)bx[r] * G.Cin * G.Tin + (vb ? tau : 0));
+          float v[NU][8];
+#pragma unroll
+          for (int u = 0; u < NU; ++u) {
+            const int cg = cg0 + u * TPP;
+            load8(pb + (long long)cg * 8 * G.Tin, G.Tin, (vb && cg < ncg) ? cols_b - cg * 8 : 0, v[u]);
+          }
+          unsigned char* d0 = sb + sx[r];
+#pragma unroll
+          for (int u = 0; u < NU; ++u) {
+            const int cg = cg0 + u * TPP;
+            if (cg < ncg) put16(d0 + cg * sbo_b, d0 + cg * sbo_b + plane_b, v[u]);
+          }
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(&full[st]);
+      if (++st == S) { st = 0; par ^= 1u; }
+      ta += kWsTC;
+      while (ta >= R) { ta -= R; ++ba; }
+#pragma unroll
+      for (int r = 0; r < MAXR; ++r) {
+        px[r] += kWsTC * s;
+        while (px[r] >= Ppos) { px[r] -= Ppos; ++bx[r]; }
+      }
+    }
+    // ===================== epilogue: TMEM -> fp32 reductions into dW[co][ci][k] =====================
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int q = warp & 3, part = warp >> 2;                     // TMEM lane quarter; PW / 4 warps share it
+    const int co = co0 + q * 32 + lane;
+    const bool ev = co < G.Cout_g;
+    float* dst = G.Y + ((long long)(grp * G.Cout_g + co) * G.Cin_g + ci0) * G.K + tap0;
+    const int nblk = ntap * NCI / 16;
+    for (int blk = part; blk < nblk; blk += PW / 4) {
+      float acc[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * 16), acc);
+      const int tl = (blk * 16) / NCI, n0 = (blk * 16) % NCI;
+      if (!ev) continue;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (n0 + j < cols_b) atomicAdd(dst + (long long)(n0 + j) * G.K + tl, acc[j]);
+    }
+  } else {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(NCI, /*a_mn=*/true, /*b_mn=*/true);
+      int st = 0;
+      uint32_t par = 0;
+      for (int c = 0; c < nstage; ++c) {
+        mbar_wait(&full[st], par);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + (size_t)st * stage_sz), a_lo = a_hi + plane_a;
+        const uint32_t b_base = a_hi + a_stage;
+        for (int tl = 0; tl < ntap; ++tl) {
+          const uint32_t b_hi = b_base + (uint32_t)tapoff[tl], b_lo = b_hi + plane_b;
+          const uint32_t d = tmem_base + (uint32_t)(tl * NCI);
+#pragma unroll
+          for (int ks = 0; ks < kWsTC / 16; ++ks) {
+            const uint64_t da_hi = make_desc(a_hi + ks * 256, 128, sbo_a), da_lo = make_desc(a_lo + ks * 256, 128, sbo_a);
+            const uint64_t db_hi = make_desc(b_hi + ks * 256, 128, sbo_b), db_lo = make_desc(b_lo + ks * 256, 128, sbo_b);
+            mma_bf16_ss(d, da_hi, db_hi, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+            mma_bf16_ss(d, da_hi, db_lo, idesc, 1);
+            mma_bf16_ss(d, da_lo, db_hi, idesc, 1);
+          }
+        }
+        mma_commit(&empty[st]);
+        if (++st == S) { st = 0; par ^= 1u; }
+      }
+      mma_commit(acc_full);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == PW) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+}
+
+static size_t ws_smem_bytes(const TcWS& P) {
+  return (size_t)P.stages * (ws_a_stage() + ws_b_stage(P.g, P.NCI, P.UB)) + (2 * P.stages + 1) * sizeof(uint64_t) + 16 +
+         (size_t)P.TG * sizeof(int) + 16;
+}
+
+// Returns false when the geometry is left to the gather kernel.
+static bool plan_wslab(TcWS& P, const vbx_conv_desc* d) {
+  static const bool off = getenv("VBX_TC_WSLAB") && atoi(getenv("VBX_TC_WSLAB")) == 0;
+  static const int min_k = getenv("VBX_TC_WSLAB_MIN_K") ? atoi(getenv("VBX_TC_WSLAB_MIN_K")) : 2;
+  static const int min_cin = getenv("VBX_TC_WSLAB_MIN_CIN") ? atoi(getenv("VBX_TC_WSLAB_MIN_CIN")) : 8;
+  fill(P.g, d);
+  const GemmP& G = P.g;
+  if (off || G.K < min_k || G.K > 128 || G.Cin_g < min_cin || G.stride > 8) return false;
+  const int R = G.Tout - 1 + ((G.K - 1) * G.dil + 1 + G.stride - 1) / G.stride;
+  if ((long long)G.B * R * G.stride + 4096 >= (1ll << 31)) return false;
+  P.R = R;
+  P.NCI = G.Cin_g >= 64 ? 64 : (G.Cin_g + 15) / 16 * 16;
+  P.ci_tiles = (G.Cin_g + P.NCI - 1) / P.NCI;
+  P.co_tiles = (G.Cout_g + kRows - 1) / kRows;
+  const int cols = G.K * P.NCI <= 256 ? 256 : 512;
+  int tgmax = cols / P.NCI;
+  P.ntg = (G.K + tgmax - 1) / tgmax;
+  P.TG = (G.K + P.ntg - 1) / P.ntg;
+  P.tmem_cols = pow2_cols(P.TG * P.NCI);
+  P.UB = ws_UB(G, P.TG);
+  if (ws_npos_taps(G, P.TG) > 3 * 128) return false;
+  const long long total = (long long)G.B * R;
+  const long long tiles = (long long)P.ntg * P.ci_tiles * P.co_tiles * G.groups;
+  long long want = (148 * 3 + tiles - 1) / tiles;
+  const long long max_split = (total + kWsTC * 8 - 1) / (kWsTC * 8);
+  if (want > max_split) want = max_split;
+  if (want < 1) want = 1;
+  long long per = (total + want - 1) / want;
+  per = (per + kWsTC - 1) / kWsTC * kWsTC;
+  P.rows_per = (int)per;
+  const int stage = ws_a_stage() + ws_b_stage(G, P.NCI, P.UB);
+  int stg = (P.tmem_cols <= 256 ? 100 * 1024 : 200 * 1024) / stage;
+  if (stg > 4) stg = 4;
+  if (stg < 2) {
+    stg = 200 * 1024 / stage;
+    if (stg < 2) return false;
+    if (stg > 2) stg = 2;
+  }
+  P.stages = stg;
+  return ws_smem_bytes(P) <= (size_t)kSmemMax;
+}
+
+static int launch_wslab(const TcWS& P, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t ce = cudaFuncSetAttribute(tc_wslab_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+    if (ce == cudaSuccess)
+      ce = cudaFuncSetAttribute(tc_wslab_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+    if (ce != cudaSuccess) return fail((int)ce, "tc_wslab: cannot raise the dynamic shared memory limit");
+    attr_set = true;
+  }
+  const long long total = (long long)P.g.B * P.R;
+  dim3 grid((unsigned)(P.ntg * P.ci_tiles), (unsigned)(P.co_tiles * P.g.groups),
+            (unsigned)((total + P.rows_per - 1) / P.rows_per));
+  if (grid.y > 65535 || grid.z > 65535) return fail(VBX_UNSUPPORTED, "tc_wslab: grid too large");
+  if (P.tmem_cols > 256) tc_wslab_kernel<16, 1><<<grid, 16 * 32 + 32, ws_smem_bytes(P), st>>>(P);
+  else tc_wslab_kernel<8, 2><<<grid, 8 * 32 + 32, ws_smem_bytes(P), st>>>(P);
+  return launched("tc_wslab_kernel");
+}
