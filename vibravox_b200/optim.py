@@ -94,4 +94,8 @@ class FlatAdam(torch.optim.Optimizer):
         ops.adam_tick(self.step_count)
         ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count, g["lr"],
                       g["betas"][0], g["betas"][1], g["eps"], self.grad_scale)
+        # the kernel writes the parameters behind autograd's back (no version bump): drop what was derived from
+        # the old values (packed tensor-core tiles of convs that use their weight directly)
+        for p in self.params:
+            p.__dict__.pop("_vbx_packs", None)
         return None
