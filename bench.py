@@ -110,10 +110,16 @@ def layer_microbench(device, B, L):
     flops = 2.0 * B * To * 1024 * 256 * 41
     byt = 4.0 * (B * 1024 * T3 + B * 1024 * To + w.numel())
     t = timeit(lambda: ops.conv_fwd(x, w, g, bias=bias, slope=0.2), reps=5, warm=2)
-    kname = "tc_conv_kernel<FWD> (tcgen05, bf16x3)" if ops.use_tc(g, "fwd") else "gemm_conv_kernel<FWD> (fp32 FMA)"
+    kname = "tc_slab_kernel fwd (tcgen05, bf16x3)" if ops.use_tc(g, "fwd") else "gemm_conv_kernel<FWD> (fp32 FMA)"
+    # DRAM bytes of this launch from the committed `ncu --set full` capture (profiles/README.md), bs = 32 only
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath) and B == 32 and ops.use_tc(g, "fwd"):
+        traffic = json.load(open(tpath)).get("melgan4_fwd_dram_bytes")
     out.append({"kernel": kname + " melgan.4 (1024->1024,k41,s4,g4)", "bound": "tensor",
                 "achieved": flops / t / 1e12, "peak": tens, "unit": "TFLOP/s", "frac": flops / t / 1e12 / tens,
-                "ms": t * 1e3, "algorithmic_bytes": byt, "peak_source": src + " bf16 sustained", "traffic": None})
+                "ms": t * 1e3, "algorithmic_bytes": byt, "peak_source": src + " bf16 sustained", "traffic": traffic,
+                "note": "3 bf16 MMAs per fp32 product: the useful-flop ceiling is peak / 3"})
     # (b) generator residual unit convs at C=32, T=11968
     Tb = (L + 32) // 4
     for C, T in ((32, Tb), (64, Tb // 2), (128, Tb // 8)):

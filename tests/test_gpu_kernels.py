@@ -372,3 +372,26 @@ def test_tensor_core_three_way_split_is_fp32_grade(case):
     (gx,) = torch.autograd.grad(want, x64, dy)
     dx = ops.tc_conv1d_dgrad(dy.float().to(DEV), ops.tc_pack(wc, geom, 1, 3), geom, Tin, nsplit=3)
     assert float((dx.cpu().double() - gx).norm() / gx.norm()) < 3e-7 + 4e-8 * n_mma(Cout // groups, K)
+
+
+def test_flat_adam_update_invalidates_packed_weight_tiles():
+    """A conv that uses its parameter directly caches bf16 tiles on the tensor; FlatAdam rewrites the parameter
+    through a raw pointer, so the cache has to be dropped by the optimizer (regression: stale tiles after step 1)."""
+    from vibravox_b200 import ops
+    from vibravox_b200.optim import FlatAdam
+    torch.manual_seed(3)
+    conv = torch.nn.Conv1d(16, 32, 3).to(DEV)
+    opt = FlatAdam(conv.parameters(), lr=0.05, betas=(0.5, 0.9))
+    opt.materialize()
+    geom = ops.ConvGeom(16, 32, 3, 1, 1, 1, 0, 1)
+    x = torch.randn(2, 16, 400, device=DEV)
+    assert ops.use_tc(geom, "fwd")
+    y0 = ops.conv_fwd(x, conv.weight, geom)
+    assert "_vbx_packs" in conv.weight.__dict__
+    for p in conv.parameters():
+        p._vbx_grad.fill_(1.0)
+    opt.step()
+    y1 = ops.conv_fwd(x, conv.weight, geom)
+    want = F.conv1d(x.double(), conv.weight.detach().double(), None, 1, 1)
+    assert (y1.double() - want).abs().max() < 1e-4 * float(want.abs().max())
+    assert (y1 - y0).abs().max() > 1e-2
