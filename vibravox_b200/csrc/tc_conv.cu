@@ -717,6 +717,22 @@ using namespace vbx::tc;
 // The (b,t) range is split over blockIdx.z; partial tiles are added with fp32 reductions.
 static const int kLboW = kRows * 16 + 16;     // A: bytes between 8-t units (+16: conflict-free 2-byte stores)
 
+// Reduction split of a weight-gradient grid: `tiles` independent output tiles, `slots` CTAs resident on the GPU at
+// once.  Pick the split whose total CTA count fills whole waves best (an extra 0.3 wave costs a full one).
+static long long pick_split(long long tiles, long long slots, long long max_split) {
+  long long best = 1;
+  double best_eff = 0.0;
+  for (int w = 1; w <= 6; ++w) {
+    long long sp = w * slots / tiles;
+    if (sp < 1) sp = 1;
+    if (sp > max_split) sp = max_split;
+    const double waves = (double)(tiles * sp) / (double)slots;
+    const double eff = waves / (double)(long long)(waves + 0.999999);
+    if (eff > best_eff + 0.02) { best_eff = eff; best = sp; }
+  }
+  return best;
+}
+
 struct TcW {
   GemmP g;
   int NT, ntiles_n, mtiles, tmem_cols, stages;
@@ -1076,11 +1092,10 @@ extern "C" int vbx_tc_conv1d_wgrad(const vbx_conv_desc* d, const float* x, const
   P.tmem_cols = pow2_cols(P.NT);
   const long long total = (long long)P.g.B * P.g.Tout;
   const long long tiles = (long long)P.ntiles_n * P.mtiles * P.g.groups;
-  long long want = (148 * 4 + tiles - 1) / tiles;
   long long max_split = (total + kKC * 8 - 1) / (kKC * 8);            // >= 8 chunks per slice
-  if (want > max_split) want = max_split;
-  if (want < 1) want = 1;
-  if (want > 65535) want = 65535;
+  if (max_split > 65535) max_split = 65535;
+  if (max_split < 1) max_split = 1;
+  long long want = pick_split(tiles, 148 * (P.tmem_cols > 128 ? 2 : 3), max_split);
   long long per = (total + want - 1) / want;
   per = (per + kKC - 1) / kKC * kKC;
   P.red_per = (int)per;

@@ -259,10 +259,13 @@ static bool plan_wslab(TcWS& P, const vbx_conv_desc* d) {
   if (ws_npos_taps(G, P.TG) > 3 * 128) return false;
   const long long total = (long long)G.B * R;
   const long long tiles = (long long)P.ntg * P.ci_tiles * P.co_tiles * G.groups;
-  long long want = (148 * 3 + tiles - 1) / tiles;
-  const long long max_split = (total + kWsTC * 8 - 1) / (kWsTC * 8);
+  long long max_split = (total + kWsTC * 8 - 1) / (kWsTC * 8);
+  if (max_split > 65535) max_split = 65535;
+  if (max_split < 1) max_split = 1;
+  // (measured: with few tiles, ~3 short slices per SM beat one long one; with many, whole waves win)
+  long long want = tiles >= 48 ? pick_split(tiles, 148 * (P.tmem_cols > 256 ? 1 : 2), max_split)
+                               : (148 * 3 + tiles - 1) / tiles;
   if (want > max_split) want = max_split;
-  if (want < 1) want = 1;
   long long per = (total + want - 1) / want;
   per = (per + kWsTC - 1) / kWsTC * kWsTC;
   P.rows_per = (int)per;
