@@ -163,6 +163,20 @@ def test_elementwise_and_losses():
     want = dy.double() * torch.where(ref > 0, 1.0, 0.2).double()
     assert (dxc.cpu().double() - want).abs().max() < 1e-6
     assert (db.cpu().double() - want.sum((0, 2))).abs().max() < 1e-4
+    # vector (16-byte) and scalar paths, sign from a byte mask or from `ref`, several 1024-position chunks
+    for (Bq, Cq, Tq) in ((3, 6, 2500), (2, 5, 2048), (2, 3, 1027), (1, 4, 8)):
+        dy, ref = torch.randn(Bq, Cq, Tq), torch.randn(Bq, Cq, Tq)
+        mask = (ref > 0).to(torch.uint8)
+        want = dy.double() * torch.where(ref > 0, 1.0, 0.2).double()
+        for kw in (dict(ref=ref.to(DEV)), dict(ref=None, mask=mask.to(DEV))):
+            db = torch.zeros(Cq, device=DEV)
+            dxb = ops.leaky_relu_bwd(dy.to(DEV), kw.get("ref"), 0.2, mask=kw.get("mask"), dbias=db)
+            dxp = ops.leaky_relu_bwd(dy.to(DEV), kw.get("ref"), 0.2, mask=kw.get("mask"))
+            assert (dxb.cpu().double() - want).abs().max() < 1e-6 and (dxp.cpu().double() - want).abs().max() < 1e-6
+            assert (db.cpu().double() - want.sum((0, 2))).abs().max() < 2e-4
+            db2 = torch.zeros(Cq, device=DEV)
+            assert ops.leaky_relu_bwd(dy.to(DEV), kw.get("ref"), 0.2, mask=kw.get("mask"), dbias=db2, want_dx=False) is None
+            assert (db2 - db).abs().max() < 1e-6 * float(db.abs().max()) + 1e-5
     # feature matching + hinge against the oracle (fp64)
     shapes = [[(2, 1, 500), (2, 24, 502), (2, 48, 251), (2, 1, 251)], [(2, 1, 2000), (2, 16, 2000), (2, 1, 500)]]
     a = [[torch.randn(s, dtype=torch.float64, requires_grad=True) for s in sc] for sc in shapes]

@@ -181,37 +181,92 @@ __global__ void leaky_relu_fwd_kernel(const float* __restrict__ x, float* __rest
   for (long long i = (n4 << 2) + i0; i < n; i += stride) { float v = x[i]; y[i] = v > 0.f ? v : v * slope; }
 }
 
-__global__ void leaky_relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ ref,
+// dx = dy * (pre-activation > 0 ? 1 : slope) (+ beta * dx); the sign comes from the byte mask the forward stored or
+// from `ref`.  VEC: everything 16-byte aligned (4 elements per thread and access).
+template <bool VEC>
+__global__ void __launch_bounds__(256) leaky_relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ ref,
                                       const unsigned char* __restrict__ mask, float* __restrict__ dx,
                                       long long n, float slope, float beta) {
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+  const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (VEC) {
+    const long long n4 = n >> 2;
+    for (long long i = i0; i < n4; i += stride) {
+      const float4 d = reinterpret_cast<const float4*>(dy)[i];
+      bool p0, p1, p2, p3;
+      if (mask) {
+        const uchar4 m = reinterpret_cast<const uchar4*>(mask)[i];
+        p0 = m.x != 0; p1 = m.y != 0; p2 = m.z != 0; p3 = m.w != 0;
+      } else {
+        const float4 r = reinterpret_cast<const float4*>(ref)[i];
+        p0 = r.x > 0.f; p1 = r.y > 0.f; p2 = r.z > 0.f; p3 = r.w > 0.f;
+      }
+      float4 v = make_float4(d.x * (p0 ? 1.f : slope), d.y * (p1 ? 1.f : slope), d.z * (p2 ? 1.f : slope),
+                             d.w * (p3 ? 1.f : slope));
+      if (beta != 0.f) {
+        const float4 o = reinterpret_cast<const float4*>(dx)[i];
+        v.x += beta * o.x; v.y += beta * o.y; v.z += beta * o.z; v.w += beta * o.w;
+      }
+      reinterpret_cast<float4*>(dx)[i] = v;
+    }
+    return;
+  }
+  for (long long i = i0; i < n; i += stride) {
     bool pos = mask ? mask[i] != 0 : ref[i] > 0.f;
     float v = dy[i] * (pos ? 1.f : slope);
     dx[i] = beta != 0.f ? beta * dx[i] + v : v;
   }
 }
 
-// per-channel variant that also reduces the bias gradient: grid (C, S)
+// per-channel variant that also reduces the bias gradient: grid (C, S); a block walks (batch item, 1024-position
+// chunk) pairs of its channel, 4 consecutive positions per thread (one 16-byte access when VEC)
+template <bool VEC>
 __global__ void __launch_bounds__(256) leaky_relu_bwd_bias_kernel(const float* __restrict__ dy, const float* __restrict__ ref,
                                            const unsigned char* __restrict__ mask, float* __restrict__ dx,
                                            float* __restrict__ dbias, int B, int C, int T, float slope,
                                            float beta) {
   __shared__ double sh[32];
   const int c = blockIdx.x;
-  const long long per = (long long)B * T;
-  double acc = 0.0;
-  for (long long e = blockIdx.y * (long long)blockDim.x + threadIdx.x; e < per;
-       e += (long long)gridDim.y * blockDim.x) {
-    int b = (int)(e / T), t = (int)(e % T);
-    long long i = ((long long)b * C + c) * T + t;
-    bool pos = mask ? mask[i] != 0 : (ref ? ref[i] > 0.f : true);
-    float v = dy[i] * (pos ? 1.f : slope);
-    acc += v;
-    if (dx) dx[i] = beta != 0.f ? beta * dx[i] + v : v;
+  const int nchunk = (T + 1023) / 1024;
+  float acc = 0.f;
+  for (int sidx = blockIdx.y; sidx < B * nchunk; sidx += gridDim.y) {
+    const int b = sidx / nchunk, t = (sidx % nchunk) * 1024 + threadIdx.x * 4;
+    if (t >= T) continue;
+    const long long i = ((long long)b * C + c) * T + t;
+    if (VEC) {                                           // T % 4 == 0: the four positions exist and are aligned
+      const float4 d = *reinterpret_cast<const float4*>(dy + i);
+      bool p0, p1, p2, p3;
+      if (mask) {
+        const uchar4 m = *reinterpret_cast<const uchar4*>(mask + i);
+        p0 = m.x != 0; p1 = m.y != 0; p2 = m.z != 0; p3 = m.w != 0;
+      } else if (ref) {
+        const float4 r = *reinterpret_cast<const float4*>(ref + i);
+        p0 = r.x > 0.f; p1 = r.y > 0.f; p2 = r.z > 0.f; p3 = r.w > 0.f;
+      } else {
+        p0 = p1 = p2 = p3 = true;
+      }
+      float4 v = make_float4(d.x * (p0 ? 1.f : slope), d.y * (p1 ? 1.f : slope), d.z * (p2 ? 1.f : slope),
+                             d.w * (p3 ? 1.f : slope));
+      acc += (v.x + v.y) + (v.z + v.w);
+      if (dx) {
+        if (beta != 0.f) {
+          const float4 o = *reinterpret_cast<const float4*>(dx + i);
+          v.x += beta * o.x; v.y += beta * o.y; v.z += beta * o.z; v.w += beta * o.w;
+        }
+        *reinterpret_cast<float4*>(dx + i) = v;
+      }
+    } else {
+      for (int e = 0; e < 4 && t + e < T; ++e) {
+        const long long j = i + e;
+        const bool pos = mask ? mask[j] != 0 : (ref ? ref[j] > 0.f : true);
+        const float v = dy[j] * (pos ? 1.f : slope);
+        acc += v;
+        if (dx) dx[j] = beta != 0.f ? beta * dx[j] + v : v;
+      }
+    }
   }
-  acc = block_sum(acc, sh);
-  if (threadIdx.x == 0) atomicAdd(dbias + c, (float)acc);
+  const double tot = block_sum((double)acc, sh);
+  if (threadIdx.x == 0) atomicAdd(dbias + c, (float)tot);
 }
 
 __global__ void tanh_recompose_fwd_kernel(const float* __restrict__ x, const float* __restrict__ first,
@@ -556,19 +611,25 @@ extern "C" int vbx_leaky_relu_bwd(const float* dy, const float* ref, const uint8
   VBX_REQUIRE(dy && (dx || dbias), VBX_BAD_POINTER, "leaky_relu_bwd: null tensor");
   VBX_REQUIRE(B > 0 && C > 0 && T > 0, VBX_BAD_SHAPE, "leaky_relu_bwd: bad shape");
   long long n = (long long)B * C * T;
+  const uintptr_t al = (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)ref;
   if (dbias) {
     VBX_REQUIRE(C <= 65535 * 32, VBX_UNSUPPORTED, "leaky_relu_bwd: too many channels");
-    long long per = (long long)B * T;
-    int S = (int)((per + 2047) / 2048);
-    int cap = (kSMs * 8 + C - 1) / C;
+    const long long units = (long long)B * ((T + 1023) / 1024);      // (item, chunk) pairs per channel
+    int S = (int)(units < 65535 ? units : 65535);
+    int cap = (kSMs * 16 + C - 1) / C;
     if (S > cap) S = cap;
     if (S < 1) S = 1;
     dim3 grid(C, S);
-    leaky_relu_bwd_bias_kernel<<<grid, 256, 0, ST>>>(dy, ref, mask, dx, dbias, B, C, T, slope, beta);
+    const bool vec = (T & 3) == 0 && (al & 15) == 0 && ((uintptr_t)mask & 3) == 0;
+    if (vec) leaky_relu_bwd_bias_kernel<true><<<grid, 256, 0, ST>>>(dy, ref, mask, dx, dbias, B, C, T, slope, beta);
+    else leaky_relu_bwd_bias_kernel<false><<<grid, 256, 0, ST>>>(dy, ref, mask, dx, dbias, B, C, T, slope, beta);
     return launched("leaky_relu_bwd_bias_kernel");
   }
   VBX_REQUIRE(ref || mask, VBX_BAD_POINTER, "leaky_relu_bwd: need ref or mask");
-  leaky_relu_bwd_kernel<<<stream_blocks(n, 1024), 256, 0, ST>>>(dy, ref, mask, dx, n, slope, beta);
+  if ((n & 3) == 0 && (al & 15) == 0 && ((uintptr_t)mask & 3) == 0)
+    leaky_relu_bwd_kernel<true><<<stream_blocks(n, 4096), 256, 0, ST>>>(dy, ref, mask, dx, n, slope, beta);
+  else
+    leaky_relu_bwd_kernel<false><<<stream_blocks(n, 1024), 256, 0, ST>>>(dy, ref, mask, dx, n, slope, beta);
   return launched("leaky_relu_bwd_kernel");
 }
 extern "C" int vbx_tanh_recompose_fwd(const float* x, const float* first, float* y, int32_t B, int32_t m,
