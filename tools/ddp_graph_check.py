@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import vibravox_b200
 from vibravox_b200 import parallel
-from oracle import eben_oracle as O
+from vibravox_b200 import data as O
 
 rank, local_rank, world = parallel.init_from_env("nccl")
 torch.cuda.set_device(local_rank)

@@ -5,7 +5,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import vibravox_b200
-from oracle import eben_oracle as O
+from vibravox_b200 import data as O
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 12
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 32

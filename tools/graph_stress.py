@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import vibravox_b200
-from oracle import eben_oracle as O
+from vibravox_b200 import data as O
 gold = torch.load("tests/golden/train_step.pt")
 body, air = O.synthetic_pairs(gold["B"], gold["S"], seed=gold["data_seed"])
 batch = {"audio_body_conducted": body.cuda(), "audio_airborne": air.cuda()}

@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import vibravox_b200
 from vibravox_b200 import ops
-from oracle import eben_oracle as O
+from vibravox_b200 import data as O
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 S = int(float(sys.argv[2]) * 16000) if len(sys.argv) > 2 else 48000

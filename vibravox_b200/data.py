@@ -19,6 +19,15 @@ def _samples(collate_strategy: str, sample_rate: int) -> int:
     return int(m.group(1)) * sample_rate // 1000
 
 
+def synthetic_pairs(batch: int, samples: int, seed: int):
+    """(body-conducted, airborne) noise pair of SURVEY 8(d): 0.1*randn clamped to +-1, (B,1,samples) each, drawn
+    from a host generator so that every tool / bench / test sees the same batch for a seed."""
+    g = torch.Generator().manual_seed(seed)
+    air = (0.1 * torch.randn(batch, 1, samples, generator=g)).clamp(-1, 1)
+    body = (0.1 * torch.randn(batch, 1, samples, generator=g)).clamp(-1, 1)
+    return body, air
+
+
 class SyntheticBWEDataModule:
     def __init__(self, sample_rate: int = 16000, batch_size: int = 32,
                  collate_strategy: str = "constant_length-3000-ms", seed: int = 42, id: str = "synthetic_bwe"):
