@@ -304,6 +304,9 @@ TC_CASES = [
     # zero-halo input gradients (merged phases on a unit or dilated tap lattice), stride-1 flipped-tap gradients
     (3, 48, 96, 700, 7, 2, 3, 3, 0, 4), (3, 48, 96, 701, 7, 2, 2, 3, 0, 4), (2, 64, 64, 333, 5, 1, 3, 6, 0, 2),
     (2, 40, 80, 500, 5, 3, 2, 4, 0, 2), (3, 512, 512, 187, 41, 4, 1, 20, 0, 2), (2, 36, 20, 450, 3, 1, 9, 9, 9, 1),
+    # narrow groups densified into one block-diagonal conv (MelGAN stage 1, PQMF-discriminator stages 1-2, odd group counts)
+    (2, 16, 64, 1203, 41, 4, 1, 20, 0, 4), (2, 24, 48, 533, 7, 2, 1, 3, 0, 4), (3, 12, 36, 222, 5, 1, 1, 2, 0, 3),
+    (2, 48, 96, 300, 7, 2, 1, 3, 0, 4),
 ]
 
 

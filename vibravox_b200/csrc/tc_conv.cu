@@ -59,6 +59,15 @@ struct TcP {
   int sl_tpb;       // taps per weight stage
   int sl_nbst;      // weight stages per channel group = ceil(K / sl_tpb)
   int sl_SA, sl_SB; // ring depths: slab stages / weight stages
+  // Densified groups (slab form only): a grouped conv whose groups are narrower than the 16-channel reduction unit
+  // runs as ONE dense conv over all channels against block-diagonal packed weights.  The MMAs are far from the
+  // bound on such layers; what counts is that every input position is staged once per tile instead of once per
+  // group and that a tile writes all output channels.  dg = original group count (0: not densified).
+  int dg, dg_cin, dg_cout;
+  // Persistent slab form (tc_pslab.cuh): weights resident in shared memory, CTAs walk row tiles.
+  int ps;           // 1: launch tc_pslab_kernel (then sl_tpb = K, sl_nbst = 1, tmem_cols = two accumulator buffers)
+  int ps_slots;     // slab ring depth in whole tiles (1 or 2)
+  int ps_gx;        // CTAs along the row-tile axis
 };
 
 // one reduction segment of a tile: FWD has one; DGRAD has one per mirror image it touches
@@ -556,6 +565,7 @@ __global__ void tc_pack_merged_kernel(const float* __restrict__ w, unsigned char
 }
 
 #include "tc_slab.cuh"
+#include "tc_pslab.cuh"
 
 // Merged-phase input gradient on the gather kernel: worth it only where the common tap grid has no holes
 // (dil = 1) and a phase does not already fill a 256-wide tile.  The slab kernel takes the general case.
@@ -570,6 +580,37 @@ static size_t slab_smem_bytes(const TcP& P) {
   return (size_t)P.sl_SA * slab_a_stage(P.g) + (size_t)P.sl_SB * slab_b_stage(P.NT, P.sl_tpb) +
          (2 * P.sl_SA + 2 * P.sl_SB + 1) * sizeof(uint64_t) + 16 + (size_t)P.g.K * sizeof(int) + 16;
 }
+static size_t pslab_smem_bytes(const TcP& P, int slots) {
+  return (size_t)P.sl_ncg * slab_b_stage(P.NT, P.g.K) + (size_t)slots * P.sl_ncg * slab_a_stage(P.g) +
+         (2 * slots + 5) * sizeof(uint64_t) + 16 + (size_t)P.g.K * sizeof(int) + 16;
+}
+// Persistent form when the packed weights of one (group, column tile) fit beside at least one tile's slab:
+// picks CTAs per SM (shared memory, TMEM columns, 64-register budget) and the slab ring depth.
+static void plan_pslab(TcP& P) {
+  static const int max_kb = getenv("VBX_TC_PS_MAX_KB") ? atoi(getenv("VBX_TC_PS_MAX_KB")) : 176;   // 0: off
+  P.ps = 0;
+  const size_t wbytes = (size_t)P.sl_ncg * slab_b_stage(P.NT, P.g.K);
+  if (wbytes > (size_t)max_kb * 1024) return;
+  const int cols2 = 2 * pow2_cols(P.NT);
+  if (cols2 > 512) return;
+  const int occ_tmem = 512 / cols2;
+  static const int order[6][2] = {{3, 2}, {2, 2}, {3, 1}, {2, 1}, {1, 2}, {1, 1}};   // (CTAs per SM, ring slots)
+  for (int i = 0; i < 6; ++i) {
+    const int occ = order[i][0], slots = order[i][1];
+    if (occ > occ_tmem) continue;
+    if (pslab_smem_bytes(P, slots) + 1024 > (size_t)(227 * 1024) / occ) continue;
+    const long long row_tiles = ((long long)P.g.B * P.sl_R + kRows - 1) / kRows;
+    const int gy = P.ntiles_n * P.g.groups;
+    long long gx = (148ll * occ) / gy;
+    if (gx < 1) gx = 1;
+    if (gx > row_tiles) gx = row_tiles;
+    P.ps = 1; P.ps_slots = slots; P.ps_gx = (int)gx;
+    P.sl_tpb = P.g.K; P.sl_nbst = 1;
+    P.tmem_cols = cols2;
+    return;
+  }
+}
+
 static void plan_slab(TcP& P, const vbx_conv_desc* d) {
   static const int min_cin = getenv("VBX_TC_SLAB_MIN_CIN") ? atoi(getenv("VBX_TC_SLAB_MIN_CIN")) : 8;
   static const int min_k = getenv("VBX_TC_SLAB_MIN_K") ? atoi(getenv("VBX_TC_SLAB_MIN_K")) : 2;
@@ -594,17 +635,36 @@ static void plan_slab(TcP& P, const vbx_conv_desc* d) {
     if (slab_smem_bytes(P) > 200 * 1024) return;
   }
   P.slab = 1;
+  plan_pslab(P);
 }
+
+static void densify(GemmP& g) { g.groups = 1; g.Cin_g = g.Cin; g.Cout_g = g.Cout; }
+
+// all input channels of the layer fit a few 16-channel reduction units: see TcP::dg
+static bool dense_candidate(const vbx_conv_desc* d, int nsplit) {
+  static const int max_cin = getenv("VBX_TC_DENSE_MAX_CIN") ? atoi(getenv("VBX_TC_DENSE_MAX_CIN")) : 48;
+  return nsplit == 2 && d->groups > 1 && d->Cin / d->groups > 1 && d->Cin <= max_cin && d->Cout <= 256;
+}
+
+static int fill_tc_geom(TcP& P, const vbx_conv_desc* d, int mode, int nsplit, bool dense);
 
 static int fill_tc(TcP& P, const vbx_conv_desc* d, int mode, int nsplit) {
   int code = 0;
   const char* msg = check_desc_msg(d, &code);
   if (msg) return fail(code, msg);
   if (nsplit != 2 && nsplit != 3) return fail(VBX_UNSUPPORTED, "tc: nsplit must be 2 (bf16x3) or 3 (bf16x6)");
+  if (dense_candidate(d, nsplit) && fill_tc_geom(P, d, mode, nsplit, true) == 0 && P.slab) return 0;
+  return fill_tc_geom(P, d, mode, nsplit, false);
+}
+
+static int fill_tc_geom(TcP& P, const vbx_conv_desc* d, int mode, int nsplit, bool dense) {
   fill(P.g, d);
+  P.dg = 0; P.dg_cin = P.g.Cin_g; P.dg_cout = P.g.Cout_g;
+  if (dense) { P.dg = P.g.groups; densify(P.g); }
   P.nsplit = nsplit;
   P.merged = 0;
   P.slab = 0;
+  P.ps = 0;
   if (mode == DGRAD && P.g.refl == 0 && P.g.stride <= 8) {
     // Zero-halo input gradient as a stride-1 forward conv over dy (Cout ch, Tout long) -> D (s*Cin ch, V long):
     // every stride phase of dx becomes a block of columns, the taps sit on a unit-spaced grid of J slots
@@ -650,6 +710,7 @@ static int fill_tc(TcP& P, const vbx_conv_desc* d, int mode, int nsplit) {
   P.tmem_cols = pow2_cols(P.NT);
   P.stages = pick_stages_for(stage_bytes(P.NT, P.nsplit), P.nchunks);
   if (mode == FWD && !P.slab) plan_slab(P, d);
+  if (P.slab && P.ps) plan_pslab(P);          // (re-applies tmem_cols = two accumulator buffers)
   return 0;
 }
 
@@ -692,6 +753,19 @@ static int launch_slab(const TcP& P, cudaStream_t st) {
   if (grid.y > 65535) return fail(VBX_UNSUPPORTED, "tc_slab: grid too large");
   tc_slab_kernel<<<grid, kThreads, slab_smem_bytes(P), st>>>(P);
   return launched("tc_slab_kernel");
+}
+
+static int launch_pslab(const TcP& P, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t ce = cudaFuncSetAttribute(tc_pslab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (ce != cudaSuccess) return fail((int)ce, "tc_pslab: cannot raise the dynamic shared memory limit");
+    attr_set = true;
+  }
+  dim3 grid((unsigned)P.ps_gx, (unsigned)(P.ntiles_n * P.g.groups), 1);
+  if (grid.y > 65535) return fail(VBX_UNSUPPORTED, "tc_pslab: grid too large");
+  tc_pslab_kernel<<<grid, kThreads, pslab_smem_bytes(P, P.ps_slots), st>>>(P);
+  return launched("tc_pslab_kernel");
 }
 
 template <int MODE>
@@ -1016,6 +1090,7 @@ extern "C" int vbx_tc_pack(const vbx_conv_desc* d, int32_t mode, int32_t nsplit,
   MergedDev D = {};
   if (P.merged) {
     GemmP o; fill(o, d);
+    if (P.dg) densify(o);
     const MergedPlan M = merged_plan(o);
     for (int i = 0; i < 8; ++i) { D.c[i] = M.c[i]; D.k0[i] = M.k0[i]; D.nt[i] = i < o.stride ? M.nt[i] : 0; }
     D.cmax = M.cmax; D.J = M.J; D.s = o.stride; D.Cin_g = o.Cin_g; D.Cout_g = o.Cout_g; D.K = o.K;
@@ -1049,7 +1124,7 @@ extern "C" int vbx_tc_conv1d_fwd(const vbx_conv_desc* d, const float* x, const v
   fill_epi(P.g, e);
   P.g.X = x; P.g.Y = y;
   P.packed = (const unsigned char*)packed;
-  if (P.slab) return launch_slab(P, (cudaStream_t)stream);
+  if (P.slab) return P.ps ? launch_pslab(P, (cudaStream_t)stream) : launch_slab(P, (cudaStream_t)stream);
   return launch_tc<FWD>(P, (cudaStream_t)stream);
 }
 
@@ -1062,7 +1137,7 @@ extern "C" int vbx_tc_conv1d_dgrad(const vbx_conv_desc* d, const float* dy, cons
   fill_epi(P.g, e);
   P.g.X = dy; P.g.Y = dx;
   P.packed = (const unsigned char*)packed;
-  if (P.slab) return launch_slab(P, (cudaStream_t)stream);
+  if (P.slab) return P.ps ? launch_pslab(P, (cudaStream_t)stream) : launch_slab(P, (cudaStream_t)stream);
   if (P.merged) return launch_tc<FWD>(P, (cudaStream_t)stream);
   return launch_tc<DGRAD>(P, (cudaStream_t)stream);
 }

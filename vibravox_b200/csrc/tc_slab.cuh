@@ -22,6 +22,85 @@ __host__ __device__ inline int slab_U(const GemmP& G) { return kRows + ((G.K - 1
 __host__ __device__ inline int slab_a_stage(const GemmP& G) { return 64 * G.stride * slab_U(G); }   // 2 planes x 2 halves
 __host__ __device__ inline int slab_b_stage(int NT, int tpb) { return tpb * NT * 64; }
 
+// Epilogue of one 128-row tile: the eight producer warps read the accumulator (warp & 3 = TMEM lane quadrant,
+// warp >> 2 = which half of the 16-column blocks) and write bias / LeakyReLU / residual / mask fused, coalesced
+// along time.  Shared by the streaming (tc_slab_kernel) and the persistent (tc_pslab_kernel) forms.
+__device__ __forceinline__ void slab_epilogue(const TcP& P, uint32_t tmem_base, int rv0, int nt, int grp, int warp,
+                                              int lane) {
+  const GemmP& G = P.g;
+  const int NT = P.NT, R = P.sl_R, Ccol = G.Cout_g;
+  const int q = warp & 3, half = warp >> 2;
+  const int rv = rv0 + q * 32 + lane;
+  const int eb = rv / R, et = rv % R;
+  const bool ev = eb < G.B && et < G.Tout;
+  const int nblk = NT / 16;
+  const int blk_lo = half == 0 ? 0 : (nblk + 1) / 2, blk_hi = half == 0 ? (nblk + 1) / 2 : nblk;
+  for (int blk = blk_lo; blk < blk_hi; ++blk) {
+    float acc[16];
+    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * 16), acc);
+    if (!ev) continue;
+    const int cb = nt * NT + blk * 16;
+    if (P.merged) {
+      // rows are (b, v); column = phase * Cin_g + ci  ->  dx[b, ci, r(phase) + s*v]
+      int col = cb;
+      int ph = col / P.mg_Cing, ci = col % P.mg_Cing;
+#pragma unroll
+      for (int j = 0; j < 16; ++j, ++col) {
+        if (col < Ccol) {
+          const int u = P.mg_r[ph] + P.mg_s * et;
+          if (u < P.mg_Tx) {
+            const int ch = grp * P.mg_Cing + ci;
+            const long long idx = ((long long)eb * P.mg_Cin + ch) * P.mg_Tx + u;
+            G.Y[idx] = finish(G, acc[j], ch, idx);
+          }
+        }
+        if (++ci == P.mg_Cing) { ci = 0; ++ph; }
+      }
+      continue;
+    }
+    const long long out_base = ((long long)eb * G.Cout + grp * Ccol) * G.Tout + et;
+    const int Tlen = G.Tout;
+    if (cb + 16 <= Ccol && G.beta == 0.f) {
+      const long long o = out_base + (long long)cb * Tlen;
+      if (G.bias) {
+        const float* bp = G.bias + grp * Ccol + cb;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] += __ldg(bp + j);
+      }
+      if (G.mask) {
+        unsigned char* mp = G.mask + o;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) mp[(long long)j * Tlen] = acc[j] > 0.f ? 1 : 0;
+      }
+      if (G.slope != 1.f) {
+        const float sl = G.slope;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = acc[j] > 0.f ? acc[j] : acc[j] * sl;
+      }
+      if (G.res) {
+        const float* rp = G.res + o;
+        float r[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = rp[(long long)j * Tlen];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] += r[j];
+      }
+      float* yp = G.Y + o;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) yp[(long long)j * Tlen] = acc[j];
+      continue;
+    }
+#pragma unroll 1
+    for (int j = 0; j < 16; ++j) {
+      const int col = cb + j;
+      if (col < Ccol) {
+        const long long idx = out_base + (long long)col * Tlen;
+        G.Y[idx] = finish(G, acc[j], grp * Ccol + col, idx);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 3) tc_slab_kernel(const TcP P) {
   extern __shared__ __align__(128) unsigned char smem[];
   const GemmP& G = P.g;
@@ -122,76 +201,7 @@ __global__ void __launch_bounds__(kThreads, 3) tc_slab_kernel(const TcP P) {
     // ===================== epilogue =====================
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    const int q = warp & 3, half = warp >> 2;
-    const int rv = rv0 + q * 32 + lane;
-    const int eb = rv / R, et = rv % R;
-    const bool ev = eb < G.B && et < G.Tout;
-    const int nblk = NT / 16;
-    const int blk_lo = half == 0 ? 0 : (nblk + 1) / 2, blk_hi = half == 0 ? (nblk + 1) / 2 : nblk;
-    for (int blk = blk_lo; blk < blk_hi; ++blk) {
-      float acc[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * 16), acc);
-      if (!ev) continue;
-      const int cb = nt * NT + blk * 16;
-      if (P.merged) {
-        // rows are (b, v); column = phase * Cin_g + ci  ->  dx[b, ci, r(phase) + s*v]
-        int col = cb;
-        int ph = col / P.mg_Cing, ci = col % P.mg_Cing;
-#pragma unroll
-        for (int j = 0; j < 16; ++j, ++col) {
-          if (col < Ccol) {
-            const int u = P.mg_r[ph] + P.mg_s * et;
-            if (u < P.mg_Tx) {
-              const int ch = grp * P.mg_Cing + ci;
-              const long long idx = ((long long)eb * P.mg_Cin + ch) * P.mg_Tx + u;
-              G.Y[idx] = finish(G, acc[j], ch, idx);
-            }
-          }
-          if (++ci == P.mg_Cing) { ci = 0; ++ph; }
-        }
-        continue;
-      }
-      const long long out_base = ((long long)eb * G.Cout + grp * Ccol) * G.Tout + et;
-      const int Tlen = G.Tout;
-      if (cb + 16 <= Ccol && G.beta == 0.f) {
-        const long long o = out_base + (long long)cb * Tlen;
-        if (G.bias) {
-          const float* bp = G.bias + grp * Ccol + cb;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] += __ldg(bp + j);
-        }
-        if (G.mask) {
-          unsigned char* mp = G.mask + o;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) mp[(long long)j * Tlen] = acc[j] > 0.f ? 1 : 0;
-        }
-        if (G.slope != 1.f) {
-          const float sl = G.slope;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] = acc[j] > 0.f ? acc[j] : acc[j] * sl;
-        }
-        if (G.res) {
-          const float* rp = G.res + o;
-          float r[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) r[j] = rp[(long long)j * Tlen];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] += r[j];
-        }
-        float* yp = G.Y + o;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) yp[(long long)j * Tlen] = acc[j];
-        continue;
-      }
-#pragma unroll 1
-      for (int j = 0; j < 16; ++j) {
-        const int col = cb + j;
-        if (col < Ccol) {
-          const long long idx = out_base + (long long)col * Tlen;
-          G.Y[idx] = finish(G, acc[j], grp * Ccol + col, idx);
-        }
-      }
-    }
+    slab_epilogue(P, tmem_base, rv0, nt, grp, warp, lane);
   } else if (warp == 8) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
@@ -274,12 +284,24 @@ __global__ void tc_pack_slab_kernel(const float* __restrict__ w, unsigned char* 
       float v = 0.f;
       if (col < G.Cout_g && c < G.Cin_g && tap < G.K) {
         if (!MERGED) {
-          v = w[(((long long)g * G.Cout_g + col) * G.Cin_g + c) * G.K + tap];
+          if (!P.dg) {
+            v = w[(((long long)g * G.Cout_g + col) * G.Cin_g + c) * G.K + tap];
+          } else {                                   // block-diagonal: channel c feeds column col only inside its group
+            const int cl = c - (col / P.dg_cout) * P.dg_cin;
+            if (cl >= 0 && cl < P.dg_cin) v = w[((long long)col * P.dg_cin + cl) * G.K + tap];
+          }
         } else {
           const int ph = col / M.Cin_g, ci = col % M.Cin_g;
           const int jj = merged_tap(M, ph, tap);
-          if (jj >= 0)
-            v = w[(((long long)g * M.Cout_g + c) * M.Cin_g + ci) * M.K + M.k0[ph] + jj * M.kstep];
+          if (jj >= 0) {
+            if (!P.dg) {
+              v = w[(((long long)g * M.Cout_g + c) * M.Cin_g + ci) * M.K + M.k0[ph] + jj * M.kstep];
+            } else {                                 // c = output channel of the conv, ci = its input channel (dense)
+              const int cl = ci - (c / P.dg_cout) * P.dg_cin;
+              if (cl >= 0 && cl < P.dg_cin)
+                v = w[((long long)c * P.dg_cin + cl) * M.K + M.k0[ph] + jj * M.kstep];
+            }
+          }
         }
       }
       split_bf16(v, hi[e], lo[e]);
