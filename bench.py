@@ -242,7 +242,9 @@ def run_ours(args):
                                f"bs={B}x{args.seconds:g}s@16kHz per GPU (L={L} after cut_to_valid_length), "
                                f"m=4 n=32 p=2 q=4 min_channels=24, schedule={lm.schedule}",
                    "batch_per_gpu": B, "samples": L, "parallelism": f"dp{world}",
-                   "launch": "one CUDA graph replay per step" if graphed else "eager launches",
+                   "launch": ({"whole": "one CUDA graph replay per step",
+                               "segments": "three CUDA graph replays per step, split at the two eager NCCL gradient "
+                                           "all-reduces"}[lm.graph_mode()] if graphed else "eager launches"),
                    "l2": "per-step working set (activations ~ GBs) >> 126 MB L2; no explicit flush"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roof, "kernel_rooflines": kernels,

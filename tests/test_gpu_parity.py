@@ -227,8 +227,10 @@ def test_full_size_properties(path):
             assert (sa[-1][5:6] - sb[-1]).abs().max() < 1e-4
 
 
-def test_graphed_step_matches_eager_and_golden(golden_dir):
-    """training_step_graphed (2 eager calls, capture, replays) walks the same trajectory as training_step:
+@pytest.mark.parametrize("mode", ["whole", "segments"])
+def test_graphed_step_matches_eager_and_golden(golden_dir, mode, monkeypatch):
+    """training_step_graphed (2 eager calls, capture, replays) walks the same trajectory as training_step -
+    as one graph, and as the three graphs split at the gradient all-reduces that world_size > 1 replays:
     the first two steps match the reference's golden logs, and over 6 steps the captured replay stays with an
     eager twin to within the drift two eager runs show between themselves (fp32 atomics in the split-K sums)."""
     # `out` of the previous call is kept alive across the capture on purpose (stale autograd nodes must not matter)
@@ -240,9 +242,11 @@ def test_graphed_step_matches_eager_and_golden(golden_dir):
     host_batch = {"audio_body_conducted": body.pin_memory(), "audio_airborne": air.pin_memory()}
     keys = ("train/generator/backprop_loss", "train/discriminator/backprop_loss")
 
+    monkeypatch.setenv("VBX_GRAPH_SEGMENTS", "1" if mode == "segments" else "0")
+
     def run(graphed):
         lm = vibravox_b200.build_model(seed=gold["model_seed"], device=DEV)
-        assert lm.graph_capturable()
+        assert lm.graph_capturable() and lm.graph_mode() == mode
         tr = []
         for it in range(6):
             out = lm.training_step_graphed(host_batch) if graphed else lm.training_step(batch)
@@ -251,6 +255,10 @@ def test_graphed_step_matches_eager_and_golden(golden_dir):
 
     lm_g, tr_g = run(True)
     assert lm_g.graph_launches() > 500                      # the whole step was captured
+    st = next(iter(lm_g._graphs.values()))
+    assert not getattr(lm_g, "_graph_failed", False) and st["graph"] is not None
+    if mode == "segments":
+        assert len(st["graph"].graphs) == 3 and len(st["graph"].buckets) == 2
     assert int(lm_g.generator_optimizer.step_count) == 6    # one Adam tick per call, eager or replayed
     _, tr_e = run(False)
     for it in range(2):

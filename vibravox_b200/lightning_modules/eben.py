@@ -22,6 +22,20 @@ from ..parallel import allreduce_sum_
 from ..torch_modules.utils import share_weight_norm
 
 
+class _SegmentedStep:
+    """A training step captured as consecutive CUDA graphs; after graph i the i-th gradient bucket is sum-all-reduced
+    with an ordinary (eager) collective, so NCCL calls are issued in program order on every rank."""
+
+    def __init__(self, graphs, buckets):
+        self.graphs, self.buckets = graphs, buckets
+
+    def replay(self) -> None:
+        for i, g in enumerate(self.graphs):
+            g.replay()
+            if i < len(self.buckets):
+                allreduce_sum_(self.buckets[i])
+
+
 class EBENLightningModule(torch.nn.Module):
     def __init__(self, sample_rate: int, generator: torch.nn.Module, discriminator: torch.nn.Module,
                  generator_optimizer, discriminator_optimizer,
@@ -61,6 +75,7 @@ class EBENLightningModule(torch.nn.Module):
         self._bal = None
         self.logged: Dict[str, torch.Tensor] = {}
         self._graphs: Dict[tuple, dict] = {}      # training_step_graphed: one captured step per batch shape
+        self._capture = None                      # state of a segmented capture in progress (see _capture_segments)
         self.graph_warmup_steps = 2
 
     # ---- Lightning services, restated --------------------------------------------------------
@@ -109,27 +124,45 @@ class EBENLightningModule(torch.nn.Module):
               and self.dynamic_loss_balancing is not None)
         return self._training_step_shared(batch) if ok else self._training_step_reference(batch)
 
-    def graph_capturable(self) -> bool:
-        """The step replays as one CUDA graph when nothing in it is decided on the host per step."""
+    def graph_mode(self) -> str:
+        """How `training_step_graphed` launches the step: 'whole' (one CUDA graph), 'segments' (three graphs split
+        at the two gradient all-reduces, which stay ordinary eager NCCL calls between the replays) or 'eager'.
+
+        world_size == 1 replays the whole step.  world_size > 1 uses segments: NCCL inside a captured multi-stream
+        step measured 98 % scaling on 2 GPUs but one verification run hung (opt-in: VBX_GRAPH_DDP=1), while eager
+        launches leave the step host-bound (82 %).  Segments keep every collective out of the graphs - issued from
+        the host in program order on all ranks - and still cost only three cudaGraphLaunch calls per step.
+        VBX_GRAPH_SEGMENTS=1 forces segments on one GPU (tests), =0 forces eager launches for world_size > 1."""
         import os
+        flat = all(isinstance(o, FlatAdam) for o in self.configure_optimizers())
+        if not flat or self.update_discriminator_ratio < 1 or getattr(self, "_graph_failed", False):
+            return "eager"                   # per-step host decisions / foreign optimizers cannot be captured
         multi = (torch.distributed.is_available() and torch.distributed.is_initialized()
                  and torch.distributed.get_world_size() > 1)
-        # world_size > 1: capturing the NCCL gradient all-reduce with the step works in bench.py (2 GPUs: 46.1 vs
-        # 55.4 ms per step) but a 2-rank check run hung once, so it stays opt-in (VBX_GRAPH_DDP=1) until understood
-        if multi and (os.environ.get("VBX_GRAPH_DDP", "0") != "1" or torch.distributed.get_backend() != "nccl"):
-            return False
-        flat = all(isinstance(o, FlatAdam) for o in self.configure_optimizers())
-        return flat and self.update_discriminator_ratio >= 1 and not getattr(self, "_graph_failed", False)
+        seg = os.environ.get("VBX_GRAPH_SEGMENTS")
+        if not multi:
+            return "segments" if seg == "1" else "whole"
+        if torch.distributed.get_backend() != "nccl":
+            return "eager"
+        if os.environ.get("VBX_GRAPH_DDP", "0") == "1":
+            return "whole"
+        return "eager" if seg == "0" else "segments"
+
+    def graph_capturable(self) -> bool:
+        """The step replays from CUDA graphs when nothing in it is decided on the host per step."""
+        return self.graph_mode() != "eager"
 
     def training_step_graphed(self, batch: Dict[str, torch.Tensor]):
-        """`training_step` replayed from a CUDA graph (all streams of the step included): the ~1300 kernel launches
-        of a step cost one cudaGraphLaunch, so the step no longer depends on how fast the host can issue them.
+        """`training_step` replayed from CUDA graphs (all streams of the step included): the ~1300 kernel launches
+        of a step cost one cudaGraphLaunch (three when split at the gradient all-reduces, see `graph_mode`), so the
+        step no longer depends on how fast the host can issue them.
         Every call performs exactly one training step: the first `graph_warmup_steps` calls for a batch shape run
         eagerly (they fill the weight / filter caches that outlive a step), the next call captures the step and
         replays it, later calls copy the batch into the captured input buffers and replay.  `batch` tensors may
         live on the host (pinned) or the device.  The returned tensors and `self.logged` are the graph's static
         outputs: valid until the next call.  Learning rates are baked in at capture time."""
-        if not self.graph_capturable():
+        mode = self.graph_mode()
+        if mode == "eager":
             dev = self.generator.last_conv.weight.device
             return self.training_step({k: v.to(dev, non_blocking=True) for k, v in batch.items()
                                        if isinstance(v, torch.Tensor)})
@@ -158,13 +191,17 @@ class EBENLightningModule(torch.nn.Module):
                 return out
             from .. import _lib
             torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
             multi = torch.distributed.is_available() and torch.distributed.is_initialized()
+            # (thread_local: NCCL's watchdog thread may poll its events while this thread captures)
+            error_mode = "thread_local" if multi else "global"
             try:
-                # (thread_local: NCCL's watchdog thread may poll its events while this thread captures)
-                with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local" if multi else "global"):
-                    st["out"] = self.training_step(st["inputs"])
+                if mode == "whole":
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph, stream=side, capture_error_mode=error_mode):
+                        st["out"] = self.training_step(st["inputs"])
+                else:
+                    graph = self._capture_segments(st, side, error_mode)
             except Exception as exc:           # nothing of the captured step has run: do it eagerly, stay eager
                 import warnings
                 warnings.warn(f"CUDA-graph capture of the training step failed ({exc}); using eager launches")
@@ -176,6 +213,44 @@ class EBENLightningModule(torch.nn.Module):
         self.logged = st["logged"]
         st["graph"].replay()
         return st["out"]
+
+    def _capture_segments(self, st, side, error_mode):
+        """Capture the step as consecutive graphs sharing one memory pool; `_sync_grads` closes a segment and opens
+        the next one wherever the eager step all-reduces a gradient bucket (all side streams are joined there)."""
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        cap = self._capture = dict(pool=torch.cuda.graph_pool_handle(), graphs=[], buckets=[], error_mode=error_mode,
+                                   open=False)
+        side.wait_stream(torch.cuda.current_stream())
+        try:
+            with torch.cuda.stream(side):
+                self._segment_begin()
+                st["out"] = self.training_step(st["inputs"])
+                self._segment_end()
+        except BaseException:
+            if cap["open"]:
+                try:
+                    self._segment_end()
+                except Exception:
+                    pass
+            raise
+        finally:
+            self._capture = None
+        torch.cuda.current_stream().wait_stream(side)
+        return _SegmentedStep(cap["graphs"], cap["buckets"])
+
+    def _segment_begin(self) -> None:
+        cap = self._capture
+        g = torch.cuda.CUDAGraph()
+        g.capture_begin(pool=cap["pool"], capture_error_mode=cap["error_mode"])
+        cap["graphs"].append(g)
+        cap["open"] = True
+
+    def _segment_end(self) -> None:
+        cap = self._capture
+        cap["open"] = False
+        cap["graphs"][-1].capture_end()
 
     def graph_launches(self) -> int:
         """Kernels of this library inside one captured step (0 before capture)."""
@@ -292,6 +367,15 @@ class EBENLightningModule(torch.nn.Module):
         return lambdas
 
     def _sync_grads(self, optimizer) -> None:
+        if getattr(self, "_capture", None) is not None:
+            # segmented capture: the all-reduce of this bucket happens between two graph replays
+            optimizer.gather_autograd_grads()
+            self._segment_end()
+            self._capture["buckets"].append(optimizer.grad)
+            from ..parallel import world_size
+            optimizer.grad_scale = 1.0 / world_size()
+            self._segment_begin()
+            return
         if torch.distributed.is_available() and torch.distributed.is_initialized() \
                 and torch.distributed.get_world_size() > 1:
             if isinstance(optimizer, FlatAdam):
