@@ -587,15 +587,17 @@ static size_t pslab_smem_bytes(const TcP& P, int slots) {
 // Persistent form when the packed weights of one (group, column tile) fit beside at least one tile's slab:
 // picks CTAs per SM (shared memory, TMEM columns, 64-register budget) and the slab ring depth.
 static void plan_pslab(TcP& P) {
-  static const int max_kb = getenv("VBX_TC_PS_MAX_KB") ? atoi(getenv("VBX_TC_PS_MAX_KB")) : 176;   // 0: off
+  static const int max_kb = getenv("VBX_TC_PS_MAX_KB") ? atoi(getenv("VBX_TC_PS_MAX_KB")) : 112;   // 0: off
   P.ps = 0;
   const size_t wbytes = (size_t)P.sl_ncg * slab_b_stage(P.NT, P.g.K);
   if (wbytes > (size_t)max_kb * 1024) return;
   const int cols2 = 2 * pow2_cols(P.NT);
   if (cols2 > 512) return;
   const int occ_tmem = 512 / cols2;
-  static const int order[6][2] = {{3, 2}, {2, 2}, {3, 1}, {2, 1}, {1, 2}, {1, 1}};   // (CTAs per SM, ring slots)
-  for (int i = 0; i < 6; ++i) {
+  // (CTAs per SM, ring slots).  One CTA per SM is not offered: with nothing to overlap its stage / MMA / drain chain
+  // it measured slower than the streaming kernel (192>384 k7 s2 input gradient: 77 vs 60 us).
+  static const int order[4][2] = {{3, 2}, {2, 2}, {3, 1}, {2, 1}};
+  for (int i = 0; i < 4; ++i) {
     const int occ = order[i][0], slots = order[i][1];
     if (occ > occ_tmem) continue;
     if (pslab_smem_bytes(P, slots) + 1024 > (size_t)(227 * 1024) / occ) continue;
