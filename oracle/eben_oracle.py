@@ -47,7 +47,7 @@ def pqmf_design(m: int, n: int, beta: float = 9) -> Tuple[Tensor, Tensor, float]
         keep = torch.ones(n + 1, dtype=ac.dtype)
         keep[n // 2] = 0
         phi = (ac * keep)[..., :: 2 * m].abs().max()
-        off = abs(float(cut) - 1 / (2 * m)) > 1 / (4 * m)
+        off = abs(float(cut.detach()) - 1 / (2 * m)) > 1 / (4 * m)
         return phi + (1 / (4 * m) if off else 0)
 
     cut = (torch.ones(1) / (2 * m)).requires_grad_(True)       # pqmf.py:126-138

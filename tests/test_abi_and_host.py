@@ -105,6 +105,17 @@ scale = parallel.allreduce_sum_(bucket)
 assert scale == 0.5 and torch.all(bucket == 3.0)
 assert parallel.max_over_ranks(float(rank)) == 1.0
 assert parallel.rank_seed(42, rank) == 42 + rank
+# the segmented graph replay of world_size > 1: graph, all-reduce of bucket 0, graph, all-reduce of bucket 1, graph
+from vibravox_b200.lightning_modules.eben import _SegmentedStep
+log, b0, b1 = [], torch.zeros(8), torch.zeros(4)
+class G:
+    def __init__(self, fn): self.fn = fn
+    def replay(self): self.fn()
+seg = _SegmentedStep([G(lambda: (log.append("A"), b0.fill_(rank + 1.0))),
+                      G(lambda: (log.append(("B", float(b0[0]))), b1.fill_(10.0 * (rank + 1)))),
+                      G(lambda: log.append(("C", float(b1[0]))))], [b0, b1])
+seg.replay()
+assert log == ["A", ("B", 3.0), ("C", 30.0)], log
 parallel.barrier()
 print("rank", rank, "ok")
 """
@@ -124,3 +135,76 @@ def test_data_parallel_helpers_gloo_world2(tmp_path):
         out, _ = p.communicate(timeout=120)
         assert p.returncode == 0, out
         assert "ok" in out
+
+
+def test_tensor_core_plan_pack_sizes():
+    """fill_tc on the host (no GPU): the packed-weight size tells which kernel form the geometry gets.
+    Persistent slab = one stage per 16-channel group with all K taps; densified groups = one dense conv."""
+    import ctypes
+    from vibravox_b200 import _lib, ops
+    lib = _lib.load()
+
+    def nbytes(g, mode):
+        d = ops._geom_only_desc(g)
+        return lib.vbx_tc_pack_bytes(ctypes.byref(d), mode, 2)
+
+    def up16(n):
+        return (n + 15) // 16 * 16
+
+    # generator residual conv 32 -> 32 k3 d3 reflect: persistent slab, 2 channel groups x 3 taps x NT=32 x 64 B
+    assert nbytes(ops.ConvGeom(32, 32, 3, 1, 3, 3, 3, 1), ops.TC_FWD) == 2 * 3 * 32 * 64
+    # PQMF-discriminator 24 -> 48 k7 s2 g4: densified (ONE group, 24 -> 2 channel groups, NT = 48), persistent
+    assert nbytes(ops.ConvGeom(24, 48, 7, 2, 1, 3, 0, 4), ops.TC_FWD) == 2 * 7 * 48 * 64
+    # its input gradient: merged phases -> columns 2 x 24 = 48, reduction over the 48 output channels (3 groups of 16)
+    n = nbytes(ops.ConvGeom(24, 48, 7, 2, 1, 3, 0, 4), ops.TC_DGRAD)
+    assert n > 0 and n % (3 * 48 * 64) == 0
+    # MelGAN stage 1, 16 -> 64 k41 s4 g4: densified onto the streaming slab kernel (weights too big to stay resident
+    # with two CTAs per SM): 1 channel group, taps padded to whole weight stages of 16384 / (64 * 64) = 4 taps
+    assert nbytes(ops.ConvGeom(16, 64, 41, 4, 1, 20, 0, 4), ops.TC_FWD) == 11 * 4 * 64 * 64
+    # 96 -> 192 k7 s2 g4 stays grouped (96 input channels > VBX_TC_DENSE_MAX_CIN): 4 groups x 2 channel groups, NT = 48
+    assert nbytes(ops.ConvGeom(96, 192, 7, 2, 1, 3, 0, 4), ops.TC_FWD) == 4 * 2 * 7 * up16(48) * 64
+    # wide layer: streaming slab, 4 groups x 16 channel groups x ceil(41 / 1) stages of one tap at NT = 256
+    assert nbytes(ops.ConvGeom(1024, 1024, 41, 4, 1, 20, 0, 4), ops.TC_FWD) == 4 * 16 * 41 * 256 * 64
+    # bad geometry is refused, not sized
+    assert nbytes(ops.ConvGeom(24, 50, 7, 2, 1, 3, 0, 4), ops.TC_FWD) < 0
+
+
+def test_hub_mixin_round_trip_and_reference_checkpoints(tmp_path):
+    """checkpoints in the reference's formats drop in.  save_pretrained / from_pretrained
+    (PyTorchModelHubMixin, safetensors + config.json as scripts/upload_eben_to_hub.py:13-24 of the reference
+    writes them) round-trips constructor arguments and every tensor; when the reference package is present (this
+    container, not the GPU box) its own modules' state_dicts load strictly into the drop-ins and back."""
+    pytest.importorskip("huggingface_hub")
+    from vibravox_b200.torch_modules.dnn.eben_discriminator import DiscriminatorEBENMultiScales
+    from vibravox_b200.torch_modules.dnn.eben_generator import EBENGenerator
+    torch.manual_seed(5)
+    G = EBENGenerator(m=4, n=32, p=1)
+    D = DiscriminatorEBENMultiScales(q=3, min_channels=24)
+    G.save_pretrained(tmp_path / "g")
+    D.save_pretrained(tmp_path / "d")
+    assert (tmp_path / "g" / "config.json").exists() and (tmp_path / "g" / "model.safetensors").exists()
+    G2 = EBENGenerator.from_pretrained(str(tmp_path / "g"))
+    D2 = DiscriminatorEBENMultiScales.from_pretrained(str(tmp_path / "d"))
+    assert (G2.p, G2.multiple, G2.pqmf.decimation, G2.pqmf.kernel_size) == (1, G.multiple, 4, 32)
+    for a, b in ((G, G2), (D, D2)):
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa) == list(sb)
+        assert all(torch.equal(sa[k], sb[k]) for k in sa)
+    ref_root = "/root/reference"
+    if not os.path.isdir(os.path.join(ref_root, "vibravox")):
+        return
+    sys.path.insert(0, ref_root)
+    try:
+        from vibravox.torch_modules.dnn.eben_discriminator import DiscriminatorEBENMultiScales as RefD
+        from vibravox.torch_modules.dnn.eben_generator import EBENGenerator as RefG
+    except Exception as exc:                      # a dependency of the reference is missing: nothing to cross-check
+        pytest.skip(f"reference modules not importable: {exc}")
+    finally:
+        sys.path.remove(ref_root)
+    torch.manual_seed(6)
+    rg, rd = RefG(m=4, n=32, p=1), RefD(q=3, min_channels=24)
+    assert G.load_state_dict(rg.state_dict(), strict=True).missing_keys == []
+    assert D.load_state_dict(rd.state_dict(), strict=True).missing_keys == []
+    assert all(torch.equal(v, rg.state_dict()[k]) for k, v in G.state_dict().items())
+    rg.load_state_dict(G2.state_dict(), strict=True)
+    rd.load_state_dict(D2.state_dict(), strict=True)

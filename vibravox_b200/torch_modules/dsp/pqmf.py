@@ -51,7 +51,7 @@ class PseudoQMFBanks(nn.Module):
         keep = torch.ones(n + 1, dtype=autocorr.dtype)
         keep[n // 2] = 0                                      # ignore the zero-lag peak
         worst = (autocorr * keep)[..., :: 2 * m].abs().max()
-        outside = abs(float(cutoff_ratio) - 1 / (2 * m)) > 1 / (4 * m)
+        outside = abs(float(cutoff_ratio.detach()) - 1 / (2 * m)) > 1 / (4 * m)
         return worst + (1 / (4 * m) if outside else 0)
 
     def initialize_cutoff_ratio(self) -> float:
