@@ -130,7 +130,9 @@ def main(argv=None):
     datamodule = instantiate(cfg["lightning_datamodule"])
     module = instantiate(cfg["lightning_module"])
     trainer = instantiate(cfg["trainer"])
-    trainer.fit(module, datamodule)
+    # `ckpt_path=last` (or a file) resumes parameters, both Adam states and the balancing EMA, like
+    # `trainer.fit(..., ckpt_path=...)` of Lightning; `trainer.default_root_dir=...` is where last.ckpt is written
+    trainer.fit(module, datamodule, ckpt_path=cfg.get("ckpt_path"))
     return module
 
 

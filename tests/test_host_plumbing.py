@@ -73,3 +73,76 @@ def test_training_step_schedule_matches_reference_golden(golden_dir, schedule):
     for k, v in gold["g_param_sums_after"].items():
         n = gsd[k].numel()
         assert abs(float(gsd[k].double().sum()) - v) <= 5e-3 * n ** 0.5 + 1e-3, k
+
+
+def test_flat_adam_state_dict_is_torch_adam_compatible():
+    """FlatAdam.state_dict() is the layout torch.optim.Adam writes: a torch Adam loaded from it takes the same next
+    step, and FlatAdam loaded from a torch Adam state continues that optimizer's trajectory."""
+    from vibravox_b200.optim import FlatAdam
+    torch.manual_seed(0)
+    shapes = [(5, 3, 2), (7,), (4, 1, 1)]
+    with cpu_ops():
+        ps = [torch.nn.Parameter(torch.randn(s)) for s in shapes]
+        flat = FlatAdam(ps, lr=3e-4, betas=(0.5, 0.9))
+        assert flat.state_dict()["state"] == {}                       # fresh, like torch Adam
+        grads = [[torch.randn(s) for s in shapes] for _ in range(4)]
+        for gs in grads[:3]:
+            for p, g in zip(ps, gs):
+                p.grad = g.clone()
+            flat.step(); flat.zero_grad()
+        sd = flat.state_dict()
+        assert sorted(sd["state"]) == [0, 1, 2] and float(sd["state"][0]["step"]) == 3.0
+        assert sd["param_groups"][0]["betas"] == (0.5, 0.9) and sd["param_groups"][0]["params"] == [0, 1, 2]
+        # torch Adam continues from FlatAdam's state
+        qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+        adam = torch.optim.Adam(qs, lr=3e-4, betas=(0.5, 0.9))
+        adam.load_state_dict(sd)
+        for p, q, g in zip(ps, qs, grads[3]):
+            p.grad, q.grad = g.clone(), g.clone()
+        flat.step(); adam.step()
+        for p, q in zip(ps, qs):
+            assert torch.allclose(p, q, rtol=0, atol=2e-7)
+        # FlatAdam continues from torch Adam's state (a reference checkpoint), moments copied in place
+        rs = [torch.nn.Parameter(q.detach().clone()) for q in qs]
+        flat2 = FlatAdam(rs, lr=1.0, betas=(0.9, 0.999))
+        flat2.materialize()
+        ptr = flat2.exp_avg.data_ptr()
+        flat2.load_state_dict(adam.state_dict())
+        assert flat2.exp_avg.data_ptr() == ptr and int(flat2.step_count[0]) == 4
+        assert flat2.param_groups[0]["lr"] == 3e-4 and flat2.param_groups[0]["betas"] == (0.5, 0.9)
+        g5 = [torch.randn(s) for s in shapes]
+        for q, r, g in zip(qs, rs, g5):
+            q.grad, r.grad = g.clone(), g.clone()
+        adam.step(); flat2.step()
+        for q, r in zip(qs, rs):
+            assert torch.allclose(q, r, rtol=0, atol=2e-7)
+        with pytest.raises(ValueError):
+            flat2.load_state_dict(torch.optim.Adam(qs[:2]).state_dict())
+
+
+def test_run_py_trainer_checkpoint_resume(tmp_path):
+    """run.py's override grammar -> Trainer.fit -> last.ckpt -> `ckpt_path=last`: three steps in one go and two steps
+    + resume + one step end on the same parameters, Adam moments and balancing state."""
+    import run
+    common = ["lightning_datamodule=bwe", "lightning_module=eben", "lightning_datamodule.batch_size=1",
+              "lightning_datamodule.collate_strategy=constant_length-250-ms", "lightning_module.generator.p=1",
+              "lightning_module.discriminator.q=3", "++trainer.accelerator=cpu", "++trainer.log_every_n_steps=1000"]
+    with cpu_ops():
+        a = run.main(common + ["++trainer.max_steps=3", f"++trainer.default_root_dir={tmp_path}/a"])
+        run.main(common + ["++trainer.max_steps=2", f"++trainer.default_root_dir={tmp_path}/b"])
+        ck = torch.load(tmp_path / "b" / "checkpoints" / "last.ckpt", weights_only=False)
+        assert ck["global_step"] == 2 and len(ck["optimizer_states"]) == 2 and "vbx_balancing" in ck
+        assert any(k.endswith("parametrizations.weight.original0") for k in ck["state_dict"])
+        assert float(ck["optimizer_states"][0]["state"][0]["step"]) == 2.0
+        b = run.main(common + ["++trainer.max_steps=3", f"++trainer.default_root_dir={tmp_path}/b", "+ckpt_path=last"])
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa) == list(sb)
+    for k in sa:
+        assert torch.allclose(sa[k], sb[k], rtol=0, atol=1e-6), k
+    for oa, ob in zip(a.configure_optimizers(), b.configure_optimizers()):
+        assert int(oa.step_count[0]) == int(ob.step_count[0]) == 3
+        assert torch.allclose(oa.exp_avg, ob.exp_avg, rtol=0, atol=1e-7)
+        assert torch.allclose(oa.exp_avg_sq, ob.exp_avg_sq, rtol=0, atol=1e-9)
+    assert torch.allclose(a.atomic_norms_old, b.atomic_norms_old, rtol=1e-6)
+    for k in a.logged:
+        assert float(a.logged[k]) == pytest.approx(float(b.logged[k]), rel=1e-5), k

@@ -39,8 +39,10 @@ class SyntheticBWEDataModule:
         while True:
             air = (0.1 * torch.randn(self.batch_size, 1, self.samples, generator=g)).clamp(-1, 1)
             body = (0.1 * torch.randn(self.batch_size, 1, self.samples, generator=g)).clamp(-1, 1)
-            yield {"audio_body_conducted": body.pin_memory().to(device, non_blocking=True),
-                   "audio_airborne": air.pin_memory().to(device, non_blocking=True)}
+            if torch.device(device).type == "cuda":
+                body, air = body.pin_memory(), air.pin_memory()
+            yield {"audio_body_conducted": body.to(device, non_blocking=True),
+                   "audio_airborne": air.to(device, non_blocking=True)}
 
 
 class SyntheticNoisyBWEDataModule(SyntheticBWEDataModule):

@@ -488,6 +488,42 @@ class EBENLightningModule(torch.nn.Module):
         self.last_norms, self.last_lambdas = norms, lambdas
         return lambdas
 
+    # ---- checkpoint / resume ----------------------------------------------------
+    def checkpoint(self, global_step: int = 0, epoch: int = 0) -> dict:
+        """The keys a Lightning checkpoint of the reference module carries (`state_dict` with `generator.` /
+        `discriminator.` prefixes, `optimizer_states` in `configure_optimizers()` order, `global_step`, `epoch`), plus
+        the EMA of the balancing norms, which the reference keeps as a plain attribute and therefore loses on resume."""
+        ckpt = {"state_dict": {k: v.detach().clone() for k, v in self.state_dict().items()},
+                "optimizer_states": [o.state_dict() for o in self.configure_optimizers()],
+                "global_step": int(global_step), "epoch": int(epoch)}
+        if self._bal is not None:
+            ckpt["vbx_balancing"] = {k: v.detach().clone() for k, v in self._bal.items()}
+        return ckpt
+
+    def load_checkpoint(self, ckpt: dict, strict: bool = True) -> int:
+        """Restore from `checkpoint()` or from a Lightning checkpoint of the reference's EBENLightningModule (same
+        parameter names; its `torch.optim.Adam` states load into FlatAdam).  Parameters are copied in place, so
+        captured graphs and the flat buckets stay valid.  Returns the stored global step."""
+        with torch.no_grad():
+            own = self.state_dict()
+            nets = ("generator.", "discriminator.")            # loss modules only hold constants (windows, filters)
+            missing = [k for k in own if k.startswith(nets) and k not in ckpt["state_dict"]]
+            unexpected = [k for k in ckpt["state_dict"] if k.startswith(nets) and k not in own]
+            if strict and (missing or unexpected):
+                raise KeyError(f"load_checkpoint: missing {missing[:4]}, unexpected {unexpected[:4]}")
+            for k, v in ckpt["state_dict"].items():
+                if k in own:
+                    own[k].copy_(v)
+        for opt, sd in zip(self.configure_optimizers(), ckpt.get("optimizer_states", [])):
+            opt.load_state_dict(sd)
+        for mod in (self.generator, self.discriminator):      # cached effective weights / packed tiles are stale
+            for p in mod.parameters():
+                p.__dict__.pop("_vbx_packs", None)
+        bal = ckpt.get("vbx_balancing")
+        dev = self.generator.last_conv.weight.device
+        self._bal = None if bal is None else {k: v.to(dev).clone() for k, v in bal.items()}
+        return int(ckpt.get("global_step", 0))
+
     @torch.no_grad()
     def common_eval_step(self, batch: Dict[str, torch.Tensor], batch_idx: int = 0, stage: str = "validation",
                          dataloader_idx: int = 0):

@@ -85,6 +85,58 @@ class FlatAdam(torch.optim.Optimizer):
                 ops.axpby(g, slot, 1.0, 1.0)
                 p.grad = None
 
+    # ---- checkpoints: the layout torch.optim.Adam writes (what a Lightning checkpoint of the reference holds) ----
+    def state_dict(self) -> dict:
+        """`torch.optim.Adam.state_dict()` layout - per-parameter `step` / `exp_avg` / `exp_avg_sq` indexed in
+        parameter order - so optimizer states travel both ways between this class and the reference's Adam
+        (`configs/lightning_module/optimizer/adam.yaml`).  Copies, not views of the flat buckets."""
+        g = self.param_groups[0]
+        group = {k: v for k, v in g.items() if k != "params"}
+        group.update(weight_decay=0.0, amsgrad=False, params=list(range(len(self.params))))
+        state = {}
+        if self.flat is not None and int(self.step_count[0]) > 0:
+            step = self.step_count[0].to(torch.float32)
+            off = 0
+            for i, p in enumerate(self.params):
+                n = p.numel()
+                state[i] = {"step": step.clone(), "exp_avg": self.exp_avg[off:off + n].view(p.shape).clone(),
+                            "exp_avg_sq": self.exp_avg_sq[off:off + n].view(p.shape).clone()}
+                off += (n + 3) // 4 * 4
+        return {"state": state, "param_groups": [group]}
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict: dict) -> None:
+        """Accepts its own `state_dict()` or one written by `torch.optim.Adam` over the same parameters (in the same
+        order).  Moments are copied INTO the flat buckets, so a captured CUDA graph keeps pointing at live memory."""
+        groups = state_dict["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self.params):
+            raise ValueError("FlatAdam.load_state_dict: expected one parameter group over the same parameters")
+        if groups[0].get("amsgrad", False) or groups[0].get("weight_decay", 0.0) != 0.0:
+            raise NotImplementedError("FlatAdam implements the reference configuration: weight_decay=0, amsgrad=False")
+        g = self.param_groups[0]
+        for k in ("lr", "betas", "eps"):
+            if k in groups[0]:
+                g[k] = tuple(groups[0][k]) if k == "betas" else groups[0][k]
+        self.materialize()
+        state = state_dict["state"]
+        steps = {int(float(v["step"])) for v in state.values()}
+        if len(steps) > 1:
+            raise ValueError("FlatAdam keeps one step count for all parameters; the checkpoint has several")
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        self.step_count.fill_(steps.pop() if steps else 0)
+        off = 0
+        for i, p in enumerate(self.params):
+            n = p.numel()
+            st = state.get(i, state.get(str(i)))
+            if st is not None:
+                if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                    raise ValueError(f"FlatAdam.load_state_dict: parameter {i} has shape {tuple(p.shape)}, "
+                                     f"the checkpoint {tuple(st['exp_avg'].shape)}")
+                self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+                self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+            off += (n + 3) // 4 * 4
+
     @torch.no_grad()
     def step(self, closure=None):
         assert closure is None
