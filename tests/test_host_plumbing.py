@@ -146,3 +146,30 @@ def test_run_py_trainer_checkpoint_resume(tmp_path):
     assert torch.allclose(a.atomic_norms_old, b.atomic_norms_old, rtol=1e-6)
     for k in a.logged:
         assert float(a.logged[k]) == pytest.approx(float(b.logged[k]), rel=1e-5), k
+
+
+def test_eval_step_logs_the_pre_update_losses_of_a_training_step(golden_dir):
+    """common_eval_step / validation_step / test_step (eben.py:132-165, base_se.py:132-136): on a fresh model the
+    evaluation losses are the atomic losses the first training step logs before it updates anything - and those are
+    pinned to the reference by the golden training logs."""
+    import vibravox_b200
+    gold = torch.load(os.path.join(golden_dir, "train_step.pt"))
+    body, air = O.synthetic_pairs(gold["B"], gold["S"], seed=gold["data_seed"])
+    batch = {"audio_body_conducted": body, "audio_airborne": air}
+    with cpu_ops():
+        ev = vibravox_b200.build_model(seed=gold["model_seed"], device="cpu")
+        out = ev.validation_step(batch, 0)
+        assert set(out) == {"corrupted", "enhanced", "reference"} and out["enhanced"].shape == out["reference"].shape
+        assert not out["enhanced"].requires_grad
+        keys = {"generator": ("reconstructive_loss_freq", "feature_matching_loss", "adv_loss_gen"),
+                "discriminator": ("real_loss", "fake_loss")}
+        for net, names in keys.items():
+            for n in names:
+                want = gold["steps"][0]["logs"][f"{net}/{n}"]
+                assert float(ev.logged[f"validation/{net}/{n}"]) == pytest.approx(want, rel=3e-4, abs=3e-5), (net, n)
+        ev.dataloader_names = ["speech_clean", "speech_noisy"]
+        ev.logged.clear()
+        only_body = ev.test_step({"audio_body_conducted": body}, 3, dataloader_idx=1)
+        assert set(only_body) == {"corrupted", "enhanced"} and not ev.logged       # no reference: nothing to log
+        ev.test_step(batch, 0, dataloader_idx=1)
+        assert "test/generator/adv_loss_gen/speech_noisy" in ev.logged

@@ -76,6 +76,7 @@ class EBENLightningModule(torch.nn.Module):
         self.logged: Dict[str, torch.Tensor] = {}
         self._graphs: Dict[tuple, dict] = {}      # training_step_graphed: one captured step per batch shape
         self._capture = None                      # state of a segmented capture in progress (see _capture_segments)
+        self.dataloader_names = None              # base_se.py:52: names of the validation / test dataloaders, if several
         self.graph_warmup_steps = 2
 
     # ---- Lightning services, restated --------------------------------------------------------
@@ -527,6 +528,8 @@ class EBENLightningModule(torch.nn.Module):
     @torch.no_grad()
     def common_eval_step(self, batch: Dict[str, torch.Tensor], batch_idx: int = 0, stage: str = "validation",
                          dataloader_idx: int = 0):
+        """eben.py:132-165: generator forward on the (cut) body-conducted signal and, when the airborne reference is
+        in the batch, the atomic losses of both phases logged as `{stage}/{network}/{loss}[/{dataloader name}]`."""
         corrupted_speech = self.generator.cut_to_valid_length(batch["audio_body_conducted"])
         enhanced_speech, decomposed_enhanced_speech = self.generator(corrupted_speech)
         outputs = {"corrupted": corrupted_speech, "enhanced": enhanced_speech}
@@ -534,9 +537,18 @@ class EBENLightningModule(torch.nn.Module):
             reference_speech = self.generator.cut_to_valid_length(batch["audio_airborne"])
             decomposed_reference_speech = self.generator.pqmf.forward(reference_speech, "analysis")
             outputs["reference"] = reference_speech
+            names = getattr(self, "dataloader_names", None)
+            dl_name = f"/{names[dataloader_idx]}" if names else ""
             for net_type in ["generator", "discriminator"]:
                 for key, value in self.compute_atomic_losses(
                         net_type, enhanced_speech, reference_speech, decomposed_enhanced_speech,
                         decomposed_reference_speech).items():
-                    self.log(f"{stage}/{net_type}/{key}", value, sync_dist=True, add_dataloader_idx=False)
+                    self.log(f"{stage}/{net_type}/{key}{dl_name}", value, sync_dist=True, add_dataloader_idx=False)
         return outputs
+
+    # base_se.py:132-136 (the metric / audio logging of common_eval_logging is torchmetrics territory: out of scope)
+    def validation_step(self, batch, batch_idx: int = 0, dataloader_idx: int = 0):
+        return self.common_eval_step(batch, batch_idx, "validation", dataloader_idx)
+
+    def test_step(self, batch, batch_idx: int = 0, dataloader_idx: int = 0):
+        return self.common_eval_step(batch, batch_idx, "test", dataloader_idx)
