@@ -121,7 +121,6 @@ __global__ void __launch_bounds__(kThreads, 3) tc_slab_kernel(const TcP P) {
   int* tapoff = reinterpret_cast<int*>(tmem_slot + 2);        // per tap: byte offset of its view into a stage
 
   const int grp = blockIdx.y / P.ntiles_n, nt = blockIdx.y % P.ntiles_n;
-  const int Ccol = G.Cout_g;
   const int R = P.sl_R, Ppos = R * s;
   const int ncg = P.sl_ncg, nbst = P.sl_nbst, tpb = P.sl_tpb;
   const int rv0 = blockIdx.x * kRows;                          // first virtual output row of this tile
