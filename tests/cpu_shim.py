@@ -270,6 +270,15 @@ def adam_step(p, grad, m, v, step, lr, b1, b2, eps, grad_scale=1.0):
     p.addcdiv_(m, denom, value=-lr / (1 - b1 ** t))
 
 
+def noise_mix_crop(body, air, noise, start, off, length):
+    """(body + noise[start : start + Ls])[off : off + length] and air[off : off + length], per item."""
+    Ls = body.shape[-1]
+    ob = torch.stack([(body[b, 0] + noise[b, 0, int(s): int(s) + Ls])[int(o): int(o) + length]
+                      for b, (s, o) in enumerate(zip(start, off))]).unsqueeze(1)
+    oa = torch.stack([air[b, 0, int(o): int(o) + length] for b, o in enumerate(off)]).unsqueeze(1)
+    return ob, oa
+
+
 def require_cuda(device):
     return None
 

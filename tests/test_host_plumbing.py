@@ -173,3 +173,28 @@ def test_eval_step_logs_the_pre_update_losses_of_a_training_step(golden_dir):
         assert set(only_body) == {"corrupted", "enhanced"} and not ev.logged       # no reference: nothing to log
         ev.test_step(batch, 0, dataloader_idx=1)
         assert "test/generator/adv_loss_gen/speech_noisy" in ev.logged
+
+
+def test_run_py_noisy_bwe_datamodule_steps():
+    """BASELINE config 4 through run.py: the noisy-BWE datamodule (noise mix + joint crop on the device, here the
+    host stand-in of vbx_noise_mix_crop) feeds the same training step; batches are (B, 1, samples) pairs, differ
+    from step to step, and the losses stay finite."""
+    import run
+    from vibravox_b200.data import SyntheticNoisyBWEDataModule
+    with cpu_ops():
+        dm = SyntheticNoisyBWEDataModule(sample_rate=16000, batch_size=2, collate_strategy="constant_length-250-ms",
+                                         noise_seconds=1.0, seed=3)
+        it = dm.batches(torch.device("cpu"), rank=0)
+        b0, b1 = next(it), next(it)
+        assert b0["audio_body_conducted"].shape == b0["audio_airborne"].shape == (2, 1, 4000)
+        assert not torch.equal(b0["audio_body_conducted"], b1["audio_body_conducted"])
+        other = next(SyntheticNoisyBWEDataModule(sample_rate=16000, batch_size=2, noise_seconds=1.0, seed=3,
+                                                 collate_strategy="constant_length-250-ms").batches("cpu", rank=1))
+        assert not torch.equal(other["audio_airborne"], b0["audio_airborne"])        # each rank draws its own stream
+        lm = run.main(["lightning_datamodule=noisybwe", "lightning_module=eben", "lightning_datamodule.batch_size=1",
+                       "lightning_datamodule.collate_strategy=constant_length-250-ms",
+                       "lightning_datamodule.noise_seconds=1", "lightning_module.generator.p=1",
+                       "lightning_module.discriminator.q=3", "++trainer.accelerator=cpu", "++trainer.max_steps=2",
+                       "++trainer.log_every_n_steps=1000"])
+    assert int(lm.generator_optimizer.step_count[0]) == 2
+    assert all(torch.isfinite(v).all() for v in lm.logged.values()) and len(lm.logged) == 7
