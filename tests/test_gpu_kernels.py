@@ -412,3 +412,31 @@ def test_flat_adam_update_invalidates_packed_weight_tiles():
     want = F.conv1d(x.double(), conv.weight.detach().double(), None, 1, 1)
     assert (y1.double() - want).abs().max() < 1e-4 * float(want.abs().max())
     assert (y1 - y0).abs().max() > 1e-2
+
+
+PERSISTENT_CASES = [
+    (12, 32, 32, 11968, 3, 1, 3, 3, 3, 1),     # generator residual conv: 1123 row tiles on 444 persistent CTAs
+    (20, 24, 48, 11970, 7, 2, 1, 3, 0, 4),     # PQMF-discriminator stage 1, groups densified: 936 tiles on 296 CTAs
+]
+
+
+@pytest.mark.parametrize("case", PERSISTENT_CASES, ids=[str(c) for c in PERSISTENT_CASES])
+def test_persistent_slab_many_tiles_per_cta_matches_fma(case):
+    """tc_pslab_kernel at sizes where every CTA walks two to three row tiles (both TMEM accumulator buffers reused,
+    the slab ring wrapped): forward with bias + LeakyReLU and the input gradient against the fp32 FMA kernels of
+    the same library on the same device tensors (the small TC_CASES give each persistent CTA a single tile)."""
+    from vibravox_b200 import ops
+    B, Cin, Cout, Tin, K, s, d, pad, refl, groups = case
+    g = ops.ConvGeom(Cin, Cout, K, s, d, pad, refl, groups)
+    To = g.tout(Tin)
+    torch.manual_seed(0)
+    x = torch.randn(B, Cin, Tin, device=DEV)
+    dy = torch.randn(B, Cout, To, device=DEV)
+    w = torch.randn(Cout, Cin // groups, K, device=DEV) / (Cin // groups * K) ** 0.5
+    bias = torch.randn(Cout, device=DEV)
+    y = ops.tc_conv1d_fwd(x, ops.tc_pack(w, g, ops.TC_FWD), g, bias=bias, slope=0.2)
+    y0 = ops.conv1d_fwd(x, w, g, bias=bias, slope=0.2)
+    assert float((y - y0).norm() / y0.norm()) < 2e-5
+    dx = ops.tc_conv1d_dgrad(dy, ops.tc_pack(w, g, ops.TC_DGRAD), g, Tin)
+    dx0 = ops.conv1d_dgrad(dy, ops.transpose_weight(w, groups), g, Tin)
+    assert float((dx - dx0).norm() / dx0.norm()) < 2e-5
