@@ -101,17 +101,36 @@ def _ref_collate(U, batch, sample_rate, strategy, deterministic, noisy):
     return (torch.stack([p[0].unsqueeze(0) for p in pairs]), torch.stack([p[1].unsqueeze(0) for p in pairs]))
 
 
+def _ref_aug(**kw):
+    sys.path.insert(0, REF)
+    try:
+        from vibravox.torch_modules.dsp.data_augmentation import WaveformDataAugmentation
+    finally:
+        sys.path.remove(REF)
+    return WaveformDataAugmentation(16000, **kw)
+
+
 @pytest.mark.parametrize("noisy", [False, True])
 @pytest.mark.parametrize("strategy", ["pad", "constant_length-250-ms"])
 @pytest.mark.parametrize("deterministic", [True, False])
 def test_collators_match_the_reference(ref_utils, noisy, strategy, deterministic):
     batch = items(5, 2500, 6000, noise=12000 if noisy else None, seed=7)       # target 4000: some crop, some pad
-    torch.manual_seed(21)
-    wb, wa = _ref_collate(ref_utils, batch, 16000, strategy, deterministic, noisy)
-    torch.manual_seed(21)
-    got = (C.noisybwe_collate if noisy else C.bwe_collate)(batch, 16000, strategy, deterministic)
-    assert got["audio_body_conducted"].shape == wb.shape and wb.dim() == 3 and wb.shape[1] == 1
-    assert torch.equal(got["audio_body_conducted"], wb) and torch.equal(got["audio_airborne"], wa)
+    from vibravox_b200.torch_modules.dsp.data_augmentation import WaveformDataAugmentation
+    for aug in ({}, dict(p_data_augmentation=1, p_speed_perturbation=0, p_pitch_shift=0, p_time_masking=1)):
+        torch.manual_seed(21)
+        wb, wa = _ref_collate(ref_utils, batch, 16000, strategy, deterministic, noisy)
+        if deterministic is False:
+            with torch.no_grad():
+                wb, wa = _ref_aug(**aug)(wb, wa)
+        w_next = torch.rand(1)                               # the generator must be left in the same state
+        torch.manual_seed(21)
+        got = (C.noisybwe_collate if noisy else C.bwe_collate)(
+            batch, 16000, strategy, deterministic, data_augmentation=WaveformDataAugmentation(16000, **aug) if aug else None)
+        assert torch.equal(torch.rand(1), w_next)
+        assert got["audio_body_conducted"].shape == wb.shape and wb.dim() == 3 and wb.shape[1] == 1
+        assert torch.equal(got["audio_body_conducted"], wb) and torch.equal(got["audio_airborne"], wa)
+        if aug and deterministic is False:
+            assert (wb == 0).all(dim=1).any()                # the masked block is really there
 
 
 def test_noisy_collate_without_reference_signal_only_pads():
@@ -148,3 +167,20 @@ def test_fused_device_path_takes_the_same_draws(monkeypatch):
     assert len(calls) == 1 and len(calls[0][0]) == 4
     assert torch.equal(got["audio_body_conducted"], want["audio_body_conducted"])
     assert torch.equal(got["audio_airborne"], want["audio_airborne"])
+
+
+@pytest.mark.parametrize("aug", [dict(p_speed_perturbation=1, p_pitch_shift=0, p_time_masking=0),
+                                 dict(p_speed_perturbation=0, p_pitch_shift=1, p_time_masking=1)], ids=str)
+def test_waveform_data_augmentation_matches_the_reference(ref_utils, aug):
+    """Same draws, same torchaudio transforms, same in-place time mask as the reference module."""
+    pytest.importorskip("torchaudio")
+    from vibravox_b200.torch_modules.dsp.data_augmentation import WaveformDataAugmentation
+    torch.manual_seed(4)
+    a, b = torch.randn(2, 1, 4000), torch.randn(2, 1, 4000)
+    torch.manual_seed(8)
+    wa, wb = _ref_aug(p_data_augmentation=1, **aug)(a.clone(), b.clone())
+    torch.manual_seed(8)
+    ga, gb = WaveformDataAugmentation(16000, p_data_augmentation=1, **aug)(a.clone(), b.clone())
+    assert ga.shape == wa.shape and torch.equal(ga, wa) and torch.equal(gb, wb)
+    with pytest.raises(AssertionError):
+        WaveformDataAugmentation(16000, p_pitch_shift=1.5)

@@ -10,8 +10,8 @@ Design: the random decisions are taken first (`plan_*`: a few host integers per 
 `torch.randint` calls in the reference's order), the samples are moved second.  When every item of a noisy-BWE
 batch has the same length, lives on the GPU and is at least as long as the target, the move is ONE launch of
 `vbx_noise_mix_crop` (mix + joint crop fused, `ops.noise_mix_crop`); otherwise plain slicing / padding on
-whatever device the items live on (the reference does this in CPU dataloader workers).  Data augmentation
-(torchaudio speed / pitch) is outside this path and left to the caller.
+whatever device the items live on (the reference does this in CPU dataloader workers).  The augmentation hook is
+`torch_modules/dsp/data_augmentation.WaveformDataAugmentation` (same draws; a no-op at its default probability 0).
 """
 from __future__ import annotations
 
@@ -124,21 +124,35 @@ def _constant_length(body: List[torch.Tensor], air: List[torch.Tensor], samples:
     return torch.stack(outs_b, dim=0), torch.stack(outs_a, dim=0)
 
 
+def _augment(body: torch.Tensor, air: torch.Tensor, deterministic: bool, data_augmentation, sample_rate: int):
+    """`if deterministic is False: with torch.no_grad(): data_augmentation(body, air)` (`bwe.py:282-287`).  The default
+    hook is the reference's default `WaveformDataAugmentation(sample_rate)`: a no-op that still draws one `rand(1)`."""
+    if deterministic is not False:
+        return body, air
+    if data_augmentation is None:
+        from .torch_modules.dsp.data_augmentation import WaveformDataAugmentation
+        data_augmentation = WaveformDataAugmentation(sample_rate)
+    with torch.no_grad():
+        return data_augmentation(body, air)
+
+
 def bwe_collate(batch: Sequence[dict], sample_rate: int = 16000, collate_strategy: str = "constant_length-3000-ms",
-                deterministic: bool = False) -> Dict[str, torch.Tensor]:
-    """`BWELightningDataModule.data_collator` (`bwe.py:232-293`) without the augmentation hook: items carry
-    'audio_body_conducted' / 'audio_airborne' as 1-D tensors (or HF `{"array": tensor}` dicts); returns the
-    (B, 1, samples) pair the training step consumes."""
+                deterministic: bool = False, data_augmentation=None) -> Dict[str, torch.Tensor]:
+    """`BWELightningDataModule.data_collator` (`bwe.py:232-293`): items carry 'audio_body_conducted' /
+    'audio_airborne' as 1-D tensors (or HF `{"array": tensor}` dicts); returns the (B, 1, samples) pair the training
+    step consumes.  `data_augmentation` is the datamodule's hook (`bwe.py:32,75-81`), applied when not deterministic."""
     body, air = _arrays(batch, "audio_body_conducted"), _arrays(batch, "audio_airborne")
     if collate_strategy == "pad":
-        return {"audio_body_conducted": _pad_batch(body), "audio_airborne": _pad_batch(air)}
-    b, a = _constant_length(body, air, _target_samples(collate_strategy, sample_rate), deterministic)
+        b, a = _pad_batch(body), _pad_batch(air)
+    else:
+        b, a = _constant_length(body, air, _target_samples(collate_strategy, sample_rate), deterministic)
+    b, a = _augment(b, a, deterministic, data_augmentation, sample_rate)
     return {"audio_body_conducted": b, "audio_airborne": a}
 
 
 def noisybwe_collate(batch: Sequence[dict], sample_rate: int = 16000,
-                     collate_strategy: str = "constant_length-3000-ms", deterministic: bool = False
-                     ) -> Dict[str, torch.Tensor]:
+                     collate_strategy: str = "constant_length-3000-ms", deterministic: bool = False,
+                     data_augmentation=None) -> Dict[str, torch.Tensor]:
     """`NoisyBWELightningDataModule.data_collator` (`noisybwe.py:225-300`): real noisy recordings (no airborne
     reference) are padded; otherwise body-conducted speech + a random segment of the speech-free noise recording,
     then the joint crop / pad of (corrupted, airborne)."""
@@ -161,9 +175,12 @@ def noisybwe_collate(batch: Sequence[dict], sample_rate: int = 16000,
                                     torch.stack(noise).unsqueeze(1),
                                     torch.tensor(starts, dtype=torch.int32, device=dev),
                                     torch.tensor(offs, dtype=torch.int32, device=dev), samples)
+        ob, oa = _augment(ob, oa, deterministic, data_augmentation, sample_rate)
         return {"audio_body_conducted": ob, "audio_airborne": oa}
     corrupted, _ = mix_speech_and_noise_without_rescaling(body, noise)
     if samples is None:
-        return {"audio_body_conducted": _pad_batch(corrupted), "audio_airborne": _pad_batch(air)}
-    b, a = _constant_length(corrupted, air, samples, deterministic)
+        b, a = _pad_batch(corrupted), _pad_batch(air)
+    else:
+        b, a = _constant_length(corrupted, air, samples, deterministic)
+    b, a = _augment(b, a, deterministic, data_augmentation, sample_rate)
     return {"audio_body_conducted": b, "audio_airborne": a}
