@@ -43,6 +43,7 @@ CASES = [  # B, Cin, Cout, Tin, K, dil, pad, refl, groups, aligned
     (2, 32, 32, 301, 3, 1, 1, 1, 1, True),       # length not a multiple of 4: every group takes the per-sample path
     (2, 16, 16, 260, 7, 1, 3, 3, 1, False),      # unaligned base pointer
     (1, 24, 8, 64, 3, 1, 1, 0, 1, True),         # shorter than one tile
+    (2, 32, 32, 256, 1, 1, 0, 0, 1, True),       # pointwise (K = 1): every group aligned, no halo at all
 ]
 
 

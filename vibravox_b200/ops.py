@@ -435,6 +435,13 @@ TC_FWD, TC_DGRAD = 0, 1
 STFT_VIA_FRAMES = os.environ.get("VBX_STFT_VIA_FRAMES", "1" if TC_ENABLED else "0") == "1"
 
 
+# Experiment knob (default 0 = off): weight gradients whose (input channels per group x taps) is at most this run on
+# the fp32 FMA split-K kernel instead of the gather-form tensor-core one.  The narrow pointwise weight gradients
+# sit at 4-8x their HBM roofline on the tensor-core kernel (M = Cout padded to 128 rows) while their FMA time is
+# within reach of it (profiles/r1_layer_roofline_table.md).
+WGRAD_FMA_MAX_CK = int(os.environ.get("VBX_WGRAD_FMA_MAX_CK", "0"))
+
+
 def use_tc(g: ConvGeom, kind: str) -> bool:
     if not TC_ENABLED or g.stride > 8:
         return False
@@ -445,6 +452,8 @@ def use_tc(g: ConvGeom, kind: str) -> bool:
         return cout_g >= 8 or cin_g * g.K >= 512      # incl. the 1-channel certainty convs (K*Cin = 2-3k)
     if kind == "dgrad":
         return cin_g >= 4
+    if cin_g * g.K <= WGRAD_FMA_MAX_CK:
+        return False
     return cout_g >= 4 and cin_g * g.K >= 3           # wgrad
 
 
