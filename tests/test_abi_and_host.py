@@ -208,3 +208,30 @@ def test_hub_mixin_round_trip_and_reference_checkpoints(tmp_path):
     assert all(torch.equal(v, rg.state_dict()[k]) for k, v in G.state_dict().items())
     rg.load_state_dict(G2.state_dict(), strict=True)
     rd.load_state_dict(D2.state_dict(), strict=True)
+
+
+def test_run_py_override_grammar():
+    """run.py restates the slice of Hydra the reference's CLI uses (README.md:60-67 of the reference):
+    `group=choice`, nested `group@package` defaults, `a.b.c=value`, `+new=value`, `++force=value`, `${...}`
+    interpolation, `_target_` / `_partial_` / `_args_` instantiation, OmegaConf's reading of `3e-4` as a float."""
+    import functools
+    import run
+    cfg = run.compose(["lightning_datamodule=noisybwe", "lightning_module=eben", "lightning_module.generator.p=4",
+                       "lightning_datamodule.batch_size=8", "++trainer.max_steps=7", "+ckpt_path=last",
+                       "sample_rate=8000", "lightning_module.generator_optimizer.lr=1e-3"])
+    assert cfg["lightning_datamodule"]["_target_"].endswith("SyntheticNoisyBWEDataModule")
+    assert cfg["lightning_datamodule"]["batch_size"] == 8 and cfg["lightning_datamodule"]["sample_rate"] == 8000
+    assert cfg["lightning_module"]["sample_rate"] == 8000                       # ${sample_rate} follows the override
+    assert cfg["lightning_module"]["generator"]["p"] == 4 and cfg["lightning_module"]["generator"]["m"] == 4
+    assert cfg["lightning_module"]["discriminator"]["_target_"].endswith("DiscriminatorEBENMultiScales")
+    assert cfg["lightning_module"]["generator_optimizer"]["lr"] == 1e-3
+    assert cfg["lightning_module"]["discriminator_optimizer"]["lr"] == 3e-4     # "3e-4" in YAML 1.1 is a string
+    assert cfg["trainer"]["max_steps"] == 7 and cfg["ckpt_path"] == "last"
+    opt = run.instantiate(cfg["lightning_module"]["discriminator_optimizer"])
+    assert isinstance(opt, functools.partial) and opt.keywords["betas"] == (0.5, 0.9) and opt.keywords["lr"] == 3e-4
+    stft = run.instantiate(cfg["lightning_module"]["reconstructive_loss_freq_fn"])
+    assert tuple(stft.fft_sizes) == (512, 1024, 2048) and tuple(stft.hop_sizes) == (50, 120, 240)
+    with pytest.raises(SystemExit):
+        run.compose(["lightning_module=eben"])                                  # the datamodule group is mandatory
+    with pytest.raises(SystemExit):
+        run.compose(["lightning_datamodule=bwe", "lightning_module=eben", "nonsense"])
