@@ -5,7 +5,9 @@
 // (profiles/r1_ncu_full_pslab_kernel.csv) shows a load-latency chain with lg_throttle stalls; this form issues a
 // quarter of the load instructions and has twice the bytes in flight per thread.  Known cost: the 16-byte slab
 // stores of a quarter-warp fall on two bank groups (4-way conflict); rotate the sample order per lane if it shows.
-// Not yet run on a GPU - the round's GPU budget was spent when it was written.
+// Not yet run on a GPU - the round's GPU budget was spent when it was written.  It is a copy of tc_pslab_kernel with
+// the staging lambda and the per-tile descriptor shift replaced; once measured, fold the two into one kernel
+// templated on the staging (or drop this file).
 #pragma once
 // (ps_vec_stage.h is included by tc_conv.cu at file scope: this header sits inside namespace vbx::tc)
 
