@@ -33,6 +33,26 @@ def synthetic_pairs(batch: int, samples: int, seed: int):
     return body, air
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """Multi-rank runs: keep stdout for the ONE JSON line.  Libraries write banners to fd 1 (NCCL prints
+    "NCCL version ..." there when the box sets NCCL_DEBUG), so fd 1 is pointed at stderr for the life of the
+    process and the original stdout is kept aside for `emit`."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -143,6 +163,8 @@ def run_ours(args):
     from vibravox_b200 import _lib, parallel
     import vibravox_b200
 
+    if parallel.env_world()[2] > 1:
+        claim_stdout()
     rank, local_rank, world = parallel.init_from_env("nccl")
     if world != args.gpus:
         assert world == 1 and args.gpus == 1, f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks"
@@ -183,7 +205,7 @@ def run_ours(args):
         t_dev, _ = timed(step, args.steps)
         torch.cuda.cudart().cudaProfilerStop()
         if rank == 0:
-            print(json.dumps({"profile_run": True, "ms_per_step": t_dev / args.steps * 1e3}))
+            emit({"profile_run": True, "ms_per_step": t_dev / args.steps * 1e3})
         return
     n_warm = max(args.warmup, 3) + (3 if graphed else 0)   # graph mode: 2 eager calls + the capture come first
     for _ in range(n_warm):
@@ -251,7 +273,7 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, bounded=True)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def _shutdown():
@@ -299,7 +321,7 @@ def run_reference(args):
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():

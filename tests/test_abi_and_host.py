@@ -235,3 +235,29 @@ def test_run_py_override_grammar():
         run.compose(["lightning_module=eben"])                                  # the datamodule group is mandatory
     with pytest.raises(SystemExit):
         run.compose(["lightning_datamodule=bwe", "lightning_module=eben", "nonsense"])
+
+
+def test_bench_keeps_stdout_for_the_one_json_line(tmp_path):
+    """Multi-rank bench runs point fd 1 at stderr (library banners such as NCCL's go there) and write the JSON line
+    to the saved stdout; the reference arm (CPU) prints exactly one parseable line."""
+    import json
+    script = tmp_path / "t.py"
+    script.write_text(
+        "import sys, os, ctypes\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import bench\n"
+        "bench.claim_stdout()\n"
+        "os.write(1, b'raw fd1 noise\\n')\n"
+        "ctypes.CDLL(None).puts(b'C stdio banner'); ctypes.CDLL(None).fflush(None)\n"
+        "print('python noise')\n"
+        "bench.emit({'metric': 'x', 'value': 1.5})\n")
+    p = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr
+    assert json.loads(p.stdout) == {"metric": "x", "value": 1.5}
+    assert "C stdio banner" in p.stderr and "python noise" in p.stderr and "raw fd1 noise" in p.stderr
+    q = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--cpu-batch", "1",
+                        "--seconds", "0.5", "--cpu-steps", "1"], capture_output=True, text=True, timeout=600)
+    assert q.returncode == 0, q.stderr
+    line = json.loads(q.stdout)
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["unit"] == "audio-s/s"
