@@ -110,11 +110,16 @@ class DiscriminatorEBENMultiScales(nn.Module, PyTorchModelHubMixin):
         cache = self.__dict__.setdefault("_vbx_streams", {})
         pool = cache.setdefault(device, [])
         while len(pool) < n:
-            pool.append(torch.cuda.Stream(device=device))
+            # experiment knob (off by default): the MelGAN chain carries 75 % of the discriminator MACs and is the
+            # last of the four to be enqueued; a high-priority stream lets its kernels take SMs first while the three
+            # PQMF-band chains fill the gaps (critical-path-first)
+            prio = -1 if (_MELGAN_PRIORITY and len(pool) == n - 1) else 0
+            pool.append(torch.cuda.Stream(device=device, priority=prio))
         return pool
 
 
 _SIDE_STREAMS = os.environ.get("VBX_D_STREAMS", "1") != "0"
+_MELGAN_PRIORITY = os.environ.get("VBX_D_PRIORITY", "0") == "1"
 if _SIDE_STREAMS and hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
     # leaves created on the caller's stream (detached generator outputs) receive gradients from side streams
     torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
