@@ -198,3 +198,42 @@ def test_run_py_noisy_bwe_datamodule_steps():
                        "++trainer.log_every_n_steps=1000"])
     assert int(lm.generator_optimizer.step_count[0]) == 2
     assert all(torch.isfinite(v).all() for v in lm.logged.values()) and len(lm.logged) == 7
+
+
+def test_graph_mode_decision_table(monkeypatch):
+    """Which launch form training_step_graphed picks: one graph on a single GPU, three graphs split at the gradient
+    all-reduces under NCCL data parallelism (the default for world_size > 1), eager launches whenever the step
+    takes a per-step decision on the host or the optimizer is not FlatAdam."""
+    import vibravox_b200
+    with cpu_ops():
+        lm = vibravox_b200.build_model(seed=1, device="cpu")
+    for k in ("VBX_GRAPH_SEGMENTS", "VBX_GRAPH_DDP"):
+        monkeypatch.delenv(k, raising=False)
+    assert lm.graph_mode() == "whole" and lm.graph_capturable()
+    monkeypatch.setenv("VBX_GRAPH_SEGMENTS", "1")
+    assert lm.graph_mode() == "segments"
+    monkeypatch.delenv("VBX_GRAPH_SEGMENTS")
+    # world_size 2 over NCCL
+    import torch.distributed as dist
+    monkeypatch.setattr(dist, "is_initialized", lambda: True)
+    monkeypatch.setattr(dist, "get_world_size", lambda *a, **k: 2)
+    monkeypatch.setattr(dist, "get_backend", lambda *a, **k: "nccl")
+    assert lm.graph_mode() == "segments"
+    monkeypatch.setenv("VBX_GRAPH_SEGMENTS", "0")
+    assert lm.graph_mode() == "eager" and not lm.graph_capturable()
+    monkeypatch.delenv("VBX_GRAPH_SEGMENTS")
+    monkeypatch.setenv("VBX_GRAPH_DDP", "1")
+    assert lm.graph_mode() == "whole"
+    monkeypatch.delenv("VBX_GRAPH_DDP")
+    monkeypatch.setattr(dist, "get_backend", lambda *a, **k: "gloo")
+    assert lm.graph_mode() == "eager"
+    monkeypatch.setattr(dist, "get_backend", lambda *a, **k: "nccl")
+    # host-side decisions
+    lm.update_discriminator_ratio = 0.5
+    assert lm.graph_mode() == "eager"
+    lm.update_discriminator_ratio = 1.0
+    lm._graph_failed = True
+    assert lm.graph_mode() == "eager"
+    lm._graph_failed = False
+    lm.generator_optimizer = torch.optim.Adam(lm.generator.parameters(), lr=3e-4)
+    assert lm.graph_mode() == "eager"
