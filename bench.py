@@ -283,8 +283,10 @@ def _shutdown():
         dist.destroy_process_group()
 
 
-def cpu_baseline(args, bounded: bool):
-    """The oracle port of the reference path on the host cores (kind 'port'), bounded sample."""
+def cpu_baseline(args, steps: int, warmup: int = 1, budget_s: float = 1e9):
+    """The oracle port of the reference path on the host cores (kind 'port'): the SAME workload as the GPU arm
+    (batch, length, seeds), all host threads.  `steps` timed steps after `warmup` untimed ones; when the first
+    warm-up step shows that the run would not fit `budget_s`, fewer timed steps are taken and the line says so."""
     import torch
     from oracle import eben_oracle as O
     cores = os.cpu_count() or 1
@@ -292,17 +294,98 @@ def cpu_baseline(args, bounded: bool):
     B = args.cpu_batch
     S = int(args.seconds * SR)
     body, air = synthetic_pairs(B, S, 42)
+    if args.workload == "noisybwe":
+        body, air = noisy_batch_host(B, S, 42)
     step = O.OracleEBENStep(seed=42)
-    step.step(body, air)                                  # warm-up (allocator, oneDNN primitives)
-    k = args.cpu_steps
     t0 = time.perf_counter()
+    step.step(body, air)                                  # warm-up (allocator, oneDNN primitives)
+    first = time.perf_counter() - t0
+    for _ in range(max(warmup, 1) - 1):
+        if (time.perf_counter() - t0) + first * (steps + 1) > budget_s:
+            break
+        step.step(body, air)
+    k = steps
+    left = budget_s - (time.perf_counter() - t0)
+    if first * k > left:
+        k = max(1, int(left / first))
+    t1 = time.perf_counter()
     for _ in range(k):
         step.step(body, air)
-    dt = (time.perf_counter() - t0) / k
+    dt = (time.perf_counter() - t1) / k
     L = S - (S + 32) % 256
     return {"value": B * L / SR / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
-            "s_per_step": dt, "sample": f"{k} timed steps (+1 warm-up) of the same train step at bs={B}x{args.seconds:g}s, "
-                                        f"fp32, torch CPU ({cores} threads)"}
+            "s_per_step": dt, "steps": k, "batch": B,
+            "sample": f"{k} timed steps (+{max(warmup, 1)} warm-up) of the same train step at bs={B}x{args.seconds:g}s "
+                      f"({args.workload}), fp32, torch CPU ({cores} threads)"}
+
+
+def noisy_batch_host(B: int, S: int, seed: int):
+    """Config 4 on the host (the CPU arm's input): the same draws and arithmetic as `NoisyFeeder` below - speech +
+    noise[start:start+len] (no rescaling), then the joint crop - restated with slicing (vibravox/utils.py:195-254,50-81)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    Ls, Ln = S + S // 4, 4 * S
+    air = (0.1 * torch.randn(B, 1, Ls, generator=g)).clamp(-1, 1)
+    body = (0.1 * torch.randn(B, 1, Ls, generator=g)).clamp(-1, 1)
+    noise = 0.05 * torch.randn(B, 1, Ln, generator=g)
+    start = torch.randint(0, Ln - Ls, (B,), generator=g)
+    off = torch.randint(0, Ls - S + 1, (B,), generator=g)
+    ob = torch.stack([(body[i, :, :] + noise[i, :, start[i]:start[i] + Ls])[:, off[i]:off[i] + S] for i in range(B)])
+    oa = torch.stack([air[i, :, off[i]:off[i] + S] for i in range(B)])
+    return ob, oa
+
+
+def gpu_eager_baseline(args, device, steps: int = 5, warmup: int = 2):
+    """SURVEY 2.3 / 8(d) bar: the reference path's arithmetic as plain PyTorch eager modules on the SAME B200 through
+    ATen / cuDNN (the oracle port moved to the device; the reference enables cudnn.benchmark, run.py:67-71), once with
+    PyTorch's default TF32 convolutions (what the reference itself runs on a GPU) and once with
+    fp32_precision='ieee'.  Same batch, same step.  A reported baseline - none of this repo's kernels run here."""
+    import torch
+    from oracle import eben_oracle as O
+    B, S = args.batch, int(args.seconds * SR)
+    body, air = synthetic_pairs(B, S, 42)
+    if args.workload == "noisybwe":
+        body, air = noisy_batch_host(B, S, 42)
+    body, air = body.to(device), air.to(device)
+    L = S - (S + 32) % 256
+    out = {}
+    prev_bench = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True
+    try:
+        for mode in ("tf32", "ieee"):
+            try:
+                torch.backends.cudnn.conv.fp32_precision = mode
+                torch.backends.cuda.matmul.fp32_precision = mode
+            except Exception:
+                torch.backends.cudnn.allow_tf32 = mode == "tf32"
+                torch.backends.cuda.matmul.allow_tf32 = mode == "tf32"
+            step = O.OracleEBENStep(seed=42, device=device, host_logs=False)
+            for _ in range(warmup):
+                logs = step.step(body, air)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()
+            for _ in range(steps):
+                logs = step.step(body, air)
+            e1.record()
+            torch.cuda.synchronize()
+            wall = (time.perf_counter() - t0) / steps
+            ms = e0.elapsed_time(e1) / steps
+            out[mode] = {"step_ms": ms, "wall_ms": wall * 1e3, "value": B * L / SR / (ms * 1e-3), "unit": "audio-s/s",
+                         "loss": float(logs["generator/backprop_loss"])}
+            del step
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.benchmark = prev_bench
+        try:
+            torch.backends.cudnn.conv.fp32_precision = "tf32"
+            torch.backends.cuda.matmul.fp32_precision = "ieee"
+        except Exception:
+            pass
+    out["what"] = (f"oracle port of the reference modules + step, PyTorch eager on this GPU (ATen/cuDNN, cudnn.benchmark), "
+                   f"bs={B}x{args.seconds:g}s, {warmup} warm-up + {steps} timed steps, CUDA events")
+    return out
 
 
 def run_reference(args):

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define VBX_ABI_VERSION 2
+#define VBX_ABI_VERSION 3
 #if defined(__GNUC__)
 #define VBX_API __attribute__((visibility("default")))
 #else
@@ -55,6 +55,18 @@ VBX_API const char* vbx_last_error(void);
 VBX_API uint64_t vbx_launch_count(void);
 /* opt-in tensor-core path for dense layers (0 = fp32 FMA everywhere) */
 VBX_API int vbx_set_tensor_core_mode(int mode);
+/* Deterministic reductions (returns the previous setting).  Off (default): weight gradients split their (b,t)
+ * reduction over several CTAs and bias gradients / loss sums over several blocks, combined with fp32 / fp64
+ * atomics - fastest, but the summation order varies from launch to launch (~1e-7 relative).  On: every such
+ * reduction is walked by ONE CTA per output tile in a fixed order, so repeated runs - eager launches or a CUDA-graph
+ * replay - are bit-identical.  Meant for tests and debugging (large layers lose their split-K parallelism). */
+VBX_API int vbx_set_deterministic(int on);
+/* out[i] = scale * *p_i for up to 8 device scalars (NULL entries beyond n are ignored): packs the step's logged
+ * losses into the tail of a gradient bucket so that ONE all-reduce carries them (the reference logs with
+ * sync_dist=True, eben.py:103-124), and unpacks the rank mean afterwards. */
+VBX_API int vbx_gather_scalars(const float* p0, const float* p1, const float* p2, const float* p3, const float* p4,
+                       const float* p5, const float* p6, const float* p7, int32_t n, float scale, float* out,
+                       void* stream);
 
 /* ---- Conv1d family ------------------------------------------------------------------
  * replaces aten::conv1d / aten::reflection_pad1d / aten::leaky_relu / aten::add issued by

@@ -301,7 +301,7 @@ STFT_RESOLUTIONS = ((512, 50, 240), (1024, 120, 600), (2048, 240, 1200))   # mul
 def stft_magnitude(x: Tensor, n_fft: int, hop: int, win: int, eps: float = 1e-8) -> Tensor:
     """auraloss STFTLoss.stft: hann(win) centred in n_fft, center/reflect, onesided;
     sqrt(clamp(re^2+im^2, eps)).  x: (B, L) -> (B, bins, frames)."""
-    window = torch.hann_window(win, dtype=x.dtype)
+    window = torch.hann_window(win, dtype=x.dtype, device=x.device)
     X = torch.stft(x, n_fft, hop, win, window, return_complex=True)
     return torch.sqrt(torch.clamp(X.real ** 2 + X.imag ** 2, min=eps))
 
@@ -335,15 +335,18 @@ class OracleEBENStep:
 
     def __init__(self, m=4, n=32, p=2, q=4, min_channels=24, seed=42, dtype=torch.float32,
                  lr=3e-4, betas=(0.5, 0.9), balancing="ema", beta_ema=0.9,
-                 g_state: State = None, d_state: State = None):
+                 g_state: State = None, d_state: State = None, device="cpu", host_logs: bool = True):
         if g_state is None or d_state is None:
             torch.manual_seed(seed)
             g_state = init_generator_state(m, n, p)
             d_state = init_discriminator_state(q, min_channels)
         self.m, self.n, self.p, self.q, self.mc = m, n, p, q, min_channels
         self.dtype = dtype
-        self.g = OrderedDict((k, v.detach().clone().to(dtype)) for k, v in g_state.items())
-        self.d = OrderedDict((k, v.detach().clone().to(dtype)) for k, v in d_state.items())
+        # device != "cpu" is the "same arithmetic through ATen/cuDNN on the GPU" baseline leg of bench.py;
+        # host_logs=False keeps the logged scalars on the device (no per-loss host sync, like Lightning's self.log)
+        self.device, self.host_logs = torch.device(device), host_logs
+        self.g = OrderedDict((k, v.detach().clone().to(device=self.device, dtype=dtype)) for k, v in g_state.items())
+        self.d = OrderedDict((k, v.detach().clone().to(device=self.device, dtype=dtype)) for k, v in d_state.items())
         self.g_train = [k for k in self.g if not k.startswith("pqmf.")]   # pqmf.py:51-56
         for k in self.g_train:
             self.g[k].requires_grad_(True)
@@ -351,7 +354,7 @@ class OracleEBENStep:
             v.requires_grad_(True)
         self.opt_g = torch.optim.Adam([self.g[k] for k in self.g_train], lr=lr, betas=betas)
         self.opt_d = torch.optim.Adam(list(self.d.values()), lr=lr, betas=betas)
-        self.taps = a_weighting_fir().to(dtype)
+        self.taps = a_weighting_fir().to(device=self.device, dtype=dtype)
         self.balancing, self.beta_ema = balancing, beta_ema
         self.norms_old = None                                   # eben.py:73
         self.last = {}
@@ -386,14 +389,17 @@ class OracleEBENStep:
             self.norms_old = [self.beta_ema * o + (1 - self.beta_ema) * nw
                               for o, nw in zip(self.norms_old, norms)]
         lambdas = [torch.clamp(1 / (nm + 1e-4), min=0.0, max=1e4) for nm in self.norms_old]
-        self.last["norms"] = [float(x) for x in norms]
-        self.last["lambdas"] = [float(x) for x in lambdas]
+        self.last["norms"] = [self._log(x) for x in norms]
+        self.last["lambdas"] = [self._log(x) for x in lambdas]
         return OrderedDict((k, v * lam) for (k, v), lam in zip(losses.items(), lambdas))
+
+    def _log(self, v):
+        return float(v.detach()) if self.host_logs else v.detach()
 
     def step(self, body: Tensor, air: Tensor, keep_grads: bool = False) -> Dict[str, float]:
         logs: Dict[str, float] = {}
-        x = cut_to_valid_length(body.to(self.dtype), self.n, self.m)
-        y = cut_to_valid_length(air.to(self.dtype), self.n, self.m)
+        x = cut_to_valid_length(body.to(device=self.device, dtype=self.dtype), self.n, self.m)
+        y = cut_to_valid_length(air.to(device=self.device, dtype=self.dtype), self.n, self.m)
         # ---- generator phase (D frozen: toggle_optimizer)
         for v in self.d.values():
             v.requires_grad_(False)
@@ -401,11 +407,11 @@ class OracleEBENStep:
         ref_bands = pqmf_analysis(y, self.g["pqmf.analysis_weights"])
         losses = self.generator_losses(enhanced, y, enh_bands, ref_bands)
         for k, v in losses.items():
-            logs["generator/" + k] = float(v)
+            logs["generator/" + k] = self._log(v)
         if self.balancing is not None:
             losses = self.balance(losses)
         total = sum(losses.values())
-        logs["generator/backprop_loss"] = float(total)
+        logs["generator/backprop_loss"] = self._log(total)
         total.backward()
         if keep_grads:
             self.last["g_grads"] = {k: self.g[k].grad.detach().clone() for k in self.g_train}
@@ -418,9 +424,9 @@ class OracleEBENStep:
             self.g[k].requires_grad_(False)
         dl = self.discriminator_losses(enhanced, y, enh_bands, ref_bands)
         for k, v in dl.items():
-            logs["discriminator/" + k] = float(v)
+            logs["discriminator/" + k] = self._log(v)
         back = dl["real_loss"] + dl["fake_loss"]
-        logs["discriminator/backprop_loss"] = float(back)
+        logs["discriminator/backprop_loss"] = self._log(back)
         back.backward()
         if keep_grads:
             self.last["d_grads"] = {k: v.grad.detach().clone() for k, v in self.d.items()}

@@ -158,6 +158,16 @@ def axpby_dev(x, y, alpha, beta):
     return y
 
 
+def gather_scalars(scalars, out, scale=1.0):
+    for i, v in enumerate(scalars):
+        out[i] = scale * v.reshape(())
+    return out
+
+
+def set_deterministic(on):
+    return False
+
+
 def fill(t, value):
     return t.fill_(value)
 

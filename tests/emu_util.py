@@ -29,18 +29,6 @@ def build():
     return ctypes.CDLL(SO)
 
 
-SLAB_SO = os.path.join(HERE, "emu", "libemu_slab.so")
-SLAB_SRC = os.path.join(HERE, "emu", "emu_slab.cpp")
-
-
-def build_slab():
-    """CPU harness of the 16-byte slab staging (csrc/ps_vec_stage.h), see tests/test_emu_slab.py."""
-    deps = [SLAB_SRC] + [os.path.join(HERE, "..", "vibravox_b200", "csrc", f) for f in ("ps_vec_stage.h", "gemm_conv.cuh")]
-    if not os.path.exists(SLAB_SO) or any(os.path.getmtime(d) > os.path.getmtime(SLAB_SO) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", SLAB_SO, SLAB_SRC])
-    return ctypes.CDLL(SLAB_SO)
-
-
 _lib = None
 
 

@@ -137,6 +137,73 @@ def test_data_parallel_helpers_gloo_world2(tmp_path):
         assert "ok" in out
 
 
+_GLOO_STEP_WORKER = r"""
+import os, sys, torch
+import torch.distributed as dist
+root = sys.argv[1]
+sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "tests"))
+from cpu_shim import cpu_ops
+import vibravox_b200
+from vibravox_b200 import parallel
+from vibravox_b200.data import synthetic_pairs
+rank, local, world = parallel.init_from_env("gloo")
+torch.set_num_threads(2)
+body, air = synthetic_pairs(1, 4000, seed=100 + rank)          # every rank its own batch
+batch = {"audio_body_conducted": body, "audio_airborne": air}
+with cpu_ops():
+    twin = vibravox_b200.build_model(seed=42, device="cpu")     # rank-local values: no exchange at all
+    twin._sync_grads = lambda opt: None
+    twin.training_step(batch)
+    local_logs = {k: float(v) for k, v in twin.logged.items()}
+    lm = vibravox_b200.build_model(seed=42, device="cpu")
+    lm.training_step(batch)
+    logs = {k: float(v) for k, v in lm.logged.items()}
+assert len(logs) == 7 and set(logs) == set(local_logs)
+for k in sorted(logs):
+    t = torch.tensor([local_logs[k]], dtype=torch.float64)
+    dist.all_reduce(t)
+    mean = float(t) / world
+    assert abs(logs[k] - mean) <= 1e-6 * max(1.0, abs(mean)), (k, logs[k], mean, local_logs[k])
+# the all-reduced gradients drive identical updates on every rank; the un-exchanged twin's differ between ranks
+for mod, want_equal in ((lm, True), (twin, False)):
+    flat = mod.discriminator_optimizer.flat.double()
+    lo, hi = flat.clone(), flat.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    assert bool((hi - lo).abs().max() == 0) == want_equal, (want_equal, float((hi - lo).abs().max()))
+# start-up broadcast: a rank seeded differently is pulled onto rank 0's parameters
+with cpu_ops():
+    odd = vibravox_b200.build_model(seed=42 + rank, device="cpu")
+    for opt in odd.configure_optimizers():
+        opt.broadcast_(0)
+    flat = odd.generator_optimizer.flat.double()
+    lo, hi = flat.clone(), flat.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    assert float((hi - lo).abs().max()) == 0
+    assert torch.equal(odd.generator.first_conv.weight.data.reshape(-1), odd.generator_optimizer.flat[:odd.generator.first_conv.weight.numel()])
+parallel.barrier()
+print("rank", rank, "ok")
+"""
+
+
+def test_sync_dist_logging_and_gradient_exchange_gloo_world2(tmp_path):
+    """world_size 2 on CPU (gloo): the logged losses are the rank MEAN (sync_dist=True, eben.py:103-124 of the
+    reference) carried by the gradient buckets' all-reduce, updates are identical on both ranks, and the start-up
+    broadcast aligns ranks that were seeded differently."""
+    script = tmp_path / "w2.py"
+    script.write_text(_GLOO_STEP_WORKER)
+    port = 29250 + os.getpid() % 200
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=600)
+        assert p.returncode == 0, out[-3000:]
+        assert "ok" in out
+
+
 def test_tensor_core_plan_pack_sizes():
     """fill_tc on the host (no GPU): the packed-weight size tells which kernel form the geometry gets.
     Persistent slab = one stage per 16-channel group with all K taps; densified groups = one dense conv."""

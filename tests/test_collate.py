@@ -115,7 +115,6 @@ def _ref_aug(**kw):
 @pytest.mark.parametrize("deterministic", [True, False])
 def test_collators_match_the_reference(ref_utils, noisy, strategy, deterministic):
     batch = items(5, 2500, 6000, noise=12000 if noisy else None, seed=7)       # target 4000: some crop, some pad
-    from vibravox_b200.torch_modules.dsp.data_augmentation import WaveformDataAugmentation
     for aug in ({}, dict(p_data_augmentation=1, p_speed_perturbation=0, p_pitch_shift=0, p_time_masking=1)):
         torch.manual_seed(21)
         wb, wa = _ref_collate(ref_utils, batch, 16000, strategy, deterministic, noisy)
@@ -125,7 +124,7 @@ def test_collators_match_the_reference(ref_utils, noisy, strategy, deterministic
         w_next = torch.rand(1)                               # the generator must be left in the same state
         torch.manual_seed(21)
         got = (C.noisybwe_collate if noisy else C.bwe_collate)(
-            batch, 16000, strategy, deterministic, data_augmentation=WaveformDataAugmentation(16000, **aug) if aug else None)
+            batch, 16000, strategy, deterministic, data_augmentation=_ref_aug(**aug) if aug else None)   # the hook = the reference's object
         assert torch.equal(torch.rand(1), w_next)
         assert got["audio_body_conducted"].shape == wb.shape and wb.dim() == 3 and wb.shape[1] == 1
         assert torch.equal(got["audio_body_conducted"], wb) and torch.equal(got["audio_airborne"], wa)
@@ -167,20 +166,3 @@ def test_fused_device_path_takes_the_same_draws(monkeypatch):
     assert len(calls) == 1 and len(calls[0][0]) == 4
     assert torch.equal(got["audio_body_conducted"], want["audio_body_conducted"])
     assert torch.equal(got["audio_airborne"], want["audio_airborne"])
-
-
-@pytest.mark.parametrize("aug", [dict(p_speed_perturbation=1, p_pitch_shift=0, p_time_masking=0),
-                                 dict(p_speed_perturbation=0, p_pitch_shift=1, p_time_masking=1)], ids=str)
-def test_waveform_data_augmentation_matches_the_reference(ref_utils, aug):
-    """Same draws, same torchaudio transforms, same in-place time mask as the reference module."""
-    pytest.importorskip("torchaudio")
-    from vibravox_b200.torch_modules.dsp.data_augmentation import WaveformDataAugmentation
-    torch.manual_seed(4)
-    a, b = torch.randn(2, 1, 4000), torch.randn(2, 1, 4000)
-    torch.manual_seed(8)
-    wa, wb = _ref_aug(p_data_augmentation=1, **aug)(a.clone(), b.clone())
-    torch.manual_seed(8)
-    ga, gb = WaveformDataAugmentation(16000, p_data_augmentation=1, **aug)(a.clone(), b.clone())
-    assert ga.shape == wa.shape and torch.equal(ga, wa) and torch.equal(gb, wb)
-    with pytest.raises(AssertionError):
-        WaveformDataAugmentation(16000, p_pitch_shift=1.5)

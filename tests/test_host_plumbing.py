@@ -120,6 +120,61 @@ def test_flat_adam_state_dict_is_torch_adam_compatible():
             flat2.load_state_dict(torch.optim.Adam(qs[:2]).state_dict())
 
 
+def test_flat_adam_keeps_frozen_parameters_in_the_index_space_of_torch_adam():
+    """generator.parameters() starts with the two requires_grad=False PQMF banks (pqmf.py:51-56): torch.optim.Adam
+    indexes all 92 tensors (state keys start at 2); FlatAdam must use the same indices in both directions."""
+    from vibravox_b200.optim import FlatAdam
+    torch.manual_seed(1)
+    shapes = [(4, 1, 8), (4, 1, 8), (6, 2, 3), (5,)]
+
+    def make():
+        ps = [torch.nn.Parameter(torch.randn(s)) for s in shapes]
+        ps[0].requires_grad_(False); ps[1].requires_grad_(False)
+        return ps
+
+    with cpu_ops():
+        ps, qs = make(), None
+        torch.manual_seed(1)
+        qs = make()
+        flat, adam = FlatAdam(ps, lr=3e-4, betas=(0.5, 0.9)), torch.optim.Adam(qs, lr=3e-4, betas=(0.5, 0.9))
+        assert len(flat.param_groups[0]["params"]) == 4 and len(flat.params) == 2
+        # a fresh torch Adam state dict (what the advisor's repro loads) is accepted
+        flat.load_state_dict(adam.state_dict())
+        for _ in range(2):
+            gs = [torch.randn(s) for s in shapes[2:]]
+            for p, q, g in zip(ps[2:], qs[2:], gs):
+                p.grad, q.grad = g.clone(), g.clone()
+            flat.step(); flat.zero_grad(); adam.step()
+        sd, ref = flat.state_dict(), adam.state_dict()
+        assert sorted(sd["state"]) == sorted(ref["state"]) == [2, 3]
+        assert sd["param_groups"][0]["params"] == ref["param_groups"][0]["params"] == [0, 1, 2, 3]
+        for i in (2, 3):
+            assert torch.allclose(sd["state"][i]["exp_avg"], ref["state"][i]["exp_avg"], atol=1e-7)
+        # both directions
+        adam2 = torch.optim.Adam(make(), lr=1.0); adam2.load_state_dict(sd)
+        flat2 = FlatAdam(make(), lr=1.0); flat2.load_state_dict(ref)
+        assert int(flat2.step_count[0]) == 2 and flat2.param_groups[0]["lr"] == 3e-4
+        assert torch.equal(ps[0], qs[0])                              # frozen tensors untouched
+
+
+def test_flat_adam_round_trips_with_adam_over_generator_parameters():
+    from vibravox_b200.optim import FlatAdam
+    from vibravox_b200.torch_modules.dnn.eben_generator import EBENGenerator
+    torch.manual_seed(3)
+    G = EBENGenerator(m=4, n=32, p=2)
+    with cpu_ops():
+        flat = FlatAdam(G.parameters(), lr=3e-4, betas=(0.5, 0.9))
+        adam = torch.optim.Adam(G.parameters(), lr=3e-4, betas=(0.5, 0.9))
+        flat.load_state_dict(adam.state_dict())                      # the advisor's failing call
+        assert len(flat.all_params) == 92 and len(flat.params) == 90
+        flat.materialize()
+        flat.grad.fill_(1e-3)
+        flat.step()
+        sd = flat.state_dict()
+        assert min(sd["state"]) == 2 and len(sd["state"]) == 90
+        adam.load_state_dict(sd)
+
+
 def test_run_py_trainer_checkpoint_resume(tmp_path):
     """run.py's override grammar -> Trainer.fit -> last.ckpt -> `ckpt_path=last`: three steps in one go and two steps
     + resume + one step end on the same parameters, Adam moments and balancing state."""

@@ -14,7 +14,7 @@ import torch  # noqa: F401  (must precede the CDLL load, see module docstring)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvbx_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 c_int, c_i64, c_f, c_d, c_p = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double, ctypes.c_void_p
 
@@ -38,6 +38,8 @@ SIGNATURES = {
     "vbx_last_error": [],
     "vbx_launch_count": [],
     "vbx_set_tensor_core_mode": [c_int],
+    "vbx_set_deterministic": [c_int],
+    "vbx_gather_scalars": [c_p] * 8 + [c_int, c_f, c_p, c_p],
     "vbx_conv1d_fwd": [_PD, c_p, c_p, _PE, c_p, c_p],
     "vbx_conv1d_dgrad": [_PD, c_p, c_p, _PE, c_p, c_p],
     "vbx_conv1d_wgrad": [_PD, c_p, c_p, c_p, c_p],

@@ -10,8 +10,10 @@ Design: the random decisions are taken first (`plan_*`: a few host integers per 
 `torch.randint` calls in the reference's order), the samples are moved second.  When every item of a noisy-BWE
 batch has the same length, lives on the GPU and is at least as long as the target, the move is ONE launch of
 `vbx_noise_mix_crop` (mix + joint crop fused, `ops.noise_mix_crop`); otherwise plain slicing / padding on
-whatever device the items live on (the reference does this in CPU dataloader workers).  The augmentation hook is
-`torch_modules/dsp/data_augmentation.WaveformDataAugmentation` (same draws; a no-op at its default probability 0).
+whatever device the items live on (the reference does this in CPU dataloader workers).  Waveform augmentation
+(`torch_modules/dsp/data_augmentation.py` of the reference: SURVEY 2 row 12, out of scope) is a caller-supplied hook:
+pass the reference's own `WaveformDataAugmentation` object as `data_augmentation`; without one the collators consume
+the one `rand(1)` gate draw the reference's default (probability 0) hook takes, so seeded runs stay in step.
 """
 from __future__ import annotations
 
@@ -125,13 +127,14 @@ def _constant_length(body: List[torch.Tensor], air: List[torch.Tensor], samples:
 
 
 def _augment(body: torch.Tensor, air: torch.Tensor, deterministic: bool, data_augmentation, sample_rate: int):
-    """`if deterministic is False: with torch.no_grad(): data_augmentation(body, air)` (`bwe.py:282-287`).  The default
-    hook is the reference's default `WaveformDataAugmentation(sample_rate)`: a no-op that still draws one `rand(1)`."""
+    """`if deterministic is False: with torch.no_grad(): data_augmentation(body, air)` (`bwe.py:282-287`).  The
+    reference's default hook (`WaveformDataAugmentation(sample_rate)`, probability 0) is a no-op that still draws one
+    `rand(1)` for its gate: without a hook that draw is taken here, so the generator state stays the reference's."""
     if deterministic is not False:
         return body, air
     if data_augmentation is None:
-        from .torch_modules.dsp.data_augmentation import WaveformDataAugmentation
-        data_augmentation = WaveformDataAugmentation(sample_rate)
+        torch.rand(1)
+        return body, air
     with torch.no_grad():
         return data_augmentation(body, air)
 

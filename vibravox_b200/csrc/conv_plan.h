@@ -8,6 +8,9 @@ namespace vbx {
 
 inline int plan_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// vbx_set_deterministic: one CTA per output tile walks a whole reduction in a fixed order (no split-K atomics)
+inline int& deterministic_flag() { static int flag = 0; return flag; }
+
 inline int pick_tm(int M) {
   if (M > 64) return 128;
   if (M > 32) return 64;
@@ -86,7 +89,7 @@ inline Plan plan_conv(int mode, GemmP& P) {
     long long want = (148 * 4 + tiles - 1) / tiles;
     long long max_split = (red + 16 * 8 - 1) / (16 * 8);   // >= 8 chunks per slice
     if (want > max_split) want = max_split;
-    if (want < 1) want = 1;
+    if (want < 1 || deterministic_flag()) want = 1;
     if (want > 65535) want = 65535;
     long long split = (red + want - 1) / want;
     split = (split + 15) / 16 * 16;

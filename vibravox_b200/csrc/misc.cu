@@ -5,6 +5,7 @@
 // reductions (double accumulators so the result does not depend on block order at
 // fp32 resolution).  include/vbx.h cites the reference call site of each entry point.
 #include "common.cuh"
+#include "conv_plan.h"
 
 namespace vbx {
 thread_local char g_err[512] = "";
@@ -37,6 +38,10 @@ static inline int stream_blocks(long long n, int per_block) {
   if (b > kSMs * 8) b = kSMs * 8;
   if (b < 1) b = 1;
   return (int)b;
+}
+// grid of a reduction that ends in one atomic per block: a single block in deterministic mode (fixed order)
+static inline int reduce_blocks(long long n, int per_block) {
+  return deterministic_flag() ? 1 : stream_blocks(n, per_block);
 }
 
 // ------------------------------------------------------------------ weight norm
@@ -557,6 +562,24 @@ extern "C" int vbx_abi_version(void) { return VBX_ABI_VERSION; }
 extern "C" const char* vbx_last_error(void) { return g_err; }
 extern "C" uint64_t vbx_launch_count(void) { return g_launches.load(); }
 extern "C" int vbx_set_tensor_core_mode(int mode) { int o = g_tc_mode; g_tc_mode = mode; return o; }
+extern "C" int vbx_set_deterministic(int on) { int o = deterministic_flag(); deterministic_flag() = on ? 1 : 0; return o; }
+
+namespace vbx {
+struct ScalarPtrs { const float* p[8]; };
+__global__ void gather_scalars_kernel(ScalarPtrs s, int n, float scale, float* __restrict__ out) {
+  const int i = threadIdx.x;
+  if (i < n && s.p[i]) out[i] = scale * s.p[i][0];
+}
+}  // namespace vbx
+extern "C" int vbx_gather_scalars(const float* p0, const float* p1, const float* p2, const float* p3, const float* p4,
+                                  const float* p5, const float* p6, const float* p7, int32_t n, float scale,
+                                  float* out, void* stream) {
+  VBX_REQUIRE(out, VBX_BAD_POINTER, "gather_scalars: null output");
+  VBX_REQUIRE(n >= 1 && n <= 8, VBX_BAD_SHAPE, "gather_scalars: 1..8 scalars");
+  ScalarPtrs s{{p0, p1, p2, p3, p4, p5, p6, p7}};
+  gather_scalars_kernel<<<1, 32, 0, ST>>>(s, n, scale, out);
+  return launched("gather_scalars_kernel");
+}
 
 extern "C" int vbx_weight_norm_fwd(const float* g, const float* v, float* w, float* wt, float* inv_norm,
                                    int32_t R, int32_t Cin_g, int32_t K, int32_t groups, void* stream) {
@@ -618,7 +641,7 @@ extern "C" int vbx_leaky_relu_bwd(const float* dy, const float* ref, const uint8
     int S = (int)(units < 65535 ? units : 65535);
     int cap = (kSMs * 16 + C - 1) / C;
     if (S > cap) S = cap;
-    if (S < 1) S = 1;
+    if (S < 1 || deterministic_flag()) S = 1;
     dim3 grid(C, S);
     const bool vec = (T & 3) == 0 && (al & 15) == 0 && ((uintptr_t)mask & 3) == 0;
     if (vec) leaky_relu_bwd_bias_kernel<true><<<grid, 256, 0, ST>>>(dy, ref, mask, dx, dbias, B, C, T, slope, beta);
@@ -674,7 +697,7 @@ extern "C" int vbx_fill(float* p, int64_t n, float value, void* stream) {
 extern "C" int vbx_l1_pair_sums(const float* a, const float* b, int64_t n, double* sums, void* stream) {
   VBX_REQUIRE(a && b && sums, VBX_BAD_POINTER, "l1_pair_sums: null tensor");
   VBX_REQUIRE(n > 0, VBX_BAD_SHAPE, "l1_pair_sums: empty");
-  l1_pair_sums_kernel<<<stream_blocks(n, 2048), 256, 0, ST>>>(a, b, n, sums);
+  l1_pair_sums_kernel<<<reduce_blocks(n, 2048), 256, 0, ST>>>(a, b, n, sums);
   return launched("l1_pair_sums_kernel");
 }
 extern "C" int vbx_fm_finalize(const double* sums, int32_t npairs, float scale, float* loss, void* stream) {
@@ -692,7 +715,7 @@ extern "C" int vbx_l1_pair_bwd(const float* a, const float* b, int64_t n, const 
 extern "C" int vbx_hinge_fwd(const float* c, int64_t n, float target, float scale, double* acc, void* stream) {
   VBX_REQUIRE(c && acc, VBX_BAD_POINTER, "hinge_fwd: null tensor");
   VBX_REQUIRE(n > 0, VBX_BAD_SHAPE, "hinge_fwd: empty");
-  hinge_fwd_kernel<<<stream_blocks(n, 2048), 256, 0, ST>>>(c, n, target, scale, acc);
+  hinge_fwd_kernel<<<reduce_blocks(n, 2048), 256, 0, ST>>>(c, n, target, scale, acc);
   return launched("hinge_fwd_kernel");
 }
 extern "C" int vbx_hinge_bwd(const float* c, int64_t n, float target, float scale, const float* go, float* dc,
@@ -712,7 +735,7 @@ extern "C" int vbx_stft_stats(const float* X, const float* Y, int32_t B, int32_t
                               double* stats, void* stream) {
   VBX_REQUIRE(X && Y && stats, VBX_BAD_POINTER, "stft_stats: null tensor");
   VBX_REQUIRE(B > 0 && bins > 0 && F > 0, VBX_BAD_SHAPE, "stft_stats: bad shape");
-  stft_stats_kernel<<<stream_blocks((long long)B * bins * F, 2048), 256, 0, ST>>>(X, Y, B, bins, F, eps, stats);
+  stft_stats_kernel<<<reduce_blocks((long long)B * bins * F, 2048), 256, 0, ST>>>(X, Y, B, bins, F, eps, stats);
   return launched("stft_stats_kernel");
 }
 extern "C" int vbx_stft_finalize(const double* stats, const double* counts, int32_t nres, float w, float* loss,
@@ -766,7 +789,7 @@ extern "C" int vbx_scalar_mul(const float* go, const float* lam, float* out, int
 extern "C" int vbx_sumsq(const float* x, int64_t n, double* acc, void* stream) {
   VBX_REQUIRE(x && acc, VBX_BAD_POINTER, "sumsq: null tensor");
   VBX_REQUIRE(n > 0, VBX_BAD_SHAPE, "sumsq: empty");
-  sumsq_kernel<<<stream_blocks(n, 2048), 256, 0, ST>>>(x, n, acc);
+  sumsq_kernel<<<reduce_blocks(n, 2048), 256, 0, ST>>>(x, n, acc);
   return launched("sumsq_kernel");
 }
 extern "C" int vbx_balance(const double* sumsq, float* norms_old, int32_t* initialised, float* lambdas,

@@ -21,7 +21,6 @@
 #include "common.cuh"
 #include "conv_plan.h"
 #include "tc_common.cuh"
-#include "ps_vec_stage.h"
 #include <limits.h>
 #include <stdlib.h>
 
@@ -69,8 +68,6 @@ struct TcP {
   int ps;           // 1: launch tc_pslab_kernel (then sl_tpb = K, sl_nbst = 1, tmem_cols = two accumulator buffers)
   int ps_slots;     // slab ring depth in whole tiles (1 or 2)
   int ps_gx;        // CTAs along the row-tile axis
-  int ps_vec;       // experimental (VBX_TC_PS_VEC=1): tc_pslab_vec_kernel, 16-byte staging (stride 1, Tin % 4 == 0)
-  int ps_vec_aligned;   // x is 16-byte aligned (else every item takes the per-sample path)
 };
 
 // one reduction segment of a tile: FWD has one; DGRAD has one per mirror image it touches
@@ -569,7 +566,6 @@ __global__ void tc_pack_merged_kernel(const float* __restrict__ w, unsigned char
 
 #include "tc_slab.cuh"
 #include "tc_pslab.cuh"
-#include "tc_pslab_vec.cuh"
 
 // Merged-phase input gradient on the gather kernel: worth it only where the common tap grid has no holes
 // (dil = 1) and a phase does not already fill a 256-wide tile.  The slab kernel takes the general case.
@@ -584,12 +580,8 @@ static size_t slab_smem_bytes(const TcP& P) {
   return (size_t)P.sl_SA * slab_a_stage(P.g) + (size_t)P.sl_SB * slab_b_stage(P.NT, P.sl_tpb) +
          (2 * P.sl_SA + 2 * P.sl_SB + 1) * sizeof(uint64_t) + 16 + (size_t)P.g.K * sizeof(int) + 16;
 }
-static bool pslab_vec_wanted(const GemmP& G) {
-  static const bool on = getenv("VBX_TC_PS_VEC") && atoi(getenv("VBX_TC_PS_VEC")) == 1;
-  return on && G.stride == 1 && (G.Tin & 3) == 0;
-}
 static size_t pslab_smem_bytes(const TcP& P, int slots) {
-  const size_t a_stage = pslab_vec_wanted(P.g) ? (size_t)ps_vec_geom(P.g).a_stage : (size_t)slab_a_stage(P.g);
+  const size_t a_stage = (size_t)slab_a_stage(P.g);
   return (size_t)P.sl_ncg * slab_b_stage(P.NT, P.g.K) + (size_t)slots * P.sl_ncg * a_stage +
          (2 * slots + 5) * sizeof(uint64_t) + 16 + (size_t)P.g.K * sizeof(int) + 16;
 }
@@ -616,7 +608,6 @@ static void plan_pslab(TcP& P) {
     if (gx < 1) gx = 1;
     if (gx > row_tiles) gx = row_tiles;
     P.ps = 1; P.ps_slots = slots; P.ps_gx = (int)gx;
-    P.ps_vec = pslab_vec_wanted(P.g) ? 1 : 0; P.ps_vec_aligned = 0;
     P.sl_tpb = P.g.K; P.sl_nbst = 1;
     P.tmem_cols = cols2;
     return;
@@ -677,7 +668,6 @@ static int fill_tc_geom(TcP& P, const vbx_conv_desc* d, int mode, int nsplit, bo
   P.merged = 0;
   P.slab = 0;
   P.ps = 0;
-  P.ps_vec = 0; P.ps_vec_aligned = 0;
   if (mode == DGRAD && P.g.refl == 0 && P.g.stride <= 8) {
     // Zero-halo input gradient as a stride-1 forward conv over dy (Cout ch, Tout long) -> D (s*Cin ch, V long):
     // every stride phase of dx becomes a block of columns, the taps sit on a unit-spaced grid of J slots
@@ -777,18 +767,6 @@ static int launch_pslab(const TcP& P, cudaStream_t st) {
   }
   dim3 grid((unsigned)P.ps_gx, (unsigned)(P.ntiles_n * P.g.groups), 1);
   if (grid.y > 65535) return fail(VBX_UNSUPPORTED, "tc_pslab: grid too large");
-  if (P.ps_vec) {
-    static bool vec_attr_set = false;
-    if (!vec_attr_set) {
-      cudaError_t ce = cudaFuncSetAttribute(tc_pslab_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      if (ce != cudaSuccess) return fail((int)ce, "tc_pslab_vec: cannot raise the dynamic shared memory limit");
-      vec_attr_set = true;
-    }
-    TcP Q = P;
-    Q.ps_vec_aligned = ((uintptr_t)P.g.X & 15) == 0 ? 1 : 0;
-    tc_pslab_vec_kernel<<<grid, kThreads, pslab_smem_bytes(P, P.ps_slots), st>>>(Q);
-    return launched("tc_pslab_vec_kernel");
-  }
   tc_pslab_kernel<<<grid, kThreads, pslab_smem_bytes(P, P.ps_slots), st>>>(P);
   return launched("tc_pslab_kernel");
 }
@@ -1196,6 +1174,7 @@ extern "C" int vbx_tc_conv1d_wgrad(const vbx_conv_desc* d, const float* x, const
   if (max_split > 65535) max_split = 65535;
   if (max_split < 1) max_split = 1;
   long long want = pick_split(tiles, 148 * (P.tmem_cols > 128 ? 2 : 3), max_split);
+  if (deterministic_flag()) want = 1;
   long long per = (total + want - 1) / want;
   per = (per + kKC - 1) / kKC * kKC;
   P.red_per = (int)per;

@@ -266,6 +266,7 @@ static bool plan_wslab(TcWS& P, const vbx_conv_desc* d) {
   long long want = tiles >= 48 ? pick_split(tiles, 148 * (P.tmem_cols > 256 ? 1 : 2), max_split)
                                : (148 * 3 + tiles - 1) / tiles;
   if (want > max_split) want = max_split;
+  if (deterministic_flag()) want = 1;
   long long per = (total + want - 1) / want;
   per = (per + kWsTC - 1) / kWsTC * kWsTC;
   P.rows_per = (int)per;

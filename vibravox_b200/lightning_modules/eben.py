@@ -33,7 +33,7 @@ class _SegmentedStep:
         for i, g in enumerate(self.graphs):
             g.replay()
             if i < len(self.buckets):
-                allreduce_sum_(self.buckets[i])
+                allreduce_sum_(self.buckets[i])        # gradients + the logged scalars packed behind them
 
 
 class EBENLightningModule(torch.nn.Module):
@@ -63,6 +63,10 @@ class EBENLightningModule(torch.nn.Module):
         self.beta_ema = beta_ema
         assert 0 <= update_discriminator_ratio <= 1, "update_discriminator_ratio must be in [0, 1]"
         self.update_discriminator_ratio = update_discriminator_ratio
+        if push_to_hub_after_testing:
+            # eben.py:177-182 of the reference pushes the generator in on_test_end; there is no network on this path
+            raise NotImplementedError("push_to_hub_after_testing=True is not supported: call "
+                                      "generator.push_to_hub(...) (PyTorchModelHubMixin) yourself after testing")
         self.push_to_hub_after_testing = push_to_hub_after_testing
         self.automatic_optimization = False
         assert schedule in {"shared", "reference"}
@@ -76,6 +80,7 @@ class EBENLightningModule(torch.nn.Module):
         self.logged: Dict[str, torch.Tensor] = {}
         self._graphs: Dict[tuple, dict] = {}      # training_step_graphed: one captured step per batch shape
         self._capture = None                      # state of a segmented capture in progress (see _capture_segments)
+        self.max_graph_shapes = 4                 # captured steps kept (LRU by batch shape); more shapes run eagerly
         self.dataloader_names = None              # base_se.py:52: names of the validation / test dataloaders, if several
         self.graph_warmup_steps = 2
 
@@ -88,6 +93,7 @@ class EBENLightningModule(torch.nn.Module):
 
     def log(self, name: str, value: torch.Tensor, **_) -> None:
         self.logged[name] = value.detach() if isinstance(value, torch.Tensor) else value
+        self.__dict__.setdefault("_synced", set()).discard(name)      # (re-)logged: not yet rank-averaged
 
     def toggle_optimizer(self, optimizer) -> None:
         mine = {id(p) for g in optimizer.param_groups for p in g["params"]}
@@ -170,8 +176,17 @@ class EBENLightningModule(torch.nn.Module):
         names = ("audio_body_conducted", "audio_airborne")
         key = tuple(tuple(batch[n].shape) for n in names)
         st = self._graphs.get(key)
+        if st is not None:
+            self._graphs[key] = self._graphs.pop(key)          # most recently used last
         if st is None:
             dev = self.generator.last_conv.weight.device
+            if len(self._graphs) >= self.max_graph_shapes:
+                # 'pad' collation yields a new length per batch: a captured graph (and its private memory pool) per
+                # shape would grow without bound.  Keep the most recent shapes, run a shape seen for the first time
+                # while the cache is full eagerly, and evict the least recently used capture.
+                self._graphs.pop(next(iter(self._graphs)))
+                return self.training_step({k: v.to(dev, non_blocking=True) for k, v in batch.items()
+                                           if isinstance(v, torch.Tensor)})
             st = self._graphs[key] = dict(calls=0, graph=None, out=None, logged=None, launches=0,
                                           stream=torch.cuda.Stream(dev),
                                           inputs={n: torch.empty(batch[n].shape, device=dev, dtype=torch.float32)
@@ -368,20 +383,27 @@ class EBENLightningModule(torch.nn.Module):
         return lambdas
 
     def _sync_grads(self, optimizer) -> None:
+        """Gradient exchange of one network (DDP's all-reduce, mean semantics) - and, in the same collective, the
+        scalars logged since the previous exchange: the reference logs every loss with `sync_dist=True`
+        (eben.py:103-124), i.e. the rank MEAN; here they are packed behind the gradients in the flat bucket."""
         if getattr(self, "_capture", None) is not None:
             # segmented capture: the all-reduce of this bucket happens between two graph replays
             optimizer.gather_autograd_grads()
+            keys = self._pack_logs(optimizer)
             self._segment_end()
-            self._capture["buckets"].append(optimizer.grad)
+            self._capture["buckets"].append(optimizer.bucket)
             from ..parallel import world_size
             optimizer.grad_scale = 1.0 / world_size()
             self._segment_begin()
+            self._unpack_logs(optimizer, keys, optimizer.grad_scale)
             return
         if torch.distributed.is_available() and torch.distributed.is_initialized() \
                 and torch.distributed.get_world_size() > 1:
             if isinstance(optimizer, FlatAdam):
                 optimizer.gather_autograd_grads()
-                optimizer.grad_scale = allreduce_sum_(optimizer.grad)
+                keys = self._pack_logs(optimizer)
+                optimizer.grad_scale = allreduce_sum_(optimizer.bucket)
+                self._unpack_logs(optimizer, keys, optimizer.grad_scale)
             else:
                 world = torch.distributed.get_world_size()
                 for g in optimizer.param_groups:
@@ -389,6 +411,30 @@ class EBENLightningModule(torch.nn.Module):
                         if p.grad is not None:
                             torch.distributed.all_reduce(p.grad)
                             p.grad.div_(world)
+                for k in self._unsynced_logs():
+                    v = self.logged[k].clone()
+                    torch.distributed.all_reduce(v)
+                    self.logged[k] = v / world
+                    self._synced.add(k)
+
+    def _unsynced_logs(self):
+        synced = self.__dict__.setdefault("_synced", set())
+        return [k for k, v in self.logged.items() if k not in synced and isinstance(v, torch.Tensor)]
+
+    def _pack_logs(self, optimizer):
+        keys = self._unsynced_logs()[:FlatAdam.TAIL]
+        for i in range(0, len(keys), 8):
+            ops.gather_scalars([self.logged[k].reshape(1) for k in keys[i:i + 8]], optimizer.tail[i:i + 8], 1.0)
+        return keys
+
+    def _unpack_logs(self, optimizer, keys, scale: float) -> None:
+        if not keys:
+            return
+        mean = torch.empty(len(keys), device=optimizer.tail.device, dtype=torch.float32)
+        ops.axpby(optimizer.tail[:len(keys)], mean, scale, 0.0)
+        for i, k in enumerate(keys):
+            self.logged[k] = mean[i]
+            self._synced.add(k)
 
     def _training_step_reference(self, batch: Dict[str, torch.Tensor]):
         corrupted_speech = self.generator.cut_to_valid_length(batch["audio_body_conducted"])
@@ -522,7 +568,15 @@ class EBENLightningModule(torch.nn.Module):
                 p.__dict__.pop("_vbx_packs", None)
         bal = ckpt.get("vbx_balancing")
         dev = self.generator.last_conv.weight.device
-        self._bal = None if bal is None else {k: v.to(dev).clone() for k, v in bal.items()}
+        if bal is None:
+            if self._bal is not None:                          # a captured graph reads these buffers: reset in place
+                self._bal["old"].zero_(); self._bal["init"].zero_()
+        elif self._bal is not None and self._bal["old"].numel() == bal["old"].numel():
+            for k, v in bal.items():                           # in place, so a captured step keeps reading live memory
+                self._bal[k].copy_(v)
+        else:
+            self._bal = {k: v.to(dev).clone() for k, v in bal.items()}
+            self._graphs.clear()                               # (buffers were re-created: captured steps are stale)
         return int(ckpt.get("global_step", 0))
 
     @torch.no_grad()

@@ -286,6 +286,20 @@ def axpby_dev(x: Tensor, y: Tensor, alpha: Tensor, beta: float) -> Tensor:
     return y
 
 
+def set_deterministic(on: bool) -> bool:
+    """Fixed-order reductions (include/vbx.h: vbx_set_deterministic); returns the previous setting."""
+    return bool(_lib.load().vbx_set_deterministic(1 if on else 0))
+
+
+def gather_scalars(scalars, out: Tensor, scale: float = 1.0) -> Tensor:
+    """out[i] = scale * scalars[i] for up to 8 one-element device tensors, one launch."""
+    n = len(scalars)
+    assert 1 <= n <= 8 and out.numel() >= n
+    ptrs = [_p(s) for s in scalars] + [None] * (8 - n)
+    check(_lib.load().vbx_gather_scalars(*ptrs, n, float(scale), _p(out), _stream()), "vbx_gather_scalars")
+    return out
+
+
 def fill(t: Tensor, value: float) -> Tensor:
     check(_lib.load().vbx_fill(_p(t), t.numel(), value, _stream()), "vbx_fill")
     return t
@@ -428,10 +442,12 @@ def noise_mix_crop(body: Tensor, air: Tensor, noise: Tensor, start: Tensor, off:
 TC_ENABLED = os.environ.get("VBX_TC", "1") != "0"
 TC_FWD, TC_DGRAD = 0, 1
 # STFT as framing (unfold) + a pointwise conv over the frame axis (so that it rides the tensor-core conv
-# kernels) instead of one strided conv with a 240..1200-tap kernel on the FMA path.  OFF by default: the
-# log-magnitude term divides by bins that sit 60-100 dB under the frame energy (A-weighting), which turns the
-# 2^-17 operand rounding of bf16x3 into a 1.8e-2 gradient error / +1 % gradient-norm bias (measured, fp32
-# arithmetic: 4e-3 / <1e-4), and that norm drives the loss balancing.  The FMA path keeps fp32 there.
+# kernels) instead of one strided conv with a 240..1200-tap kernel on the FMA path.  ON whenever the tensor-core
+# path is on, and run with the 3-way operand split (nsplit = 3, "bf16x6", 24 mantissa bits): the log-magnitude
+# term divides by bins that sit 60-100 dB under the frame energy (A-weighting), which turned the 2^-17 operand
+# rounding of the 2-way split into a 1.8e-2 gradient error / +1 % gradient-norm bias (measured); with the 3-way
+# split the gradient error is the fp32 oracle's own 4e-3 vs fp64.  VBX_STFT_VIA_FRAMES=0 (or VBX_TC=0)
+# runs the STFT as one strided conv on the fp32 FMA kernel instead.
 STFT_VIA_FRAMES = os.environ.get("VBX_STFT_VIA_FRAMES", "1" if TC_ENABLED else "0") == "1"
 
 

@@ -18,16 +18,24 @@ from . import ops
 
 
 class FlatAdam(torch.optim.Optimizer):
+    TAIL = 16        # floats appended to the gradient bucket (see materialize)
+
     def __init__(self, params: Iterable[torch.Tensor], lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.0, amsgrad: bool = False):
         if weight_decay != 0.0 or amsgrad:
             raise NotImplementedError("FlatAdam implements the reference configuration: weight_decay=0, amsgrad=False")
         defaults = dict(lr=lr, betas=tuple(betas), eps=eps)
-        super().__init__([p for p in params if p.requires_grad], defaults)
+        # Every parameter stays in param_groups[0]["params"] - frozen ones too (generator.parameters() starts with the
+        # two requires_grad=False PQMF banks, pqmf.py:51-56) - so that state indices are those torch.optim.Adam uses
+        # over the same iterable and optimizer states travel both ways.  Only the trainable ones get a slice of the
+        # flat buckets (`params`); frozen ones never receive a gradient, exactly as Adam skips `grad is None`.
+        super().__init__(list(params), defaults)
         if len(self.param_groups) != 1:
             raise NotImplementedError("FlatAdam supports a single parameter group")
+        self._trainable_idx = [i for i, p in enumerate(self.param_groups[0]["params"]) if p.requires_grad]
+        self._params = [self.param_groups[0]["params"][i] for i in self._trainable_idx]
         self._indirect: List[int] = []      # ids of params whose grads arrive through autograd (.grad)
-        self.flat = self.grad = self.exp_avg = self.exp_avg_sq = self.step_count = None
+        self.flat = self.grad = self.bucket = self.tail = self.exp_avg = self.exp_avg_sq = self.step_count = None
         self.grad_scale = 1.0               # set to 1/world_size after a sum all-reduce of `grad`
 
     # ---- layout ---------------------------------------------------------------------------------
@@ -39,6 +47,11 @@ class FlatAdam(torch.optim.Optimizer):
 
     @property
     def params(self) -> List[torch.Tensor]:
+        """The trainable parameters, in order: the ones that own a slice of the flat buckets."""
+        return self._params
+
+    @property
+    def all_params(self) -> List[torch.Tensor]:
         return self.param_groups[0]["params"]
 
     def materialize(self) -> None:
@@ -54,7 +67,10 @@ class FlatAdam(torch.optim.Optimizer):
             offs.append(total)
             total += (p.numel() + 3) // 4 * 4          # keep every slice 16-byte aligned
         self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
-        self.grad = torch.zeros_like(self.flat)
+        # the gradient bucket carries TAIL extra floats behind the gradients: the step's logged scalars ride in the
+        # same all-reduce (lightning_modules/eben.py: sync_dist semantics without extra collectives)
+        self.bucket = torch.zeros(total + self.TAIL, device=dev, dtype=torch.float32)
+        self.grad, self.tail = self.bucket[:total], self.bucket[total:]
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.step_count = torch.zeros(1, device=dev, dtype=torch.int32)
@@ -73,7 +89,7 @@ class FlatAdam(torch.optim.Optimizer):
     # ---- torch.optim API ------------------------------------------------------------------------
     def zero_grad(self, set_to_none: bool = True) -> None:
         self.materialize()
-        ops.fill(self.grad, 0.0)
+        ops.fill(self.bucket, 0.0)
         for p in self.params:
             p.grad = None
 
@@ -85,6 +101,16 @@ class FlatAdam(torch.optim.Optimizer):
                 ops.axpby(g, slot, 1.0, 1.0)
                 p.grad = None
 
+    def broadcast_(self, src: int = 0) -> None:
+        """Data-parallel start-up (what DDP does when it wraps a module): every rank takes rank `src`'s parameters,
+        moments and step count, so ranks that were seeded differently cannot silently diverge."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        self.materialize()
+        for t in (self.flat, self.exp_avg, self.exp_avg_sq, self.step_count):
+            dist.broadcast(t, src=src)
+
     # ---- checkpoints: the layout torch.optim.Adam writes (what a Lightning checkpoint of the reference holds) ----
     def state_dict(self) -> dict:
         """`torch.optim.Adam.state_dict()` layout - per-parameter `step` / `exp_avg` / `exp_avg_sq` indexed in
@@ -92,12 +118,12 @@ class FlatAdam(torch.optim.Optimizer):
         (`configs/lightning_module/optimizer/adam.yaml`).  Copies, not views of the flat buckets."""
         g = self.param_groups[0]
         group = {k: v for k, v in g.items() if k != "params"}
-        group.update(weight_decay=0.0, amsgrad=False, params=list(range(len(self.params))))
+        group.update(weight_decay=0.0, amsgrad=False, params=list(range(len(self.all_params))))
         state = {}
         if self.flat is not None and int(self.step_count[0]) > 0:
             step = self.step_count[0].to(torch.float32)
             off = 0
-            for i, p in enumerate(self.params):
+            for i, p in zip(self._trainable_idx, self.params):      # indices in the FULL parameter order (as Adam)
                 n = p.numel()
                 state[i] = {"step": step.clone(), "exp_avg": self.exp_avg[off:off + n].view(p.shape).clone(),
                             "exp_avg_sq": self.exp_avg_sq[off:off + n].view(p.shape).clone()}
@@ -109,7 +135,7 @@ class FlatAdam(torch.optim.Optimizer):
         """Accepts its own `state_dict()` or one written by `torch.optim.Adam` over the same parameters (in the same
         order).  Moments are copied INTO the flat buckets, so a captured CUDA graph keeps pointing at live memory."""
         groups = state_dict["param_groups"]
-        if len(groups) != 1 or len(groups[0]["params"]) != len(self.params):
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self.all_params):
             raise ValueError("FlatAdam.load_state_dict: expected one parameter group over the same parameters")
         if groups[0].get("amsgrad", False) or groups[0].get("weight_decay", 0.0) != 0.0:
             raise NotImplementedError("FlatAdam implements the reference configuration: weight_decay=0, amsgrad=False")
@@ -125,8 +151,11 @@ class FlatAdam(torch.optim.Optimizer):
         self.exp_avg.zero_()
         self.exp_avg_sq.zero_()
         self.step_count.fill_(steps.pop() if steps else 0)
+        stray = [k for k in state if int(k) not in self._trainable_idx]
+        if stray:
+            raise ValueError(f"FlatAdam.load_state_dict: the checkpoint holds state for frozen parameters {stray[:4]}")
         off = 0
-        for i, p in enumerate(self.params):
+        for i, p in zip(self._trainable_idx, self.params):
             n = p.numel()
             st = state.get(i, state.get(str(i)))
             if st is not None:

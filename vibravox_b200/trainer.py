@@ -49,6 +49,14 @@ class Trainer:
         if ckpt_path:
             # every rank reads the same file: parameters, Adam moments and the balancing EMA continue where they were
             self.global_step = module.load_checkpoint(torch.load(ckpt_path, map_location=dev, weights_only=False))
+        if self.accelerator == "gpu" and world > 1:
+            # what DDP does at wrap time: every rank starts from rank 0's parameters / optimizer state / balancing EMA
+            for opt in module.configure_optimizers():
+                if hasattr(opt, "broadcast_"):
+                    opt.broadcast_(0)
+            if getattr(module, "_bal", None) is not None:
+                for t in module._bal.values():
+                    torch.distributed.broadcast(t, src=0)
         it = datamodule.batches(dev, rank)
         for _ in range(self.global_step):                   # the synthetic stream is replayed up to the resume point
             next(it)
