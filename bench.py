@@ -94,30 +94,37 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peaks = json.load(open(path)) if os.path.exists(path) else {}
+    return (peaks.get("hbm_gbs", 6650.0), peaks.get("bf16_tflops_sustained", 1400.0),
+            "measured" if peaks else "fallback")
+
+
+def _timeit(fn, reps=10, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e-3
+
+
 def layer_microbench(device, B, L):
-    """Per-kernel roofline evidence, measured live with CUDA events on the launching stream:
-    (a) the dominant kernel of the step = the dense MelGAN stage 4 implicit-GEMM conv,
-    (b) the HBM-bound generator residual-unit convs (north_star's 60 % target)."""
+    """Per-kernel roofline evidence, measured live with CUDA events on the launching stream (every tensor set is
+    larger than L2 or the kernel is timed over several distinct buffers, see `rot`):
+    (a) the dominant kernel of the step = the dense MelGAN stage 4 implicit-GEMM conv (tensor bound),
+    (b) the generator ResidualUnit - north_star's "fused EBEN Conv1d kernel", 60 % of HBM target - as ONE fused
+        kernel (algorithmic bytes = read x once + write out once = 4*2*B*C*T) and, next to it, the two-kernel form,
+    (c) the PQMF analysis / synthesis polyphase kernels (HBM bound)."""
     import torch
     from vibravox_b200 import ops
-    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
-        os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-    hbm = peaks.get("hbm_gbs", 6650.0)
-    tens = peaks.get("bf16_tflops_sustained", 1400.0)
-    src = "measured" if peaks else "fallback"
-
-    def timeit(fn, reps=10, warm=3):
-        for _ in range(warm):
-            fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / reps * 1e-3
-
+    hbm, tens, src = _peaks()
     out = []
     # (a) MelGAN stage 4: 1024 -> 1024, k41, s4, groups 4 on (B,1024,748)
     T3 = ((L - 41 + 40) // 4 + 1 - 41 + 40) // 4 + 1
@@ -129,33 +136,139 @@ def layer_microbench(device, B, L):
     To = g.tout(T3)
     flops = 2.0 * B * To * 1024 * 256 * 41
     byt = 4.0 * (B * 1024 * T3 + B * 1024 * To + w.numel())
-    t = timeit(lambda: ops.conv_fwd(x, w, g, bias=bias, slope=0.2), reps=5, warm=2)
+    t = _timeit(lambda: ops.conv_fwd(x, w, g, bias=bias, slope=0.2), reps=5, warm=2)
     kname = "tc_slab_kernel fwd (tcgen05, bf16x3)" if ops.use_tc(g, "fwd") else "gemm_conv_kernel<FWD> (fp32 FMA)"
-    # DRAM bytes of this launch from the committed `ncu --set full` capture (profiles/README.md), bs = 32 only
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tpath) and B == 32 and ops.use_tc(g, "fwd"):
-        traffic = json.load(open(tpath)).get("melgan4_fwd_dram_bytes")
+    traffic = _traffic("melgan4_fwd_dram_bytes") if (B == 32 and ops.use_tc(g, "fwd")) else None
     out.append({"kernel": kname + " melgan.4 (1024->1024,k41,s4,g4)", "bound": "tensor",
                 "achieved": flops / t / 1e12, "peak": tens, "unit": "TFLOP/s", "frac": flops / t / 1e12 / tens,
                 "ms": t * 1e3, "algorithmic_bytes": byt, "peak_source": src + " bf16 sustained", "traffic": traffic,
                 "note": "3 bf16 MMAs per fp32 product: the useful-flop ceiling is peak / 3"})
-    # (b) generator residual unit convs at C=32, T=11968
+    del x, w
+    # (b) generator residual units at the three widths of the network
     Tb = (L + 32) // 4
     for C, T in ((32, Tb), (64, Tb // 2), (128, Tb // 8)):
-        xg = torch.randn(B, C, T, device=device)
+        nbuf = max(2, int(300e6 // (4 * B * C * T)) + 1)          # rotate over > 2 x L2 worth of inputs
+        xs = [torch.randn(B, C, T, device=device) for _ in range(nbuf)]
         w1 = torch.randn(C, C, 3, device=device) * 0.1
         w2 = torch.randn(C, C, 1, device=device) * 0.1
         g1 = ops.ConvGeom(C, C, 3, 1, 3, 3, 3, 1)
         g2 = ops.ConvGeom(C, C, 1, 1, 1, 0, 0, 1)
         byt = 4.0 * 2 * B * C * T
-        t1 = timeit(lambda: ops.conv_fwd(xg, w1, g1))
-        t2 = timeit(lambda: ops.conv_fwd(xg, w2, g2, res=xg, slope=0.01))
+        it = [0]
+
+        def rot():
+            it[0] = (it[0] + 1) % nbuf
+            return xs[it[0]]
+        if hasattr(ops, "residual_unit_fwd") and ops.use_fused_unit(C, T, 3):
+            pk = ops.residual_unit_pack(w1, w2)
+            tf = _timeit(lambda: ops.residual_unit_fwd(rot(), pk, 3, 0.01), reps=20)
+            out.append({"kernel": f"fused ResidualUnit fwd (one kernel: dilated k3 d3 -> 1x1 -> LeakyReLU -> +x) C={C} T={T}",
+                        "bound": "hbm", "achieved": byt / tf / 1e9, "peak": hbm, "unit": "GB/s",
+                        "frac": byt / tf / 1e9 / hbm, "ms": tf * 1e3, "algorithmic_bytes": byt,
+                        "peak_source": src + " copy", "traffic": _traffic(f"fused_unit_c{C}_dram_bytes")})
+        t1 = _timeit(lambda: ops.conv_fwd(rot(), w1, g1))
+        xg = xs[0]
+        t2 = _timeit(lambda: ops.conv_fwd(rot(), w2, g2, res=xg, slope=0.01))
         for nm, tt, bb in (("dilated k3 d3", t1, byt), ("pointwise+lrelu+res", t2, byt * 1.5)):
-            out.append({"kernel": f"conv fwd residual {nm} C={C} T={T}", "bound": "hbm",
+            out.append({"kernel": f"conv fwd residual {nm} C={C} T={T} (two-kernel form)", "bound": "hbm",
                         "achieved": bb / tt / 1e9, "peak": hbm, "unit": "GB/s", "frac": bb / tt / 1e9 / hbm,
                         "ms": tt * 1e3, "algorithmic_bytes": bb, "peak_source": src + " copy", "traffic": None})
+        del xs
+    # (c) PQMF polyphase kernels (pqmf.py:194-213): analysis 4*B*(L + bands*T) bytes, synthesis+sum 4*B*(m*T + L)
+    wa = torch.randn(4, 1, 32, device=device)
+    sig = [torch.randn(B, 1, L, device=device) for _ in range(24)]
+    bnd = [torch.randn(B, 4, Tb, device=device) for _ in range(12)]
+    it = [0]
+    for bands in (2, 4):
+        def f():
+            it[0] += 1
+            return ops.pqmf_analysis(sig[it[0] % len(sig)], wa, bands)
+        ta = _timeit(f, reps=24)
+        bb = 4.0 * B * (L + bands * Tb)
+        out.append({"kernel": f"pqmf_analysis_kernel bands={bands} L={L}", "bound": "hbm", "achieved": bb / ta / 1e9,
+                    "peak": hbm, "unit": "GB/s", "frac": bb / ta / 1e9 / hbm, "ms": ta * 1e3, "algorithmic_bytes": bb,
+                    "peak_source": src + " copy", "traffic": None})
+
+    def fs():
+        it[0] += 1
+        return ops.pqmf_synthesis(bnd[it[0] % len(bnd)], wa, True)
+    tsyn = _timeit(fs, reps=24)
+    bb = 4.0 * B * (4 * Tb + L)
+    out.append({"kernel": f"pqmf_synthesis_kernel (+ band sum) L={L}", "bound": "hbm", "achieved": bb / tsyn / 1e9,
+                "peak": hbm, "unit": "GB/s", "frac": bb / tsyn / 1e9 / hbm, "ms": tsyn * 1e3, "algorithmic_bytes": bb,
+                "peak_source": src + " copy", "traffic": None})
     return out
+
+
+def _traffic(key):
+    """DRAM bytes per launch from the committed `ncu --set full` captures (profiles/README.md)."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            v = json.load(open(path)).get(key)
+            if v is not None:
+                return v
+    return None
+
+
+def workload_name(args, L):
+    B = args.batch
+    if args.workload == "noisybwe":
+        return (f"NoisyBWE EBEN (config 4): on-the-fly noise mix + joint crop (speech + noise[start:start+len], no rescaling) "
+                f"then the full train step with the MR-STFT loss, bs={B}x{args.seconds:g}s@16kHz per GPU (L={L})")
+    return (f"EBEN BWE full train step (gen+disc+MR-STFT/FM/hinge, EMA balancing, 2x Adam) "
+            f"bs={B}x{args.seconds:g}s@16kHz per GPU (L={L} after cut_to_valid_length), m=4 n=32 p=2 q=4 min_channels=24")
+
+
+class Feeder:
+    """The step's inputs.  bwe: one synthetic (body, air) pair per rank, resident on the device (value) or in pinned
+    host memory (e2e).  noisybwe (BASELINE config 4): utterances longer than the crop + a 4x longer noise
+    recording per item; every step draws `start ~ randint(0, len_noise - len_speech)` and the crop offset on the
+    DEVICE generator (Philox) and mixes + crops in one vbx_noise_mix_crop launch (vibravox/utils.py:195-254,50-81)."""
+
+    def __init__(self, args, dev, rank):
+        import torch
+        from vibravox_b200 import parallel
+        self.args, self.dev, self.noisy = args, dev, args.workload == "noisybwe"
+        B, S = args.batch, int(args.seconds * SR)
+        self.B, self.S = B, S
+        seed = parallel.rank_seed(42, rank)
+        if not self.noisy:
+            body, air = synthetic_pairs(B, S, seed)
+            self.host = [body.pin_memory(), air.pin_memory()]
+        else:
+            g = torch.Generator().manual_seed(seed)
+            self.Ls, self.Ln = S + S // 4, 4 * S
+            air = (0.1 * torch.randn(B, 1, self.Ls, generator=g)).clamp(-1, 1)
+            body = (0.1 * torch.randn(B, 1, self.Ls, generator=g)).clamp(-1, 1)
+            noise = 0.05 * torch.randn(B, 1, self.Ln, generator=g)
+            self.host = [body.pin_memory(), air.pin_memory(), noise.pin_memory()]
+            self.gen = torch.Generator(device=dev).manual_seed(seed)
+        self.resident = [t.to(dev) for t in self.host]
+        self.stage = [torch.empty_like(t) for t in self.resident]
+        self.h2d_bytes = sum(t.numel() * 4 for t in self.host)
+        self.launches_per_step = 1 if self.noisy else 0          # vbx_noise_mix_crop
+
+    def _mix(self, body, air, noise):
+        import torch
+        from vibravox_b200 import ops
+        start = torch.randint(0, self.Ln - self.Ls, (self.B,), generator=self.gen, device=self.dev, dtype=torch.int32)
+        off = torch.randint(0, self.Ls - self.S + 1, (self.B,), generator=self.gen, device=self.dev, dtype=torch.int32)
+        ob, oa = ops.noise_mix_crop(body, air, noise, start, off, self.S)
+        return {"audio_body_conducted": ob, "audio_airborne": oa}
+
+    def device_batch(self):
+        if self.noisy:
+            return self._mix(*self.resident)
+        return {"audio_body_conducted": self.resident[0], "audio_airborne": self.resident[1]}
+
+    def host_batch(self):
+        """e2e: this step's raw inputs come from pinned host memory."""
+        if self.noisy:
+            for d, h in zip(self.stage, self.host):
+                d.copy_(h, non_blocking=True)
+            return self._mix(*self.stage)
+        return {"audio_body_conducted": self.host[0], "audio_airborne": self.host[1]}
 
 
 def run_ours(args):
@@ -172,17 +285,18 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     B, S = args.batch, int(args.seconds * SR)
     lm = vibravox_b200.build_model(seed=42, device=dev)
+    if world > 1:
+        for opt in lm.configure_optimizers():
+            opt.broadcast_(0)
     L = S - (S + 32) % lm.generator.multiple
-    body_h, air_h = synthetic_pairs(B, S, parallel.rank_seed(42, rank))
-    body_h, air_h = body_h.pin_memory(), air_h.pin_memory()
-    body_d, air_d = body_h.to(dev), air_h.to(dev)
-    batch = {"audio_body_conducted": body_d, "audio_airborne": air_d}
+    feed = Feeder(args, dev, rank)
 
     graphed = (not args.no_graph) and (not args.profile) and lm.graph_capturable()
+    run_step = lm.training_step_graphed if graphed else lm.training_step
 
     def step():
         # the public call: replays the captured step (after 2 eager calls + 1 capture, all inside the warm-up)
-        (lm.training_step_graphed if graphed else lm.training_step)(batch)
+        run_step(feed.device_batch())
 
     def timed(fn, k):
         parallel.barrier()
@@ -207,8 +321,9 @@ def run_ours(args):
         if rank == 0:
             emit({"profile_run": True, "ms_per_step": t_dev / args.steps * 1e3})
         return
-    n_warm = max(args.warmup, 3) + (3 if graphed else 0)   # graph mode: 2 eager calls + the capture come first
-    for _ in range(n_warm):
+    # graph mode: the first 2 calls run eagerly and the 3rd captures - those 3 come BEFORE the --warmup replays
+    n_pre = 3 if graphed else 0
+    for _ in range(n_pre + max(args.warmup, 3)):
         step()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -218,23 +333,20 @@ def run_ours(args):
     launches = _lib.launch_count() - n0
     if graphed:
         assert lm.graph_launches() > 0, "the step was not captured during the warm-up"
-        launches = lm.graph_launches() * args.steps     # kernel nodes of the replayed graph, counted at capture
+        launches = (lm.graph_launches() + feed.launches_per_step) * args.steps   # kernel nodes of the replayed graph
     clocks = sampler.stop() if rank == 0 else None
     audio_s = world * B * L / SR
     value = audio_s * args.steps / t_dev
 
     # e2e: the public call with HOST buffers; H2D of the step's inputs and D2H of its losses inside the timed region
-    stage_body, stage_air = torch.empty_like(body_d), torch.empty_like(air_d)
     loss_h = torch.empty(2, dtype=torch.float32).pin_memory()
-    host_batch = {"audio_body_conducted": body_h, "audio_airborne": air_h}
 
     def e2e_step():
-        if graphed:
-            lm.training_step_graphed(host_batch)          # H2D straight into the captured step's input buffers
+        hb = feed.host_batch()
+        if graphed or feed.noisy:
+            run_step(hb)                                   # H2D straight into the captured step's input buffers
         else:
-            stage_body.copy_(body_h, non_blocking=True)
-            stage_air.copy_(air_h, non_blocking=True)
-            lm.training_step({"audio_body_conducted": stage_body, "audio_airborne": stage_air})
+            lm.training_step({k: v.to(dev, non_blocking=True) for k, v in hb.items()})
         loss_h[0:1].copy_(lm.logged["train/generator/backprop_loss"].view(1), non_blocking=True)
         loss_h[1:2].copy_(lm.logged["train/discriminator/backprop_loss"].view(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -243,7 +355,7 @@ def run_ours(args):
     _, wall = timed(e2e_step, args.steps)
     wall = parallel.max_over_ranks(wall, dev)
     e2e = {"value": audio_s * args.steps / wall, "unit": "audio-s/s",
-           "h2d_bytes_per_step": int(2 * body_h.numel() * 4), "d2h_bytes_per_step": 8,
+           "h2d_bytes_per_step": int(feed.h2d_bytes), "d2h_bytes_per_step": 8,
            "losses": [float(loss_h[0]), float(loss_h[1])],
            "losses_finite": bool(torch.isfinite(loss_h).all())}
     if not e2e["losses_finite"]:
@@ -258,21 +370,29 @@ def run_ours(args):
     roof = dict(kernels[0]) if kernels else None
     line = {
         "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
-        "warmup": n_warm, "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
+        "warmup": max(args.warmup, 3), "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
-        "config": {"workload": f"EBEN BWE full train step (gen+disc+MR-STFT/FM/hinge, EMA balancing, 2x Adam) "
-                               f"bs={B}x{args.seconds:g}s@16kHz per GPU (L={L} after cut_to_valid_length), "
-                               f"m=4 n=32 p=2 q=4 min_channels=24, schedule={lm.schedule}",
-                   "batch_per_gpu": B, "samples": L, "parallelism": f"dp{world}",
+        "config": {"workload": workload_name(args, L), "batch_per_gpu": B, "samples": L,
+                   "parallelism": f"dp{world}", "schedule": lm.schedule,
                    "launch": ({"whole": "one CUDA graph replay per step",
                                "segments": "three CUDA graph replays per step, split at the two eager NCCL gradient "
                                            "all-reduces"}[lm.graph_mode()] if graphed else "eager launches"),
+                   "pre_warmup": f"{n_pre} calls before the warm-up (2 eager + 1 CUDA-graph capture)" if n_pre else "none",
                    "l2": "per-step working set (activations ~ GBs) >> 126 MB L2; no explicit flush"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roof, "kernel_rooflines": kernels,
     }
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args, bounded=True)
+        line["cpu_baseline"] = cpu_baseline(args, steps=args.cpu_steps, warmup=1)
+    if world == 1 and not args.no_eager_baseline:
+        del lm
+        torch.cuda.empty_cache()
+        try:
+            line["gpu_eager_baseline"] = gpu_eager_baseline(args, dev)
+            line["gpu_eager_baseline"]["speedup_vs_tf32"] = line["gpu_eager_baseline"]["tf32"]["step_ms"] / line["ms_per_step"]
+            line["gpu_eager_baseline"]["speedup_vs_ieee"] = line["gpu_eager_baseline"]["ieee"]["step_ms"] / line["ms_per_step"]
+        except Exception as exc:                          # a baseline leg must never cost the product's number
+            line["gpu_eager_baseline"] = {"unavailable": repr(exc)[:300]}
     emit(line)
 
 
@@ -293,41 +413,57 @@ def cpu_baseline(args, steps: int, warmup: int = 1, budget_s: float = 1e9):
     torch.set_num_threads(cores)
     B = args.cpu_batch
     S = int(args.seconds * SR)
-    body, air = synthetic_pairs(B, S, 42)
-    if args.workload == "noisybwe":
-        body, air = noisy_batch_host(B, S, 42)
+    fixed = synthetic_pairs(B, S, 42)
+    draw = [0]
+
+    def inputs():                                         # noisybwe: the mix + crop is part of every step, as on the GPU
+        if args.workload != "noisybwe":
+            return fixed
+        draw[0] += 1
+        return noisy_batch_host(B, S, 42, draw[0])
     step = O.OracleEBENStep(seed=42)
     t0 = time.perf_counter()
-    step.step(body, air)                                  # warm-up (allocator, oneDNN primitives)
+    step.step(*inputs())                                  # warm-up (allocator, oneDNN primitives)
     first = time.perf_counter() - t0
+    done_warm = 1
     for _ in range(max(warmup, 1) - 1):
         if (time.perf_counter() - t0) + first * (steps + 1) > budget_s:
             break
-        step.step(body, air)
+        step.step(*inputs())
+        done_warm += 1
     k = steps
     left = budget_s - (time.perf_counter() - t0)
     if first * k > left:
         k = max(1, int(left / first))
     t1 = time.perf_counter()
     for _ in range(k):
-        step.step(body, air)
+        step.step(*inputs())
     dt = (time.perf_counter() - t1) / k
     L = S - (S + 32) % 256
     return {"value": B * L / SR / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
-            "s_per_step": dt, "steps": k, "batch": B,
-            "sample": f"{k} timed steps (+{max(warmup, 1)} warm-up) of the same train step at bs={B}x{args.seconds:g}s "
+            "s_per_step": dt, "steps": k, "warmup": done_warm, "batch": B,
+            "sample": f"{k} timed steps (+{done_warm} warm-up) of the same train step at bs={B}x{args.seconds:g}s "
                       f"({args.workload}), fp32, torch CPU ({cores} threads)"}
 
 
-def noisy_batch_host(B: int, S: int, seed: int):
-    """Config 4 on the host (the CPU arm's input): the same draws and arithmetic as `NoisyFeeder` below - speech +
-    noise[start:start+len] (no rescaling), then the joint crop - restated with slicing (vibravox/utils.py:195-254,50-81)."""
+_NOISY_RAW = {}
+
+
+def noisy_batch_host(B: int, S: int, seed: int, draw: int = 0):
+    """Config 4 on the host (the CPU arm's and the eager-GPU leg's input): the same raw material and arithmetic as
+    `Feeder` - speech + noise[start:start+len] (no rescaling), then the joint crop - restated with slicing
+    (vibravox/utils.py:195-254,50-81); `draw` selects the step's (start, offset) draws."""
     import torch
-    g = torch.Generator().manual_seed(seed)
-    Ls, Ln = S + S // 4, 4 * S
-    air = (0.1 * torch.randn(B, 1, Ls, generator=g)).clamp(-1, 1)
-    body = (0.1 * torch.randn(B, 1, Ls, generator=g)).clamp(-1, 1)
-    noise = 0.05 * torch.randn(B, 1, Ln, generator=g)
+    if (B, S, seed) not in _NOISY_RAW:
+        g = torch.Generator().manual_seed(seed)
+        Ls, Ln = S + S // 4, 4 * S
+        air = (0.1 * torch.randn(B, 1, Ls, generator=g)).clamp(-1, 1)
+        body = (0.1 * torch.randn(B, 1, Ls, generator=g)).clamp(-1, 1)
+        noise = 0.05 * torch.randn(B, 1, Ln, generator=g)
+        _NOISY_RAW[(B, S, seed)] = (air, body, noise)
+    air, body, noise = _NOISY_RAW[(B, S, seed)]
+    Ls, Ln = body.shape[-1], noise.shape[-1]
+    g = torch.Generator().manual_seed(seed * 1000003 + draw)
     start = torch.randint(0, Ln - Ls, (B,), generator=g)
     off = torch.randint(0, Ls - S + 1, (B,), generator=g)
     ob = torch.stack([(body[i, :, :] + noise[i, :, start[i]:start[i] + Ls])[:, off[i]:off[i] + S] for i in range(B)])
@@ -389,22 +525,96 @@ def gpu_eager_baseline(args, device, steps: int = 5, warmup: int = 2):
 
 
 def run_reference(args):
+    """The reference arm: the reference path's own arithmetic (oracle port, kind 'port') on the host cores of the box,
+    SAME workload / batch / length as the GPU arm, honouring --steps / --warmup unless the run would exceed
+    --cpu-budget-s (then fewer timed steps are taken and reported)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_baseline(args, bounded=True)
+    args.cpu_batch = args.batch
+    cb = cpu_baseline(args, steps=args.steps, warmup=args.warmup, budget_s=args.cpu_budget_s)
     S = int(args.seconds * SR)
     L = S - (S + 32) % 256
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "audio-s/s",
-            "n_gpus": args.gpus, "steps": args.cpu_steps, "warmup": 1, "ms_per_step": cb["s_per_step"] * 1e3,
+            "n_gpus": args.gpus, "steps": cb["steps"], "warmup": cb["warmup"], "ms_per_step": cb["s_per_step"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": f"EBEN BWE full train step, CPU port of the reference path, bounded sample "
-                                   f"bs={args.cpu_batch}x{args.seconds:g}s@16kHz (L={L})",
-                       "batch_per_gpu": args.cpu_batch, "samples": L, "parallelism": "host-cpu"},
+            "config": {"workload": workload_name(args, L), "batch_per_gpu": args.batch, "samples": L,
+                       "parallelism": f"host-cpu: 1 process, {cb['cores']} threads (no GPU)"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
+
+
+def conv_sweep(args):
+    """BASELINE.json configs[4]: dilated / strided Conv1d micro-bench, this repo's kernels vs cuDNN
+    (torch.nn.functional.conv1d / aten::convolution_backward, fp32 'ieee' and PyTorch's default TF32, cudnn.benchmark
+    on as the reference sets it), B=32, C_in=C_out=C, reflect halo, fwd / input gradient / weight gradient."""
+    import torch
+    import torch.nn.functional as F
+    from vibravox_b200 import ops
+    dev = "cuda"
+    B = 32
+    hbm, _, src = _peaks()
+    shapes = [(3, 1, 1), (3, 3, 1), (3, 9, 1), (1, 1, 1), (7, 1, 1), (4, 1, 2), (8, 1, 4), (16, 1, 8)]   # (k, d, s)
+    Cs = [int(c) for c in args.sweep_c.split(",")]
+    Ls = [int(l) for l in args.sweep_l.split(",")]
+    torch.backends.cudnn.benchmark = True
+    rows, wins = [], {"fwd_ieee": 0, "fwd_tf32": 0, "dgrad_ieee": 0, "dgrad_tf32": 0, "wgrad_ieee": 0, "wgrad_tf32": 0}
+    n = 0
+
+    def mode(m):
+        torch.backends.cudnn.conv.fp32_precision = m
+
+    for C in Cs:
+        for L in Ls:
+            for (k, d, s) in shapes:
+                pad = d * (k - 1) // 2 if s == 1 else s - 1
+                g = ops.ConvGeom(C, C, k, s, d, pad, pad, 1)
+                x = torch.randn(B, C, L, device=dev)
+                w = torch.randn(C, C, k, device=dev) / (C * k) ** 0.5
+                xp = F.pad(x, (pad, pad), mode="reflect") if pad else x
+                reps = 10 if B * C * L < 2e8 else 4
+                y = ops.conv_fwd(x, w, g)
+                dy = torch.randn_like(y)
+                wt = ops.transpose_weight(w, 1)
+                dw = torch.zeros_like(w)
+                t = {"fwd": _timeit(lambda: ops.conv_fwd(x, w, g), reps),
+                     "dgrad": _timeit(lambda: ops.conv_dgrad(dy, w, wt, g, L), reps),
+                     "wgrad": _timeit(lambda: ops.conv_wgrad(x, dy, g, dw=dw), reps)}
+                cb = torch.ops.aten.convolution_backward
+                for m in ("ieee", "tf32"):
+                    mode(m)
+                    t["fwd_" + m] = _timeit(lambda: F.conv1d(F.pad(x, (pad, pad), mode="reflect") if pad else x, w, None, s, 0, d), reps)
+                    t["dgrad_" + m] = _timeit(lambda: cb(dy, xp, w, None, [s], [0], [d], False, [0], 1, [True, False, False]), reps)
+                    t["wgrad_" + m] = _timeit(lambda: cb(dy, xp, w, None, [s], [0], [d], False, [0], 1, [False, True, False]), reps)
+                y_tf32 = F.conv1d(xp, w, None, s, 0, d)
+                ref = F.conv1d(xp[:1].double(), w.double(), None, s, 0, d)
+                e_ours = float((y[:1].double() - ref).abs().max() / ref.abs().max())
+                e_tf32 = float((y_tf32[:1].double() - ref).abs().max() / ref.abs().max())
+                To = y.shape[2]
+                byts = 4.0 * B * (C * L + C * To) + 4.0 * C * C * k
+                n += 1
+                for op in ("fwd", "dgrad", "wgrad"):
+                    for m in ("ieee", "tf32"):
+                        wins[f"{op}_{m}"] += t[op] <= t[f"{op}_{m}"]
+                rows.append(f"| {C} | {L} | {k},{d},{s} | {t['fwd']*1e3:.3f} | {byts / t['fwd'] / 1e9:.0f} ({100 * byts / t['fwd'] / 1e9 / hbm:.0f}%) | "
+                            f"{t['fwd_ieee']*1e3:.3f} | {t['fwd_tf32']*1e3:.3f} | {t['dgrad']*1e3:.3f} | {t['dgrad_ieee']*1e3:.3f} | "
+                            f"{t['dgrad_tf32']*1e3:.3f} | {t['wgrad']*1e3:.3f} | {t['wgrad_ieee']*1e3:.3f} | {t['wgrad_tf32']*1e3:.3f} | "
+                            f"{e_ours:.1e} | {e_tf32:.1e} |")
+                del x, w, y, dy, xp, y_tf32, wt
+            torch.cuda.empty_cache()
+    mode("tf32")
+    head = [f"B=32, C_in=C_out=C, reflect halo; times in ms (CUDA events, {src} HBM copy peak {hbm:.0f} GB/s); cuDNN dgrad/wgrad = "
+            f"aten::convolution_backward on the pre-padded input (the reflect-pad backward is not charged to cuDNN)", "",
+            "| C | L | k,d,s | ours fwd | GB/s (% of peak) | cuDNN ieee fwd | cuDNN tf32 fwd | ours dgrad | cuDNN ieee dgrad | cuDNN tf32 dgrad | "
+            "ours wgrad | cuDNN ieee wgrad | cuDNN tf32 wgrad | err ours | err tf32 |", "|" + "---|" * 15]
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    path = os.path.join(ROOT, "gpurun_out", "conv_sweep.md")
+    with open(path, "w") as f:
+        f.write("\n".join(head + rows) + "\n")
+    emit({"sweep": "BASELINE config 5: Conv1d microbench vs cuDNN", "shapes": n,
+          "ours_at_least_as_fast_as": {k: f"{v}/{n}" for k, v in wins.items()}, "table": "gpurun_out/conv_sweep.md"})
 
 
 def main():
@@ -413,19 +623,32 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="bwe", choices=["bwe", "noisybwe"],
+                    help="bwe = BASELINE configs[1]/[2] (bs=32x3s); noisybwe = configs[3] (bs=16x3s, noise mix in the loop)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--batch", type=int, default=None, help="per GPU; default 32 (bwe) / 16 (noisybwe)")
     ap.add_argument("--seconds", type=float, default=3.0)
-    ap.add_argument("--cpu-batch", type=int, default=4)
-    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--cpu-batch", type=int, default=None, help="cpu_baseline batch (default: the GPU arm's)")
+    ap.add_argument("--cpu-steps", type=int, default=3, help="timed steps of the in-line cpu_baseline leg")
+    ap.add_argument("--cpu-budget-s", type=float, default=240.0, help="--impl reference: wall-clock budget")
     ap.add_argument("--no-micro", action="store_true")
     ap.add_argument("--no-tc", action="store_true", help="fp32 FMA kernels everywhere (VBX_TC=0)")
     ap.add_argument("--profile", action="store_true", help="1 warm-up + --steps steps only (for ncu)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="BASELINE config 5: conv microbench sweep vs cuDNN")
+    ap.add_argument("--sweep-c", default="32,64,128,256,512")
+    ap.add_argument("--sweep-l", default="4096,8192,16384,32768,65536")
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 16 if args.workload == "noisybwe" else 32
+    if args.cpu_batch is None:
+        args.cpu_batch = args.batch
     if args.no_tc:
         os.environ["VBX_TC"] = "0"
-    if args.impl == "reference":
+    if args.sweep:
+        conv_sweep(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), s
     assert sorted(_lib.SIGNATURES) == syms
-    assert lib.vbx_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.vbx_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_ops_refuse_cpu_tensors():
@@ -322,9 +322,12 @@ def test_bench_keeps_stdout_for_the_one_json_line(tmp_path):
     assert p.returncode == 0, p.stderr
     assert json.loads(p.stdout) == {"metric": "x", "value": 1.5}
     assert "C stdio banner" in p.stderr and "python noise" in p.stderr and "raw fd1 noise" in p.stderr
-    q = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--cpu-batch", "1",
-                        "--seconds", "0.5", "--cpu-steps", "1"], capture_output=True, text=True, timeout=600)
+    q = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--batch", "1",
+                        "--seconds", "0.5", "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600)
     assert q.returncode == 0, q.stderr
     line = json.loads(q.stdout)
     assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["unit"] == "audio-s/s"
+    # the reference arm runs the SAME workload as the GPU arm (same batch, same --steps / --warmup) and says so
+    assert line["steps"] == 2 and line["warmup"] == 1 and line["config"]["batch_per_gpu"] == 1
+    assert line["cpu_baseline"]["batch"] == 1 and "bs=1x0.5s" in line["config"]["workload"]
