@@ -102,6 +102,20 @@ VBX_API int vbx_tc_conv1d_dgrad(const vbx_conv_desc* d, const float* dy, const v
                         float* dx, int32_t nsplit, void* stream);
 /* dw += sum dy*x on tensor cores (both operands gathered from the fp32 activations; nothing packed) */
 VBX_API int vbx_tc_conv1d_wgrad(const vbx_conv_desc* d, const float* x, const float* dy, float* dw, void* stream);
+/* ---- fused ResidualUnit forward (eben_generator.py:287-316: x + LeakyReLU(pointwise_conv(dilated_conv(x)))) ----
+ * ONE persistent kernel per unit: x (B,C,T) is read once through a 3-D TMA tensor map, both convs run on tcgen05
+ * (bf16x3, the dilated conv's accumulator is re-split in place as the pointwise conv's operand), LeakyReLU + the
+ * residual (taken from the fp32 tile in shared memory) ride in the epilogue, `out` is written once.
+ * Supported: C in {16, 32, 48, 64}, T % 4 == 0, 1 <= dil <= 16, T > dil, k = 3 / k = 1, no bias (the generator's C = 32
+ * and C = 64 stages; vbx_ru_supported says so; other shapes use the two-launch form above).
+ * w_dil (C,C,3) and w_pw (C,C,1) are the effective (weight-normed) weights; vbx_ru_pack turns them into the
+ * resident shared-memory image (vbx_ru_pack_bytes bytes).  h / mask (optional, may be NULL) are what the existing
+ * backward kernels consume: h = dilated_conv(x) fp32, mask = pre-activation > 0 (1 byte). */
+VBX_API int vbx_ru_supported(int32_t B, int32_t C, int32_t T, int32_t dil);
+VBX_API int64_t vbx_ru_pack_bytes(int32_t C);
+VBX_API int vbx_ru_pack(int32_t C, const float* w_dil, const float* w_pw, void* packed, void* stream);
+VBX_API int vbx_ru_fwd(int32_t B, int32_t C, int32_t T, int32_t dil, float slope, const float* x, const void* packed,
+               float* out, float* h, uint8_t* mask, void* stream);
 /* W[co][ci_g][k] -> Wt[g][ci_g][co_g][k]  (layout for vbx_conv1d_dgrad) */
 VBX_API int vbx_transpose_weight(const float* w, float* wt, int32_t Cout, int32_t Cin_g, int32_t K,
                          int32_t groups, void* stream);

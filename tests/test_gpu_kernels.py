@@ -440,3 +440,78 @@ def test_persistent_slab_many_tiles_per_cta_matches_fma(case):
     dx = ops.tc_conv1d_dgrad(dy, ops.tc_pack(w, g, ops.TC_DGRAD), g, Tin)
     dx0 = ops.conv1d_dgrad(dy, ops.transpose_weight(w, groups), g, Tin)
     assert float((dx - dx0).norm() / dx0.norm()) < 2e-5
+
+
+RU_CASES = [  # B, C, T, dilation
+    (3, 32, 1000, 1), (3, 32, 1000, 3), (3, 32, 1000, 9), (2, 64, 516, 9), (2, 64, 1280, 3), (5, 16, 132, 1),
+    (2, 48, 300, 9), (1, 32, 40, 9), (4, 64, 128, 1), (7, 32, 388, 3), (32, 32, 11968, 3), (32, 64, 5984, 9),
+]
+
+
+@pytest.mark.parametrize("case", RU_CASES, ids=str)
+def test_fused_residual_unit_matches_fp64_and_the_two_kernel_form(case):
+    """vbx_ru_fwd (one kernel per ResidualUnit: TMA tile load, dilated conv -> TMEM -> re-split -> pointwise conv ->
+    LeakyReLU + residual) vs torch fp64 (eben_generator.py:314-316) and vs the two-launch tensor-core form: out, the
+    saved h = dilated(x) and the activation mask.  Covers edge tiles (reflect halo on both sides, T < 128, T not a
+    multiple of 128), every ring wrap (many tiles per CTA at the full BASELINE sizes) and C = 16..64."""
+    from vibravox_b200 import ops
+    B, C, T, d = case
+    assert ops.use_fused_unit(C, T, d, B)
+    torch.manual_seed(sum(case))
+    x = torch.randn(B, C, T)
+    w1 = torch.randn(C, C, 3) / (3 * C) ** 0.5
+    w2 = torch.randn(C, C, 1) / C ** 0.5
+    if B * C * T <= 4e6:
+        x64 = x.double()
+        h64 = F.conv1d(F.pad(x64, (d, d), mode="reflect"), w1.double(), None, 1, 0, d)
+        z64 = F.conv1d(h64, w2.double())
+        want = x64 + F.leaky_relu(z64, 0.01)
+    else:
+        x64 = want = None
+    xc, w1c, w2c = cuda(x, w1, w2)
+    pk = ops.residual_unit_pack(w1c, w2c)
+    out, h, mask = ops.residual_unit_fwd(xc, pk, d, 0.01, want_h=True, want_mask=True)
+    out_inf, h_none, mask_none = ops.residual_unit_fwd(xc, pk, d, 0.01)
+    assert h_none is None and mask_none is None and torch.equal(out, out_inf)
+    g1, g2 = ops.ConvGeom(C, C, 3, 1, d, d, d, 1), ops.ConvGeom(C, C, 1, 1, 1, 0, 0, 1)
+    h2 = ops.conv_fwd(xc, w1c, g1)
+    out2, mask2 = ops.conv_fwd(h2, w2c, g2, res=xc, slope=0.01, want_mask=True)
+    # same operand split, same MMA order: the two forms agree to fp32 accumulation-order noise
+    assert (h - h2).abs().max() <= 2e-5 * float(h2.abs().max())
+    assert (out - out2).abs().max() <= 2e-5 * float(out2.abs().max())
+    assert (mask != mask2).float().mean() < 1e-4
+    if want is not None:
+        assert (h.cpu().double() - h64).norm() / h64.norm() < 1e-4
+        assert (out.cpu().double() - want).norm() / want.norm() < 2e-5
+        assert (out.cpu().double() - want).abs().max() < 1e-4 * float(want.abs().max())
+        assert (mask.cpu().bool() != (z64 > 0)).float().mean() < 1e-3
+    # repeated launches on the same buffers are bit-identical (no read of a stale ring slot, no race)
+    out3, _, _ = ops.residual_unit_fwd(xc, pk, d, 0.01)
+    assert torch.equal(out, out3)
+
+
+def test_fused_residual_unit_through_autograd_matches_the_unfused_module():
+    """ResidualUnitFn with the fused forward (+ saved h / mask) gives the gradients of the two-launch form."""
+    from vibravox_b200 import ops
+    from vibravox_b200.functional import ResidualUnitFn
+    torch.manual_seed(3)
+    B, C, T, d = 2, 32, 700, 3
+    x = torch.randn(B, C, T, device=DEV, requires_grad=True)
+    w1 = (torch.randn(C, C, 3, device=DEV) / (3 * C) ** 0.5).requires_grad_(True)
+    w2 = (torch.randn(C, C, 1, device=DEV) / C ** 0.5).requires_grad_(True)
+    g1, g2 = ops.ConvGeom(C, C, 3, 1, d, d, d, 1), ops.ConvGeom(C, C, 1, 1, 1, 0, 0, 1)
+    go = torch.randn(B, C, T, device=DEV)
+    res = {}
+    for fused in (True, False):
+        old, ops.FUSED_UNIT = ops.FUSED_UNIT, fused
+        try:
+            y = ResidualUnitFn.apply(x, w1, ops.transpose_weight(w1.detach(), 1), w2, ops.transpose_weight(w2.detach(), 1),
+                                     g1, g2, 0.01)
+            res[fused] = (y.detach(),) + torch.autograd.grad(y, (x, w1, w2), go)
+        finally:
+            ops.FUSED_UNIT = old
+    for a, b in zip(res[True], res[False]):
+        assert (a - b).abs().max() <= 5e-5 * float(b.abs().max())
+    with torch.no_grad():                       # inference: no h / mask are produced at all
+        y = ResidualUnitFn.apply(x, w1, None, w2, None, g1, g2, 0.01)
+        assert (y - res[True][0]).abs().max() == 0

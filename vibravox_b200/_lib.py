@@ -49,6 +49,10 @@ SIGNATURES = {
     "vbx_tc_conv1d_fwd": [_PD, c_p, c_p, _PE, c_p, c_int, c_p],
     "vbx_tc_conv1d_dgrad": [_PD, c_p, c_p, _PE, c_p, c_int, c_p],
     "vbx_tc_conv1d_wgrad": [_PD, c_p, c_p, c_p, c_p],
+    "vbx_ru_supported": [c_int, c_int, c_int, c_int],
+    "vbx_ru_pack_bytes": [c_int],
+    "vbx_ru_pack": [c_int, c_p, c_p, c_p, c_p],
+    "vbx_ru_fwd": [c_int, c_int, c_int, c_int, c_f, c_p, c_p, c_p, c_p, c_p, c_p],
     "vbx_transpose_weight": [c_p, c_p, c_int, c_int, c_int, c_int, c_p],
     "vbx_weight_norm_fwd": [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p],
     "vbx_weight_norm_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_f, c_p],
@@ -82,7 +86,7 @@ SIGNATURES = {
     "vbx_noise_mix_crop": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p],
 }
 _RESTYPES = {"vbx_last_error": ctypes.c_char_p, "vbx_launch_count": ctypes.c_uint64,
-             "vbx_tc_pack_bytes": ctypes.c_int64}
+             "vbx_tc_pack_bytes": ctypes.c_int64, "vbx_ru_pack_bytes": ctypes.c_int64}
 
 
 class VbxError(RuntimeError):

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvbx_b200.so")
-SOURCES = ["conv.cu", "direct_conv.cu", "misc.cu", "tc_conv.cu"]
+SOURCES = ["conv.cu", "direct_conv.cu", "misc.cu", "tc_conv.cu", "ru_fused.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
               "--extended-lambda", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

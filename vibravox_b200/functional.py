@@ -162,8 +162,17 @@ class ResidualUnitFn(Function):
     def forward(ctx, x: Tensor, w1: Tensor, wt1: Tensor, w2: Tensor, wt2: Tensor, g1: ConvGeom, g2: ConvGeom,
                 slope: float):
         x = _c(x)
-        h = ops.conv_fwd(x, w1, g1)
-        out, mask = ops.conv_fwd(h, w2, g2, res=x, slope=slope, want_mask=True)
+        B, C, T = x.shape
+        fused = (g1.K == 3 and g1.stride == 1 and g1.groups == 1 and g1.refl == g1.pad == g1.dil and g2.K == 1
+                 and g1.Cin == g1.Cout == g2.Cin == g2.Cout == C and ops.use_fused_unit(C, T, g1.dil, B))
+        if fused:
+            # one kernel: x read once, out written once; h / mask only when a backward pass will need them
+            train = any(ctx.needs_input_grad)
+            pk = ops.residual_unit_pack(_c(w1), _c(w2))
+            out, h, mask = ops.residual_unit_fwd(x, pk, g1.dil, slope, want_h=train, want_mask=train)
+        else:
+            h = ops.conv_fwd(x, w1, g1)
+            out, mask = ops.conv_fwd(h, w2, g2, res=x, slope=slope, want_mask=True)
         ctx.g1, ctx.g2, ctx.slope = g1, g2, slope
         ctx.save_for_backward(x, h, mask, wt1, wt2, w1, w2)
         return out

@@ -182,6 +182,41 @@ def tc_conv1d_wgrad(x: Tensor, dy: Tensor, g: ConvGeom, dw: Optional[Tensor] = N
     return dw
 
 
+# ------------------------------------------------------------------ fused residual unit
+FUSED_UNIT = os.environ.get("VBX_FUSED_UNIT", "1") != "0"
+
+
+def use_fused_unit(C: int, T: int, dil: int, B: int = 1) -> bool:
+    """Whether ResidualUnit(C) on a (B, C, T) input runs as the single fused kernel (include/vbx.h: vbx_ru_fwd)."""
+    if not (TC_ENABLED and FUSED_UNIT):
+        return False
+    return bool(_lib.load().vbx_ru_supported(B, C, T, dil))
+
+
+def residual_unit_pack(w_dil: Tensor, w_pw: Tensor) -> Tensor:
+    C = w_dil.shape[0]
+    assert tuple(w_dil.shape) == (C, C, 3) and tuple(w_pw.shape) == (C, C, 1), (w_dil.shape, w_pw.shape)
+    nbytes = _lib.load().vbx_ru_pack_bytes(C)
+    if nbytes <= 0:
+        raise _lib.VbxError("vbx_ru_pack_bytes: unsupported channel count")
+    packed = torch.empty((nbytes,), device=w_dil.device, dtype=torch.uint8)
+    check(_lib.load().vbx_ru_pack(C, _p(w_dil), _p(w_pw), packed.data_ptr(), _stream()), "vbx_ru_pack")
+    return packed
+
+
+def residual_unit_fwd(x: Tensor, packed: Tensor, dil: int, slope: float, want_h: bool = False,
+                      want_mask: bool = False):
+    """out = x + LeakyReLU(pointwise(dilated(x))) in one launch; optionally also h = dilated(x) and the 1-byte
+    activation mask (what the backward kernels read)."""
+    B, C, T = x.shape
+    out = torch.empty_like(x)
+    h = torch.empty_like(x) if want_h else None
+    mask = torch.empty(x.shape, device=x.device, dtype=torch.uint8) if want_mask else None
+    check(_lib.load().vbx_ru_fwd(B, C, T, dil, float(slope), _p(x), packed.data_ptr(), _p(out), _p(h),
+                                 _p(mask, torch.uint8), _stream()), "vbx_ru_fwd")
+    return out, h, mask
+
+
 def transpose_weight(w: Tensor, groups: int) -> Tensor:
     Cout, Cin_g, K = w.shape
     wt = torch.empty_like(w)
