@@ -102,10 +102,13 @@ __global__ void __launch_bounds__(256) weight_norm_bwd_kernel(const float* __res
 // ------------------------------------------------------------------ PQMF
 // analysis: 256 band-rate outputs per block; the input span is staged in shared
 // memory in polyphase order (phase-major) so that thread t reads consecutive words.
-template <bool PER_BAND>
+// M, N: decimation / taps known at compile time (the reference's bank is 4 x 32: pqmf.py:26-64, eben_generator.py:101)
+// so the phase arithmetic (k % m, k / m) folds into the unrolled tap loop; 0 = run-time values (any other bank).
+template <bool PER_BAND, int M, int N>
 __global__ void __launch_bounds__(256) pqmf_analysis_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                     float* __restrict__ y, int L, int T, int m, int n, int bands) {
+                                     float* __restrict__ y, int L, int T, int m_rt, int n_rt, int bands) {
   extern __shared__ float sm[];
+  const int m = M ? M : m_rt, n = N ? N : n_rt;
   const int TT = 256;
   const int QL = TT + (n + m - 1) / m + 1;          // words per phase
   float* ws = sm;                                   // [bands][n]
@@ -128,7 +131,12 @@ __global__ void __launch_bounds__(256) pqmf_analysis_kernel(const float* __restr
     if (t < T) {
       for (int c = (PER_BAND ? c0 : 0); c < (PER_BAND ? c0 + 1 : bands); ++c) {
         float acc = 0.f;
-        for (int k = 0; k < n; ++k) acc = fmaf(ws[c * n + k], xs[(k % m) * QL + threadIdx.x + k / m], acc);
+        if (N) {
+#pragma unroll
+          for (int k = 0; k < (N ? N : 1); ++k) acc = fmaf(ws[c * n + k], xs[(k % m) * QL + threadIdx.x + k / m], acc);
+        } else {
+          for (int k = 0; k < n; ++k) acc = fmaf(ws[c * n + k], xs[(k % m) * QL + threadIdx.x + k / m], acc);
+        }
         y[((long long)b * bands + c) * T + t] = acc;
       }
     }
@@ -136,10 +144,12 @@ __global__ void __launch_bounds__(256) pqmf_analysis_kernel(const float* __restr
 }
 
 // synthesis: 1024 full-rate outputs per block (4 per thread, stride 256 for coalescing).
+template <int M, int N>
 __global__ void __launch_bounds__(256) pqmf_synthesis_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                      float* __restrict__ y, int T, int L, int m, int n, int bands,
+                                      float* __restrict__ y, int T, int L, int m_rt, int n_rt, int bands,
                                       int sum_bands) {
   extern __shared__ float sm[];
+  const int m = M ? M : m_rt, n = N ? N : n_rt;
   const int UU = 1024;
   const int J = (n + m - 1) / m;                    // taps per phase (upper bound)
   const int QL = UU / m + J + 2;
@@ -161,8 +171,13 @@ __global__ void __launch_bounds__(256) pqmf_synthesis_kernel(const float* __rest
     float tot = 0.f;
     for (int c = 0; c < bands; ++c) {
       float acc = 0.f;
-      int j = 0;
-      for (int k = ph; k < n; k += m, ++j) acc = fmaf(ws[c * n + k], xs[c * QL + tq - j], acc);
+      if (M && N) {
+#pragma unroll
+        for (int j = 0; j < (M && N ? N / (M ? M : 1) : 1); ++j) acc = fmaf(ws[c * n + ph + j * m], xs[c * QL + tq - j], acc);
+      } else {
+        int j = 0;
+        for (int k = ph; k < n; k += m, ++j) acc = fmaf(ws[c * n + k], xs[c * QL + tq - j], acc);
+      }
       if (sum_bands) tot += acc;
       else y[((long long)b * bands + c) * L + u] = acc;
     }
@@ -605,8 +620,11 @@ extern "C" int vbx_pqmf_analysis(const float* x, const float* w, float* y, int32
   size_t smem = sizeof(float) * ((size_t)bands * n + (size_t)m * QL);
   VBX_REQUIRE(smem <= 48 * 1024, VBX_UNSUPPORTED, "pqmf_analysis: filter bank too large for shared memory");
   dim3 grid(cdiv(T, 256), B);
-  if (x_per_band) pqmf_analysis_kernel<true><<<grid, 256, smem, ST>>>(x, w, y, L, T, m, n, bands);
-  else pqmf_analysis_kernel<false><<<grid, 256, smem, ST>>>(x, w, y, L, T, m, n, bands);
+  if (m == 4 && n == 32) {
+    if (x_per_band) pqmf_analysis_kernel<true, 4, 32><<<grid, 256, smem, ST>>>(x, w, y, L, T, m, n, bands);
+    else pqmf_analysis_kernel<false, 4, 32><<<grid, 256, smem, ST>>>(x, w, y, L, T, m, n, bands);
+  } else if (x_per_band) pqmf_analysis_kernel<true, 0, 0><<<grid, 256, smem, ST>>>(x, w, y, L, T, m, n, bands);
+  else pqmf_analysis_kernel<false, 0, 0><<<grid, 256, smem, ST>>>(x, w, y, L, T, m, n, bands);
   return launched("pqmf_analysis_kernel");
 }
 extern "C" int vbx_pqmf_synthesis(const float* x, const float* w, float* y, int32_t B, int32_t T, int32_t L,
@@ -618,7 +636,8 @@ extern "C" int vbx_pqmf_synthesis(const float* x, const float* w, float* y, int3
   size_t smem = sizeof(float) * ((size_t)bands * n + (size_t)bands * QL);
   VBX_REQUIRE(smem <= 48 * 1024, VBX_UNSUPPORTED, "pqmf_synthesis: filter bank too large for shared memory");
   dim3 grid(cdiv(L, 1024), B);
-  pqmf_synthesis_kernel<<<grid, 256, smem, ST>>>(x, w, y, T, L, m, n, bands, sum_bands);
+  if (m == 4 && n == 32) pqmf_synthesis_kernel<4, 32><<<grid, 256, smem, ST>>>(x, w, y, T, L, m, n, bands, sum_bands);
+  else pqmf_synthesis_kernel<0, 0><<<grid, 256, smem, ST>>>(x, w, y, T, L, m, n, bands, sum_bands);
   return launched("pqmf_synthesis_kernel");
 }
 

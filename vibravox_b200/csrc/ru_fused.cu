@@ -2,8 +2,10 @@
 //     out = x + LeakyReLU_slope( W_pw (1x1) * ( W_dil (k3, dilation d, reflect halo d) * x ) )
 // as ONE persistent kernel: x is read from HBM once, `out` is written once; the intermediate `h` never leaves the SM.
 //
-//   TMA      one thread streams the fp32 tile x[b, 0:C, t0-d : t0+128+d] into a shared-memory ring with ONE 3-D tensor-map
-//            copy per tile (cp.async.bulk.tensor: out-of-range columns arrive as zeros, nothing is gathered by threads);
+//   TMA      one thread streams the fp32 tile x[b, 0:C, t0-dA : t0+128+dA] (dA = d rounded up to 4 samples: the box must
+//            start on a 16-byte boundary of the row - an unaligned or negative start traps, measured with
+//            tools/tma_probe.cu - so the first tile of an item starts at 0) into a shared-memory ring with ONE 3-D
+//            tensor-map copy per tile (cp.async.bulk.tensor: columns beyond T arrive as zeros, nothing is gathered by threads);
 //   convert  4 warps turn the raw tile into the K-major bf16 hi/lo slab of tc_slab.cuh ([position][8 channels] units; the
 //            three taps of the dilated conv are the SAME slab read through descriptors advanced by k*d units) and fold the
 //            reflect halo in by reading the mirrored column of the raw tile;
@@ -34,12 +36,14 @@ static const int kSmemLimit = 227 * 1024;
 struct RuP {
   int B, C, T, d;
   int Wpos;         // 128 + 2d positions staged per tile
-  int Wraw;         // Wpos rounded up to a multiple of 4 (16-byte rows of the raw tile)
+  int dA;           // d rounded up to a multiple of 4: the raw tile starts at max(t0 - dA, 0) (16-byte aligned box start)
+  int Wraw;         // 128 + 2 dA columns of the raw tile
   int ncg;          // C / 16
   int tpi;          // 128-row tiles per batch item
   int ntiles;
   int NR, NA;       // ring depths: raw tiles / slabs
   int tmem_cols;
+  int dbg;          // VBX_RU_DBG bit mask (bring-up only): 1 no tensormap prefetch, 2 no tensor load, 4 no MMAs, 8 / 16 no TMEM loads in mid / epilogue
   float slope;
   const unsigned char* packed;
   float* out;
@@ -107,7 +111,7 @@ __global__ void __launch_bounds__(kThreads, 2) ru_fwd_kernel(const __grid_consta
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0 && my_tiles > 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_x)) : "memory");
+      if (!(P.dbg & 1)) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_x)) : "memory");
       mbar_expect_tx(w_full, (uint32_t)w_bytes);
       for (int off = 0; off < w_bytes; off += 32768) {
         const int n = w_bytes - off < 32768 ? w_bytes - off : 32768;
@@ -119,8 +123,10 @@ __global__ void __launch_bounds__(kThreads, 2) ru_fwd_kernel(const __grid_consta
         mbar_wait(&raw_free[s], par ^ 1u);
         const int tile = (int)blockIdx.x + i * (int)gridDim.x;
         const int b = tile / P.tpi, t0 = (tile % P.tpi) * kRows;
+        if (P.dbg & 2) { mbar_arrive(&raw_full[s]); continue; }
         mbar_expect_tx(&raw_full[s], (uint32_t)raw_bytes);
-        tma_load_3d(raw0 + (size_t)s * raw_bytes, &tmap_x, &raw_full[s], t0 - d, 0, b);
+        const int start = t0 - P.dA > 0 ? t0 - P.dA : 0;
+        tma_load_3d(raw0 + (size_t)s * raw_bytes, &tmap_x, &raw_full[s], start, 0, b);
       }
     }
   } else if (warp == 1) {
@@ -141,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, 2) ru_fwd_kernel(const __grid_consta
             const uint32_t abase = smem_u32(ab0 + (size_t)sa * ab_bytes);
             const uint32_t dcol = tmem_base + (uint32_t)((n1 & 1) * C);
             uint32_t acc = 0;
-            for (int cg = 0; cg < ncg; ++cg) {
+            for (int cg = 0; cg < ((P.dbg & 4) ? 0 : ncg); ++cg) {
               const uint32_t a_cg = abase + (uint32_t)cg * (uint32_t)Wpos * 64u;
 #pragma unroll
               for (int tap = 0; tap < 3; ++tap) {
@@ -168,7 +174,7 @@ __global__ void __launch_bounds__(kThreads, 2) ru_fwd_kernel(const __grid_consta
             const uint32_t abase = smem_u32(ab0 + (size_t)sa * ab_bytes);
             const uint32_t dcol = tmem_base + (uint32_t)(2 * C + j * C);
             uint32_t acc = 0;
-            for (int cg = 0; cg < ncg; ++cg) {
+            for (int cg = 0; cg < ((P.dbg & 4) ? 0 : ncg); ++cg) {
               const uint32_t a_hi = abase + (uint32_t)cg * 8192u;
               const uint32_t b_hi = w2base + (uint32_t)cg * tile_b;
               const uint64_t da_hi = make_desc(a_hi, 2048, 128), da_lo = make_desc(a_hi + 4096u, 2048, 128);
@@ -199,16 +205,18 @@ __global__ void __launch_bounds__(kThreads, 2) ru_fwd_kernel(const __grid_consta
       const float* raw = reinterpret_cast<const float*>(raw0 + (size_t)sr * raw_bytes);
       unsigned char* ab = ab0 + (size_t)sa * ab_bytes;
       const bool edge = t0 - d < 0 || t0 + kRows + d > P.T;
+      const int start = t0 - P.dA > 0 ? t0 - P.dA : 0;      // time of raw column 0
+      const int col0 = t0 - d - start;                      // raw column of slab position 0 (negative on the first tile)
       int u = ct, c8 = 0;
       while (u >= Wpos) { u -= Wpos; ++c8; }
       for (int it = ct; it < nitems; it += 128) {
-        int us = u;
+        int us = col0 + u;
         if (edge) {                             // mirror (no edge repeat): t -> -t, t -> 2(T-1) - t
           int t = t0 - d + u;
           if (t < 0) t = -t;
           else if (t >= P.T) t = 2 * (P.T - 1) - t;
-          us = t - t0 + d;
-          us = us < 0 ? 0 : (us >= Wpos ? Wpos - 1 : us);   // (rows beyond T + d are never stored)
+          us = t - start;
+          us = us < 0 ? 0 : (us >= Wraw ? Wraw - 1 : us);   // (rows beyond T + d are never stored)
         }
         const float* src = raw + (size_t)(c8 * 8) * Wraw + us;
         float v[8];
@@ -247,7 +255,12 @@ __global__ void __launch_bounds__(kThreads, 2) ru_fwd_kernel(const __grid_consta
       float* hp = P.h ? P.h + ((size_t)b * C) * P.T + t0 + m : nullptr;
       for (int cg = 0; cg < ncg; ++cg) {
         float v[16];
-        tmem_ld16(dcol + (uint32_t)(cg * 16), v);
+        if (P.dbg & 8) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = 0.f;
+        } else {
+          tmem_ld16(dcol + (uint32_t)(cg * 16), v);
+        }
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -281,13 +294,19 @@ __global__ void __launch_bounds__(kThreads, 2) ru_fwd_kernel(const __grid_consta
       const int b = tile / P.tpi, t0 = (tile % P.tpi) * kRows;
       mbar_wait(&mma2_done[sa], (uint32_t)((i / NA) & 1));
       tc_fence_after();
-      const float* raw = reinterpret_cast<const float*>(raw0 + (size_t)sr * raw_bytes) + d + m;
+      const int start = t0 - P.dA > 0 ? t0 - P.dA : 0;
+      const float* raw = reinterpret_cast<const float*>(raw0 + (size_t)sr * raw_bytes) + (t0 - start) + m;
       const uint32_t dcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * C + j * C);
       const bool ev = t0 + m < P.T;
       const size_t o = ((size_t)b * C) * P.T + t0 + m;
       for (int cg = 0; cg < ncg; ++cg) {
         float v[16];
-        tmem_ld16(dcol + (uint32_t)(cg * 16), v);
+        if (P.dbg & 16) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = 0.f;
+        } else {
+          tmem_ld16(dcol + (uint32_t)(cg * 16), v);
+        }
         if (cg == ncg - 1) {                    // D2[j] drained: the pointwise conv of tile i+2 may overwrite it
           tc_fence_before();
           warp_arrive(&d2_free[j], lane);
@@ -364,7 +383,8 @@ static bool plan(RuP& P, int B, int C, int T, int d) {
   if (C % 16 || C < 16 || C > 64 || T % 4 || d < 1 || d > 16 || T < d + 1 || B < 1) return false;
   P.B = B; P.C = C; P.T = T; P.d = d;
   P.Wpos = kRows + 2 * d;
-  P.Wraw = (P.Wpos + 3) & ~3;
+  P.dA = (d + 3) & ~3;
+  P.Wraw = kRows + 2 * P.dA;
   P.ncg = C / 16;
   P.tpi = (T + kRows - 1) / kRows;
   if ((long long)B * P.tpi >= (1ll << 31) || (long long)B * C * T >= (1ll << 31)) return false;
@@ -433,6 +453,8 @@ extern "C" int vbx_ru_fwd(int32_t B, int32_t C, int32_t T, int32_t dil, float sl
     snprintf(g_err, sizeof(g_err), "ru_fwd: cuTensorMapEncodeTiled failed (CUresult %d)", (int)cr);
     return VBX_UNSUPPORTED;
   }
+  static const int dbg = getenv("VBX_RU_DBG") ? atoi(getenv("VBX_RU_DBG")) : 0;
+  P.dbg = dbg;
   P.slope = slope; P.packed = (const unsigned char*)packed; P.out = out; P.h = h; P.mask = mask;
   static bool attr_set = false;
   if (!attr_set) {

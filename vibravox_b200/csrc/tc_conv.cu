@@ -363,8 +363,8 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const TcP P) {
         for (int j = 0; j < 16; ++j) yp[(long long)j * Tlen] = acc[j];
         continue;
       }
-#pragma unroll 1
-      for (int j = 0; j < 16; ++j) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {                      // (unrolled: acc[] stays in registers, no local-memory frame)
         const int col = cb + j;
         if (col < Ccol) {
           const long long idx = out_base + (long long)col * Tlen;

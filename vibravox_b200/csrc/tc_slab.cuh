@@ -90,8 +90,8 @@ __device__ __forceinline__ void slab_epilogue(const TcP& P, uint32_t tmem_base, 
       for (int j = 0; j < 16; ++j) yp[(long long)j * Tlen] = acc[j];
       continue;
     }
-#pragma unroll 1
-    for (int j = 0; j < 16; ++j) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {                        // (unrolled: acc[] stays in registers, no local-memory frame)
       const int col = cb + j;
       if (col < Ccol) {
         const long long idx = out_base + (long long)col * Tlen;
