@@ -114,6 +114,9 @@ VBX_API int vbx_tc_conv1d_wgrad(const vbx_conv_desc* d, const float* x, const fl
 VBX_API int vbx_ru_supported(int32_t B, int32_t C, int32_t T, int32_t dil);
 VBX_API int64_t vbx_ru_pack_bytes(int32_t C);
 VBX_API int vbx_ru_pack(int32_t C, const float* w_dil, const float* w_pw, void* packed, void* stream);
+/* bring-up / profiling hook: when buf != NULL (device memory, >= 16 * tiles-per-CTA int64) CTA 0 of the next
+ * vbx_ru_fwd launches records clock64() per (tile, pipeline event); NULL switches it off (tools/ru_timeline.py) */
+VBX_API int vbx_ru_set_profile_buffer(void* buf);
 VBX_API int vbx_ru_fwd(int32_t B, int32_t C, int32_t T, int32_t dil, float slope, const float* x, const void* packed,
                float* out, float* h, uint8_t* mask, void* stream);
 /* W[co][ci_g][k] -> Wt[g][ci_g][co_g][k]  (layout for vbx_conv1d_dgrad) */

@@ -52,6 +52,7 @@ SIGNATURES = {
     "vbx_ru_supported": [c_int, c_int, c_int, c_int],
     "vbx_ru_pack_bytes": [c_int],
     "vbx_ru_pack": [c_int, c_p, c_p, c_p, c_p],
+    "vbx_ru_set_profile_buffer": [c_p],
     "vbx_ru_fwd": [c_int, c_int, c_int, c_int, c_f, c_p, c_p, c_p, c_p, c_p, c_p],
     "vbx_transpose_weight": [c_p, c_p, c_int, c_int, c_int, c_int, c_p],
     "vbx_weight_norm_fwd": [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p],

@@ -9,8 +9,12 @@
 //   convert  4 warps turn the raw tile into the K-major bf16 hi/lo slab of tc_slab.cuh ([position][8 channels] units; the
 //            three taps of the dilated conv are the SAME slab read through descriptors advanced by k*d units) and fold the
 //            reflect halo in by reading the mirrored column of the raw tile;
-//   MMA      one thread issues tcgen05.mma (bf16 x bf16 -> fp32 in TMEM, three products per operand pair: hi*hi + hi*lo +
-//            lo*hi) for the dilated conv into D1, later for the pointwise conv into D2, whichever operand is ready first;
+//   MMA      one thread issues tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) for the dilated conv into D1, later for the
+//            pointwise conv into D2, whichever operand is ready first.  The three products of the split (hi*hi + hi*lo +
+//            lo*hi) take TWO instructions per (16-channel group, tap): the weight tile holds [W_hi | W_lo] side by side as
+//            2C columns, so x_hi * [W_hi | W_lo] is one N = 2C MMA and x_lo * W_hi one N = C MMA onto the first C
+//            columns; the consumer adds the two column halves (fewer instructions for the issuing thread and a third
+//            fewer shared-memory reads of the A operand - both measured as the kernel's limiter);
 //   mid      4 warps read D1 (tcgen05.ld), split it into bf16 hi/lo and store it as the A operand of the pointwise conv
 //            over the slab that the first conv has finished reading;
 //   epilogue 4 warps read D2, apply LeakyReLU, add the residual from the RAW fp32 tile still in shared memory (exact, and
@@ -30,7 +34,9 @@ namespace ru {
 using namespace vbx::tc;
 
 static const int kRows = 128;
-static const int kThreads = 448;            // warps: 0 TMA, 1 MMA, 2-5 convert, 6-9 mid, 10-13 epilogue
+// warps of a CTA: 0 TMA, 1 MMA, then CW convert warps, MW mid warps, EW epilogue warps (4 or 8 each: 4 when two CTAs
+// share an SM, 8 when the CTA owns it - two warps per TMEM lane quadrant then split the 16-channel groups)
+__host__ __device__ constexpr int ru_threads(int CW, int MW, int EW) { return (2 + CW + MW + EW) * 32; }
 static const int kSmemLimit = 227 * 1024;
 
 struct RuP {
@@ -43,13 +49,18 @@ struct RuP {
   int ntiles;
   int NR, NA;       // ring depths: raw tiles / slabs
   int tmem_cols;
-  int dbg;          // VBX_RU_DBG bit mask (bring-up only): 1 no tensormap prefetch, 2 no tensor load, 4 no MMAs, 8 / 16 no TMEM loads in mid / epilogue
+  int wait_ns;      // suspend-time hint of the mbarrier waits (VBX_RU_WAIT_NS, 0 = plain spin)
   float slope;
+  int res_global;   // 1: the epilogue re-reads the residual from global memory (L2) and the raw tile is released
+                    //    right after the conversion (shallow raw rings, C = 64); 0: residual from the raw tile
+  const float* x;
   const unsigned char* packed;
   float* out;
   float* h;         // optional
   unsigned char* mask;   // optional
+  long long* prof;  // optional (vbx_ru_set_profile_buffer): CTA 0 records clock64() per tile and pipeline event
 };
+#define RU_PROF(ev) do { if (P.prof && blockIdx.x == 0 && lane == 0) P.prof[(i) * 16 + (ev)] = clock64(); } while (0)
 
 __host__ __device__ inline int ru_w_bytes(int C) { return (C / 16) * 4 * C * 64; }       // W1 (3 taps) + W2, hi + lo
 __host__ __device__ inline int ru_raw_bytes(const RuP& P) { return P.C * P.Wraw * 4; }
@@ -71,9 +82,31 @@ __device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
   if (lane == 0) mbar_arrive(bar);
 }
 
-__global__ void __launch_bounds__(kThreads, 2) ru_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const RuP P) {
+// v = D[cols a .. a+15] + D[cols b .. b+15] of this thread's TMEM lane: both loads are issued before the one wait
+__device__ __forceinline__ void tmem_ld16_sum2(uint32_t ta, uint32_t tb, float* v) {
+  uint32_t r[16], q[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(ta)
+      : "memory");
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+        "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
+      : "r"(tb)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(q[i]);
+}
+
+template <int CW, int MW, int EW, int MINB>
+__global__ void __launch_bounds__(ru_threads(CW, MW, EW), MINB) ru_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const RuP P) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t wns = (uint32_t)P.wait_ns;
   const int C = P.C, d = P.d, Wpos = P.Wpos, Wraw = P.Wraw, ncg = P.ncg, NR = P.NR, NA = P.NA;
   const int w_bytes = ru_w_bytes(C), raw_bytes = ru_raw_bytes(P), ab_bytes = ru_ab_bytes(P);
   unsigned char* w0 = smem;
@@ -93,11 +126,13 @@ __global__ void __launch_bounds__(kThreads, 2) ru_fwd_kernel(const __grid_consta
   const int my_tiles = ((int)blockIdx.x < P.ntiles) ? (P.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (tid == 0) {
-    for (int i = 0; i < NR; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_free[i], 4); }
-    for (int i = 0; i < NA; ++i) {
-      mbar_init(&a1_full[i], 4); mbar_init(&mma1_done[i], 1); mbar_init(&a2_full[i], 4); mbar_init(&mma2_done[i], 1);
+    for (int i = 0; i < NR; ++i) {             // released by the epilogue warps, or by the convert warps (res_global)
+      mbar_init(&raw_full[i], 1); mbar_init(&raw_free[i], P.res_global ? CW : EW);
     }
-    mbar_init(&d2_free[0], 4); mbar_init(&d2_free[1], 4);
+    for (int i = 0; i < NA; ++i) {
+      mbar_init(&a1_full[i], CW); mbar_init(&mma1_done[i], 1); mbar_init(&a2_full[i], MW); mbar_init(&mma2_done[i], 1);
+    }
+    mbar_init(&d2_free[0], EW); mbar_init(&d2_free[1], EW);
     mbar_init(w_full, 1);
     fence_barrier_init();
   }
@@ -106,12 +141,12 @@ __global__ void __launch_bounds__(kThreads, 2) ru_fwd_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: D1[j] at j*C, D2[j] at 2C + j*C   (j = tile parity)
+  // TMEM columns: D1[j] at j*2C, D2[j] at 4C + j*2C   (j = tile parity; each accumulator is [x_hi W_hi + x_lo W_hi | x_hi W_lo])
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0 && my_tiles > 0) {
-      if (!(P.dbg & 1)) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_x)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_x)) : "memory");
       mbar_expect_tx(w_full, (uint32_t)w_bytes);
       for (int off = 0; off < w_bytes; off += 32768) {
         const int n = w_bytes - off < 32768 ? w_bytes - off : 32768;
@@ -120,88 +155,114 @@ __global__ void __launch_bounds__(kThreads, 2) ru_fwd_kernel(const __grid_consta
       for (int i = 0; i < my_tiles; ++i) {
         const int s = i % NR;
         const uint32_t par = (uint32_t)((i / NR) & 1);
-        mbar_wait(&raw_free[s], par ^ 1u);
+        mbar_wait_hint(&raw_free[s], par ^ 1u, wns);
         const int tile = (int)blockIdx.x + i * (int)gridDim.x;
         const int b = tile / P.tpi, t0 = (tile % P.tpi) * kRows;
-        if (P.dbg & 2) { mbar_arrive(&raw_full[s]); continue; }
         mbar_expect_tx(&raw_full[s], (uint32_t)raw_bytes);
         const int start = t0 - P.dA > 0 ? t0 - P.dA : 0;
+        RU_PROF(0);
         tma_load_3d(raw0 + (size_t)s * raw_bytes, &tmap_x, &raw_full[s], start, 0, b);
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0 && my_tiles > 0) {
-      const uint32_t idesc = make_idesc_bf16(C, /*a_mn=*/false, /*b_mn=*/false);
-      const uint32_t lbo_a1 = (uint32_t)Wpos * 16, lbo_b = (uint32_t)C * 16;
-      const uint32_t plane_a1 = (uint32_t)Wpos * 32, plane_b = (uint32_t)C * 32, tile_b = (uint32_t)C * 64;
-      const uint32_t wbase = smem_u32(w0), w2base = wbase + (uint32_t)ncg * 3u * tile_b;
-      mbar_wait(w_full, 0);
+    // ===================== MMA issuer =====================
+    // The whole warp walks the (warp-uniform) control flow so that the descriptor arithmetic stays in uniform
+    // registers; lane 0 alone issues tcgen05.mma / commit.  A descriptor is a constant 64-bit pattern plus the
+    // operand address >> 4 in its low bits (all offsets are multiples of 16 bytes, addresses < 256 KB: no carry into
+    // the stride fields), so per MMA it costs a 32-bit add instead of being rebuilt - measured: with the descriptors
+    // rebuilt per MMA by one thread, this warp was the bottleneck of the whole CTA.
+    if (my_tiles > 0) {
+      const uint32_t idesc2 = make_idesc_bf16(2 * C, /*a_mn=*/false, /*b_mn=*/false);   // x_hi * [W_hi | W_lo]
+      const uint32_t idesc1 = make_idesc_bf16(C, /*a_mn=*/false, /*b_mn=*/false);       // x_lo * W_hi
+      const uint32_t lbo_a1 = (uint32_t)Wpos * 16, lbo_b = (uint32_t)C * 32;
+      const uint32_t wbase = smem_u32(w0);
+      // low / high words of the descriptors at offset 0 of each operand region
+      const uint64_t dA1 = make_desc(0, lbo_a1, 128), dA2 = make_desc(0, 2048, 128), dB = make_desc(0, lbo_b, 128);
+      const uint32_t a1_hi32 = (uint32_t)(dA1 >> 32), a1_lo32 = (uint32_t)dA1;
+      const uint32_t a2_hi32 = (uint32_t)(dA2 >> 32), a2_lo32 = (uint32_t)dA2;
+      const uint32_t b_hi32 = (uint32_t)(dB >> 32), b_lo32 = (uint32_t)dB + (wbase >> 4);
+      const uint32_t pa1 = (uint32_t)Wpos * 2, tb = (uint32_t)C * 4;   // lo plane of the slab / weight tile, in 16-byte units
+      const uint32_t w2u = (uint32_t)ncg * 3u * tb;
+      auto mk = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; };
+      // warp-uniform copy of the TMEM base (a value loaded from shared memory lives in a vector register, and a
+      // vector-register operand makes ptxas wrap every tcgen05.mma in an ELECT / R2UR / branch "waterfall" of ~10
+      // dependent instructions; a warp reduction result is uniform by construction)
+      const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem_base);
+      mbar_wait_hint(w_full, 0, wns);
       int n1 = 0, n2 = 0;                       // next tile of the dilated / pointwise conv
       while (n2 < my_tiles) {
         bool did = false;
         if (n1 < my_tiles && n1 - n2 < 2) {     // (D1 / D2 are two deep)
           const int sa = n1 % NA;
-          if (mbar_try_wait(&a1_full[sa], (uint32_t)((n1 / NA) & 1))) {
+          if (mbar_test_wait(&a1_full[sa], (uint32_t)((n1 / NA) & 1))) {
             tc_fence_after();
-            const uint32_t abase = smem_u32(ab0 + (size_t)sa * ab_bytes);
-            const uint32_t dcol = tmem_base + (uint32_t)((n1 & 1) * C);
-            uint32_t acc = 0;
-            for (int cg = 0; cg < ((P.dbg & 4) ? 0 : ncg); ++cg) {
-              const uint32_t a_cg = abase + (uint32_t)cg * (uint32_t)Wpos * 64u;
+            const uint32_t dcol = tmem_u + (uint32_t)((n1 & 1) * 2 * C);
+            uint32_t a_u = a1_lo32 + (smem_u32(ab0 + (size_t)sa * ab_bytes) >> 4);
+            uint32_t b_u = b_lo32;
+            if (lane == 0) {
+              uint32_t acc = 0;
+              for (int cg = 0; cg < ncg; ++cg) {
 #pragma unroll
-              for (int tap = 0; tap < 3; ++tap) {
-                const uint32_t a_hi = a_cg + (uint32_t)(tap * d) * 16u;
-                const uint32_t b_hi = wbase + (uint32_t)(cg * 3 + tap) * tile_b;
-                const uint64_t da_hi = make_desc(a_hi, lbo_a1, 128), da_lo = make_desc(a_hi + plane_a1, lbo_a1, 128);
-                const uint64_t db_hi = make_desc(b_hi, lbo_b, 128), db_lo = make_desc(b_hi + plane_b, lbo_b, 128);
-                mma_bf16_ss(dcol, da_hi, db_hi, idesc, acc);
-                acc = 1;
-                mma_bf16_ss(dcol, da_hi, db_lo, idesc, 1);
-                mma_bf16_ss(dcol, da_lo, db_hi, idesc, 1);
+                for (int tap = 0; tap < 3; ++tap) {
+                  const uint32_t at = a_u + (uint32_t)(tap * d);
+                  const uint64_t db = mk(b_hi32, b_u);
+                  mma_bf16_ss(dcol, mk(a1_hi32, at), db, idesc2, acc);
+                  acc = 1;
+                  mma_bf16_ss(dcol, mk(a1_hi32, at + pa1), db, idesc1, 1);
+                  b_u += tb;
+                }
+                a_u += (uint32_t)Wpos * 4;
               }
+              mma_commit(&mma1_done[sa]);
+              { const int i = n1; RU_PROF(4); }
             }
-            mma_commit(&mma1_done[sa]);
+            __syncwarp();
             ++n1;
             did = true;
           }
         }
         if (n2 < n1) {
           const int sa = n2 % NA, j = n2 & 1;
-          if (mbar_try_wait(&a2_full[sa], (uint32_t)((n2 / NA) & 1))) {
-            if (n2 >= 2) mbar_wait(&d2_free[j], (uint32_t)(((n2 >> 1) - 1) & 1));
+          if (mbar_test_wait(&a2_full[sa], (uint32_t)((n2 / NA) & 1))) {
+            if (n2 >= 2) mbar_wait_hint(&d2_free[j], (uint32_t)(((n2 >> 1) - 1) & 1), wns);
             tc_fence_after();
-            const uint32_t abase = smem_u32(ab0 + (size_t)sa * ab_bytes);
-            const uint32_t dcol = tmem_base + (uint32_t)(2 * C + j * C);
-            uint32_t acc = 0;
-            for (int cg = 0; cg < ((P.dbg & 4) ? 0 : ncg); ++cg) {
-              const uint32_t a_hi = abase + (uint32_t)cg * 8192u;
-              const uint32_t b_hi = w2base + (uint32_t)cg * tile_b;
-              const uint64_t da_hi = make_desc(a_hi, 2048, 128), da_lo = make_desc(a_hi + 4096u, 2048, 128);
-              const uint64_t db_hi = make_desc(b_hi, lbo_b, 128), db_lo = make_desc(b_hi + plane_b, lbo_b, 128);
-              mma_bf16_ss(dcol, da_hi, db_hi, idesc, acc);
-              acc = 1;
-              mma_bf16_ss(dcol, da_hi, db_lo, idesc, 1);
-              mma_bf16_ss(dcol, da_lo, db_hi, idesc, 1);
+            const uint32_t dcol = tmem_u + (uint32_t)(4 * C + j * 2 * C);
+            uint32_t a_u = a2_lo32 + (smem_u32(ab0 + (size_t)sa * ab_bytes) >> 4);
+            uint32_t b_u = b_lo32 + w2u;
+            if (lane == 0) {
+              uint32_t acc = 0;
+              for (int cg = 0; cg < ncg; ++cg) {
+                const uint64_t db = mk(b_hi32, b_u);
+                mma_bf16_ss(dcol, mk(a2_hi32, a_u), db, idesc2, acc);
+                acc = 1;
+                mma_bf16_ss(dcol, mk(a2_hi32, a_u + 256u), db, idesc1, 1);
+                a_u += 512u;
+                b_u += tb;
+              }
+              mma_commit(&mma2_done[sa]);
+              { const int i = n2; RU_PROF(7); }
             }
-            mma_commit(&mma2_done[sa]);
+            __syncwarp();
             ++n2;
             did = true;
           }
         }
-        if (!did) __nanosleep(32);
+        if (!did) __nanosleep(20);
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + CW) {
     // ===================== convert: raw fp32 tile -> K-major bf16 hi/lo slab (+ reflect halo) =====================
-    const int ct = tid - 64;                    // 0..127
+    const int ct = tid - 64;                    // 0 .. CW*32-1
+    constexpr int kCT = CW * 32;
     const int nitems = (C / 8) * Wpos;          // (8-channel unit, position)
     for (int i = 0; i < my_tiles; ++i) {
       const int sr = i % NR, sa = i % NA;
       const int tile = (int)blockIdx.x + i * (int)gridDim.x;
       const int t0 = (tile % P.tpi) * kRows;
-      if (i >= NA) mbar_wait(&mma2_done[sa], (uint32_t)(((i / NA) - 1) & 1));     // slab free again
-      mbar_wait(&raw_full[sr], (uint32_t)((i / NR) & 1));
+      if (i >= NA) mbar_wait_hint(&mma2_done[sa], (uint32_t)(((i / NA) - 1) & 1), wns);     // slab free again
+      if (warp == 2) RU_PROF(1);
+      mbar_wait_hint(&raw_full[sr], (uint32_t)((i / NR) & 1), wns);
+      if (warp == 2) RU_PROF(2);
       const float* raw = reinterpret_cast<const float*>(raw0 + (size_t)sr * raw_bytes);
       unsigned char* ab = ab0 + (size_t)sa * ab_bytes;
       const bool edge = t0 - d < 0 || t0 + kRows + d > P.T;
@@ -209,7 +270,7 @@ __global__ void __launch_bounds__(kThreads, 2) ru_fwd_kernel(const __grid_consta
       const int col0 = t0 - d - start;                      // raw column of slab position 0 (negative on the first tile)
       int u = ct, c8 = 0;
       while (u >= Wpos) { u -= Wpos; ++c8; }
-      for (int it = ct; it < nitems; it += 128) {
+      for (int it = ct; it < nitems; it += kCT) {
         int us = col0 + u;
         if (edge) {                             // mirror (no edge repeat): t -> -t, t -> 2(T-1) - t
           int t = t0 - d + u;
@@ -234,33 +295,32 @@ __global__ void __launch_bounds__(kThreads, 2) ru_fwd_kernel(const __grid_consta
         unsigned char* dst = ab + (size_t)(c8 >> 1) * Wpos * 64 + (size_t)(c8 & 1) * Wpos * 16 + (size_t)u * 16;
         *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(dst + (size_t)Wpos * 32) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        u += 128;
+        u += kCT;
         while (u >= Wpos) { u -= Wpos; ++c8; }
       }
       fence_proxy_async();
       warp_arrive(&a1_full[sa], lane);
+      if (P.res_global) warp_arrive(&raw_free[sr], lane);     // (the epilogue will not touch the raw tile)
+      if (warp == 2) RU_PROF(3);
     }
-  } else if (warp < 10) {
+  } else if (warp < 2 + CW + MW) {
     // ===================== mid: D1 -> bf16 hi/lo A operand of the pointwise conv (+ optional h) =====================
     const int q = warp & 3, m = q * 32 + lane;
+    const int mset = (warp - (2 + CW)) >> 2;    // 0, or 0 / 1 when two warps share a lane quadrant
     for (int i = 0; i < my_tiles; ++i) {
       const int sa = i % NA;
       const int tile = (int)blockIdx.x + i * (int)gridDim.x;
       const int b = tile / P.tpi, t0 = (tile % P.tpi) * kRows;
-      mbar_wait(&mma1_done[sa], (uint32_t)((i / NA) & 1));
+      mbar_wait_hint(&mma1_done[sa], (uint32_t)((i / NA) & 1), wns);
       tc_fence_after();
+      if (warp == 2 + CW) RU_PROF(5);
       unsigned char* ab = ab0 + (size_t)sa * ab_bytes;
-      const uint32_t dcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((i & 1) * C);
+      const uint32_t dcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((i & 1) * 2 * C);
       const bool hv = P.h != nullptr && t0 + m < P.T;
       float* hp = P.h ? P.h + ((size_t)b * C) * P.T + t0 + m : nullptr;
-      for (int cg = 0; cg < ncg; ++cg) {
+      for (int cg = mset; cg < ncg; cg += MW / 4) {
         float v[16];
-        if (P.dbg & 8) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = 0.f;
-        } else {
-          tmem_ld16(dcol + (uint32_t)(cg * 16), v);
-        }
+        tmem_ld16_sum2(dcol + (uint32_t)(cg * 16), dcol + (uint32_t)(C + cg * 16), v);
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -283,37 +343,42 @@ __global__ void __launch_bounds__(kThreads, 2) ru_fwd_kernel(const __grid_consta
       fence_proxy_async();
       tc_fence_before();
       warp_arrive(&a2_full[sa], lane);
+      if (warp == 2 + CW) RU_PROF(6);
     }
   } else {
     // ===================== epilogue: D2 -> LeakyReLU -> + x (raw tile) -> out =====================
     const int q = warp & 3, m = q * 32 + lane;
+    const int eset = (warp - (2 + CW + MW)) >> 2;
     const float slope = P.slope;
     for (int i = 0; i < my_tiles; ++i) {
       const int sr = i % NR, sa = i % NA, j = i & 1;
       const int tile = (int)blockIdx.x + i * (int)gridDim.x;
       const int b = tile / P.tpi, t0 = (tile % P.tpi) * kRows;
-      mbar_wait(&mma2_done[sa], (uint32_t)((i / NA) & 1));
+      mbar_wait_hint(&mma2_done[sa], (uint32_t)((i / NA) & 1), wns);
       tc_fence_after();
+      if (warp == 2 + CW + MW) RU_PROF(8);
       const int start = t0 - P.dA > 0 ? t0 - P.dA : 0;
       const float* raw = reinterpret_cast<const float*>(raw0 + (size_t)sr * raw_bytes) + (t0 - start) + m;
-      const uint32_t dcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * C + j * C);
+      const uint32_t dcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(4 * C + j * 2 * C);
       const bool ev = t0 + m < P.T;
+      const float* xres = P.x + ((size_t)b * C) * P.T + t0 + m;
       const size_t o = ((size_t)b * C) * P.T + t0 + m;
-      for (int cg = 0; cg < ncg; ++cg) {
+      const int cg_last = ncg - 1 - ((ncg - 1 - eset) % (EW / 4));     // last group this warp handles
+      for (int cg = eset; cg < ncg; cg += EW / 4) {
         float v[16];
-        if (P.dbg & 16) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = 0.f;
-        } else {
-          tmem_ld16(dcol + (uint32_t)(cg * 16), v);
-        }
-        if (cg == ncg - 1) {                    // D2[j] drained: the pointwise conv of tile i+2 may overwrite it
+        tmem_ld16_sum2(dcol + (uint32_t)(cg * 16), dcol + (uint32_t)(C + cg * 16), v);
+        if (cg == cg_last) {                    // D2[j] drained: the pointwise conv of tile i+2 may overwrite it
           tc_fence_before();
           warp_arrive(&d2_free[j], lane);
         }
         float r[16];
+        if (P.res_global) {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) r[e] = raw[(size_t)(cg * 16 + e) * Wraw];
+          for (int e = 0; e < 16; ++e) r[e] = ev ? __ldg(xres + (size_t)(cg * 16 + e) * P.T) : 0.f;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) r[e] = raw[(size_t)(cg * 16 + e) * Wraw];
+        }
         if (ev) {
           if (P.mask) {
             unsigned char* mp = P.mask + o + (size_t)(cg * 16) * P.T;
@@ -325,7 +390,8 @@ __global__ void __launch_bounds__(kThreads, 2) ru_fwd_kernel(const __grid_consta
           for (int e = 0; e < 16; ++e) yp[(size_t)e * P.T] = (v[e] > 0.f ? v[e] : v[e] * slope) + r[e];
         }
       }
-      warp_arrive(&raw_free[sr], lane);
+      if (!P.res_global) warp_arrive(&raw_free[sr], lane);
+      if (warp == 2 + CW + MW) RU_PROF(9);
     }
   }
   tc_fence_before();
@@ -333,8 +399,9 @@ __global__ void __launch_bounds__(kThreads, 2) ru_fwd_kernel(const __grid_consta
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
 }
 
-// Weight pre-pack: one thread per 16-byte unit (8 consecutive input channels of one output channel and tap).
-// Blob = W1 tiles [16-channel group][tap] then W2 tiles [16-channel group]; tile = [hi|lo][half][n][8] (C*64 bytes).
+// Weight pre-pack: one thread per (8 consecutive input channels of one output channel and tap) -> two 16-byte units.
+// Blob = W1 tiles [16-channel group][tap] then W2 tiles [16-channel group]; tile = [half][2C rows][8] (C*64 bytes) with
+// rows 0..C-1 = bf16 hi of output channel n, rows C..2C-1 = bf16 lo of output channel n - C.
 __global__ void ru_pack_kernel(const float* __restrict__ w1, const float* __restrict__ w2, unsigned char* __restrict__ out,
                                int C) {
   const int ncg = C / 16;
@@ -354,9 +421,9 @@ __global__ void ru_pack_kernel(const float* __restrict__ w1, const float* __rest
       split_bf16(v, hi[e], lo[e]);
     }
     unsigned char* tile = out + (size_t)ti * C * 64;
-    const size_t off = ((size_t)hf * C + n) * 16;
+    const size_t off = ((size_t)hf * 2 * C + n) * 16;
     *reinterpret_cast<uint4*>(tile + off) = *reinterpret_cast<const uint4*>(hi);
-    *reinterpret_cast<uint4*>(tile + (size_t)C * 32 + off) = *reinterpret_cast<const uint4*>(lo);
+    *reinterpret_cast<uint4*>(tile + (size_t)C * 16 + off) = *reinterpret_cast<const uint4*>(lo);
   }
 }
 
@@ -401,8 +468,10 @@ static bool plan(RuP& P, int B, int C, int T, int d) {
       const size_t lim = pass == 0 ? (size_t)(kSmemLimit / 2 - 1024) : (size_t)kSmemLimit;
       if (ru_smem_bytes(P) <= lim) {
         int cols = 32;
-        while (cols < 4 * C) cols <<= 1;
+        while (cols < 8 * C) cols <<= 1;
         P.tmem_cols = cols;
+        static const int env_rg = getenv("VBX_RU_RESG") ? atoi(getenv("VBX_RU_RESG")) : -1;
+        P.res_global = env_rg >= 0 ? env_rg : (P.NR < 3 ? 1 : 0);
         return true;
       }
     }
@@ -415,6 +484,9 @@ static bool plan(RuP& P, int B, int C, int T, int d) {
 
 using namespace vbx;
 using namespace vbx::ru;
+
+static long long* g_ru_prof = nullptr;
+extern "C" int vbx_ru_set_profile_buffer(void* buf) { g_ru_prof = (long long*)buf; return 0; }
 
 extern "C" int vbx_ru_supported(int32_t B, int32_t C, int32_t T, int32_t dil) {
   RuP P;
@@ -453,12 +525,16 @@ extern "C" int vbx_ru_fwd(int32_t B, int32_t C, int32_t T, int32_t dil, float sl
     snprintf(g_err, sizeof(g_err), "ru_fwd: cuTensorMapEncodeTiled failed (CUresult %d)", (int)cr);
     return VBX_UNSUPPORTED;
   }
-  static const int dbg = getenv("VBX_RU_DBG") ? atoi(getenv("VBX_RU_DBG")) : 0;
-  P.dbg = dbg;
+  static const int wait_ns = getenv("VBX_RU_WAIT_NS") ? atoi(getenv("VBX_RU_WAIT_NS")) : 20000;
+  P.wait_ns = wait_ns;
+  P.prof = g_ru_prof;
+  P.x = x;
   P.slope = slope; P.packed = (const unsigned char*)packed; P.out = out; P.h = h; P.mask = mask;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t ce = cudaFuncSetAttribute(ru_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    cudaError_t ce = cudaFuncSetAttribute(ru_fwd_kernel<4, 4, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (ce == cudaSuccess)
+      ce = cudaFuncSetAttribute(ru_fwd_kernel<8, 8, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (ce != cudaSuccess) return fail((int)ce, "ru_fwd: cannot raise the dynamic shared memory limit");
     attr_set = true;
   }
@@ -466,6 +542,10 @@ extern "C" int vbx_ru_fwd(int32_t B, int32_t C, int32_t T, int32_t dil, float sl
   const int occ = smem <= (size_t)(kSmemLimit / 2 - 1024) && 2 * P.tmem_cols <= 512 ? 2 : 1;
   int grid = 148 * occ;
   if (grid > P.ntiles) grid = P.ntiles;
-  ru_fwd_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tm, P);
+  static const int wide = getenv("VBX_RU_WIDE") ? atoi(getenv("VBX_RU_WIDE")) : 1;
+  if (occ == 1 && wide && P.ncg >= 2)        // the CTA owns the SM: twice the warps per pipeline stage
+    ru_fwd_kernel<8, 8, 8, 1><<<grid, ru_threads(8, 8, 8), smem, (cudaStream_t)stream>>>(tm, P);
+  else
+    ru_fwd_kernel<4, 4, 4, 2><<<grid, ru_threads(4, 4, 4), smem, (cudaStream_t)stream>>>(tm, P);
   return launched("ru_fwd_kernel");
 }
