@@ -307,6 +307,8 @@ TC_CASES = [
     # narrow groups densified into one block-diagonal conv (MelGAN stage 1, PQMF-discriminator stages 1-2, odd group counts)
     (2, 16, 64, 1203, 41, 4, 1, 20, 0, 4), (2, 24, 48, 533, 7, 2, 1, 3, 0, 4), (3, 12, 36, 222, 5, 1, 1, 2, 0, 3),
     (2, 48, 96, 300, 7, 2, 1, 3, 0, 4),
+    # two row tiles per CTA (wide N, long reduction): odd tile count, last pair half empty
+    (3, 256, 256, 700, 41, 4, 1, 20, 0, 1), (2, 512, 256, 300, 5, 1, 1, 2, 0, 1),
 ]
 
 

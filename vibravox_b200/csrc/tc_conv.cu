@@ -59,6 +59,7 @@ struct TcP {
   int sl_tpb;       // taps per weight stage
   int sl_nbst;      // weight stages per channel group = ceil(K / sl_tpb)
   int sl_SA, sl_SB; // ring depths: slab stages / weight stages
+  int sl_rt;        // 128-row tiles per CTA of the streaming slab kernel (1, or 2: two accumulators share every weight tile)
   // Densified groups (slab form only): a grouped conv whose groups are narrower than the 16-channel reduction unit
   // runs as ONE dense conv over all channels against block-diagonal packed weights.  The MMAs are far from the
   // bound on such layers; what counts is that every input position is staged once per tile instead of once per
@@ -577,7 +578,7 @@ static bool use_merged(const GemmP& G) {
 // Slab form: forward-style problems (incl. merged-phase input gradients) with >= 2 taps whose reduction has enough
 // channels for 16-wide groups, when everything a producer thread indexes fits 32 bits and the rings fit shared memory.
 static size_t slab_smem_bytes(const TcP& P) {
-  return (size_t)P.sl_SA * slab_a_stage(P.g) + (size_t)P.sl_SB * slab_b_stage(P.NT, P.sl_tpb) +
+  return (size_t)P.sl_SA * slab_a_stage(P.g, P.sl_rt) + (size_t)P.sl_SB * slab_b_stage(P.NT, P.sl_tpb) +
          (2 * P.sl_SA + 2 * P.sl_SB + 1) * sizeof(uint64_t) + 16 + (size_t)P.g.K * sizeof(int) + 16;
 }
 static size_t pslab_smem_bytes(const TcP& P, int slots) {
@@ -624,6 +625,7 @@ static void plan_slab(TcP& P, const vbx_conv_desc* d) {
   const int R = G.Tout - 1 + ((G.K - 1) * G.dil + 1 + G.stride - 1) / G.stride;
   if ((long long)d->B * R * G.stride + 2048 >= (1ll << 31) || (long long)d->B * G.Cin * G.Tin >= (1ll << 31)) return;
   P.sl_R = R;
+  P.sl_rt = 1;
   P.sl_ncg = (G.Cin_g + 15) / 16;
   int tpb = 16384 / (P.NT * 64);
   if (tpb < 1) tpb = 1;
@@ -639,6 +641,22 @@ static void plan_slab(TcP& P, const vbx_conv_desc* d) {
   }
   P.slab = 1;
   plan_pslab(P);
+  if (!P.ps && !P.merged) {
+    // Two row tiles per CTA where the kernel is bound by streaming weight tiles from L2 (see tc_slab_kernel): forward
+    // layers with a long reduction whose single-tile form already owns the SM (> half the shared memory), so nothing
+    // is lost in CTAs per SM.  Measured (MelGAN stage 4 forward, alone): 0.52 -> 0.34 ms.  NOT for the merged-phase
+    // input gradients (scattered epilogue stores: they need a second CTA per SM to hide the drain; 347 -> 400 us) and
+    // not for short-K layers that fit two CTAs per SM (1024 -> 1024 k5: 170 -> 460 us when halved to 96 CTAs).
+    static const int rt2_min = getenv("VBX_TC_SLAB_RT2_MIN") ? atoi(getenv("VBX_TC_SLAB_RT2_MIN")) : 96;   // 0: off
+    const long long row_tiles = ((long long)d->B * R + kRows - 1) / kRows;
+    if (rt2_min > 0 && P.NT >= 128 && 2 * pow2_cols(P.NT) <= 512 && P.sl_ncg * G.K >= rt2_min && row_tiles >= 2 &&
+        slab_smem_bytes(P) > 113 * 1024 && slab_npos(G, 2) <= kSlabMaxU * kProducers) {
+      TcP Q = P;
+      Q.sl_rt = 2;
+      if (slab_smem_bytes(Q) > 200 * 1024) { Q.sl_SB = total_b < 2 ? total_b : 2; }
+      if (slab_smem_bytes(Q) <= 200 * 1024) { P.sl_rt = 2; P.sl_SB = Q.sl_SB; }
+    }
+  }
 }
 
 static void densify(GemmP& g) { g.groups = 1; g.Cin_g = g.Cin; g.Cout_g = g.Cout; }
@@ -667,6 +685,7 @@ static int fill_tc_geom(TcP& P, const vbx_conv_desc* d, int mode, int nsplit, bo
   P.nsplit = nsplit;
   P.merged = 0;
   P.slab = 0;
+  P.sl_rt = 1;
   P.ps = 0;
   if (mode == DGRAD && P.g.refl == 0 && P.g.stride <= 8) {
     // Zero-halo input gradient as a stride-1 forward conv over dy (Cout ch, Tout long) -> D (s*Cin ch, V long):
@@ -752,9 +771,12 @@ static int launch_slab(const TcP& P, cudaStream_t st) {
     attr_set = true;
   }
   const long long rows = (long long)P.g.B * P.sl_R;
-  dim3 grid((unsigned)((rows + kRows - 1) / kRows), (unsigned)(P.ntiles_n * P.g.groups), 1);
+  const int per = kRows * P.sl_rt;
+  dim3 grid((unsigned)((rows + per - 1) / per), (unsigned)(P.ntiles_n * P.g.groups), 1);
   if (grid.y > 65535) return fail(VBX_UNSUPPORTED, "tc_slab: grid too large");
-  tc_slab_kernel<<<grid, kThreads, slab_smem_bytes(P), st>>>(P);
+  TcP Q = P;
+  Q.tmem_cols = P.sl_rt * pow2_cols(P.NT);
+  tc_slab_kernel<<<grid, kThreads, slab_smem_bytes(P), st>>>(Q);
   return launched("tc_slab_kernel");
 }
 

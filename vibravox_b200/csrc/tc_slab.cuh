@@ -17,9 +17,11 @@
 
 static const int kSlabMaxU = 5;             // positions a producer thread stages per channel group
 
-__host__ __device__ inline int slab_npos(const GemmP& G) { return (kRows - 1) * G.stride + (G.K - 1) * G.dil + 1; }
-__host__ __device__ inline int slab_U(const GemmP& G) { return kRows + ((G.K - 1) * G.dil) / G.stride + 1; }
-__host__ __device__ inline int slab_a_stage(const GemmP& G) { return 64 * G.stride * slab_U(G); }   // 2 planes x 2 halves
+// rt = row tiles (128 rows each) a CTA of the streaming kernel works on at once: their positions are adjacent on the
+// virtual timeline, so ONE slab of rt*128 rows (+ the shared tap overhang) serves rt accumulators - see tc_slab_kernel
+__host__ __device__ inline int slab_npos(const GemmP& G, int rt = 1) { return (kRows * rt - 1) * G.stride + (G.K - 1) * G.dil + 1; }
+__host__ __device__ inline int slab_U(const GemmP& G, int rt = 1) { return kRows * rt + ((G.K - 1) * G.dil) / G.stride + 1; }
+__host__ __device__ inline int slab_a_stage(const GemmP& G, int rt = 1) { return 64 * G.stride * slab_U(G, rt); }   // 2 planes x 2 halves
 __host__ __device__ inline int slab_b_stage(int NT, int tpb) { return tpb * NT * 64; }
 
 // Epilogue of one 128-row tile: the eight producer warps read the accumulator (warp & 3 = TMEM lane quadrant,
@@ -101,13 +103,18 @@ __device__ __forceinline__ void slab_epilogue(const TcP& P, uint32_t tmem_base, 
   }
 }
 
+// Wide tiles (N >= 128 with long reductions) are bound by the weight tiles they stream from L2: 16 KB per tap and
+// 16-channel group against 3 x 128 tensor-core cycles = 43 bytes / cycle / SM, i.e. ~12 TB/s over 148 SMs - more
+// than L2 delivers (measured: tensor pipe 66 % active).  With sl_rt = 2 a CTA owns TWO adjacent 128-row tiles: one
+// slab of 256 rows, two accumulators in TMEM, and every weight tile that arrives feeds 6 MMAs instead of 3 - half
+// the L2 -> SM weight traffic per MMA.
 __global__ void __launch_bounds__(kThreads, 3) tc_slab_kernel(const TcP P) {
   extern __shared__ __align__(128) unsigned char smem[];
   const GemmP& G = P.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int NT = P.NT, SA = P.sl_SA, SB = P.sl_SB, s = G.stride;
-  const int U = slab_U(G);
-  const int a_stage = slab_a_stage(G), b_stage = slab_b_stage(NT, P.sl_tpb);
+  const int NT = P.NT, SA = P.sl_SA, SB = P.sl_SB, s = G.stride, rt = P.sl_rt;
+  const int U = slab_U(G, rt);
+  const int a_stage = slab_a_stage(G, rt), b_stage = slab_b_stage(NT, P.sl_tpb);
   const int plane_a = a_stage / 2, half_a = plane_a / 2;      // hi / lo planes; channels 0-7 / 8-15 inside a plane
   unsigned char* a0 = smem;
   unsigned char* b0 = smem + (size_t)SA * a_stage;
@@ -123,7 +130,8 @@ __global__ void __launch_bounds__(kThreads, 3) tc_slab_kernel(const TcP P) {
   const int grp = blockIdx.y / P.ntiles_n, nt = blockIdx.y % P.ntiles_n;
   const int R = P.sl_R, Ppos = R * s;
   const int ncg = P.sl_ncg, nbst = P.sl_nbst, tpb = P.sl_tpb;
-  const int rv0 = blockIdx.x * kRows;                          // first virtual output row of this tile
+  const int rv0 = blockIdx.x * kRows * rt;                     // first virtual output row of this CTA's tile(s)
+  const uint32_t dcols = (uint32_t)P.tmem_cols / (uint32_t)rt; // TMEM columns per accumulator
 
   if (tid == 0) {
     for (int i = 0; i < SA; ++i) { mbar_init(&full_a[i], kProducers); mbar_init(&empty_a[i], 1); }
@@ -143,7 +151,7 @@ __global__ void __launch_bounds__(kThreads, 3) tc_slab_kernel(const TcP P) {
 
   if (warp < 8) {
     // ===================== producers: stage the slab, 16 channels per stage =====================
-    const int npos = slab_npos(G);
+    const int npos = slab_npos(G, rt);
     int goff[kSlabMaxU], soff[kSlabMaxU];                      // per staged position: x offset (or -1) / smem offset
 #pragma unroll
     for (int n = 0; n < kSlabMaxU; ++n) {
@@ -200,7 +208,8 @@ __global__ void __launch_bounds__(kThreads, 3) tc_slab_kernel(const TcP P) {
     // ===================== epilogue =====================
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    slab_epilogue(P, tmem_base, rv0, nt, grp, warp, lane);
+    for (int r = 0; r < rt; ++r)
+      slab_epilogue(P, tmem_base + (uint32_t)r * dcols, rv0 + r * kRows, nt, grp, warp, lane);
   } else if (warp == 8) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
@@ -220,12 +229,15 @@ __global__ void __launch_bounds__(kThreads, 3) tc_slab_kernel(const TcP P) {
           for (int tt = 0; tt < tpb && tap < G.K; ++tt, ++tap) {
             const uint32_t a_hi = abase + (uint32_t)tapoff[tap];
             const uint32_t b_hi = bbase + (uint32_t)tt * (uint32_t)NT * 64u;
-            const uint64_t da_hi = make_desc(a_hi, lbo_a, 128), da_lo = make_desc(a_hi + plane_a, lbo_a, 128);
             const uint64_t db_hi = make_desc(b_hi, lbo_b, 128), db_lo = make_desc(b_hi + plane_bt, lbo_b, 128);
-            mma_bf16_ss(tmem_base, da_hi, db_hi, idesc, accumulate);
+            for (int r = 0; r < rt; ++r) {                     // row tile r: the same slab, 128 rows (units) further on
+              const uint32_t ar = a_hi + (uint32_t)r * (uint32_t)(kRows * 16), dr = tmem_base + (uint32_t)r * dcols;
+              const uint64_t da_hi = make_desc(ar, lbo_a, 128), da_lo = make_desc(ar + plane_a, lbo_a, 128);
+              mma_bf16_ss(dr, da_hi, db_hi, idesc, accumulate);
+              mma_bf16_ss(dr, da_hi, db_lo, idesc, 1);
+              mma_bf16_ss(dr, da_lo, db_hi, idesc, 1);
+            }
             accumulate = 1;
-            mma_bf16_ss(tmem_base, da_hi, db_lo, idesc, 1);
-            mma_bf16_ss(tmem_base, da_lo, db_hi, idesc, 1);
           }
           mma_commit(&empty_b[sb]);
           if (++sb == SB) { sb = 0; parb ^= 1u; }
