@@ -119,6 +119,14 @@ VBX_API int vbx_ru_pack(int32_t C, const float* w_dil, const float* w_pw, void* 
 VBX_API int vbx_ru_set_profile_buffer(void* buf);
 VBX_API int vbx_ru_fwd(int32_t B, int32_t C, int32_t T, int32_t dil, float slope, const float* x, const void* packed,
                float* out, float* h, uint8_t* mask, void* stream);
+/* Weight gradient of the residual-unit convs (stride 1, C -> C with C in {32, 64}; K = 3 dilated with reflect halo
+ * `dil`, or K = 1) on the same TMA skeleton: dw[co][ci][k] = beta*dw + sum_{b,t} dy[b,co,t] * x[b,ci,mirror(t+(k-1)*dil)].
+ * Persistent CTAs keep the accumulators in TMEM, write per-CTA partials to `workspace` (vbx_ru_wgrad_workspace bytes,
+ * -1 = unsupported shape) and a second launch sums them in a fixed order: deterministic, no atomics.
+ * Replaces aten::convolution_backward (weight gradient) of eben_generator.py:295-312. */
+VBX_API int64_t vbx_ru_wgrad_workspace(int32_t B, int32_t C, int32_t T, int32_t dil, int32_t K);
+VBX_API int vbx_ru_wgrad(int32_t B, int32_t C, int32_t T, int32_t dil, int32_t K, const float* x, const float* dy,
+                 float* dw, float beta, void* workspace, void* stream);
 /* W[co][ci_g][k] -> Wt[g][ci_g][co_g][k]  (layout for vbx_conv1d_dgrad) */
 VBX_API int vbx_transpose_weight(const float* w, float* wt, int32_t Cout, int32_t Cin_g, int32_t K,
                          int32_t groups, void* stream);

@@ -168,6 +168,10 @@ def use_fused_unit(C, T, dil, B=1):
     return False
 
 
+def unit_wgrad_workspace(B, C, T, dil, K):
+    return -1
+
+
 def set_deterministic(on):
     return False
 

@@ -517,3 +517,38 @@ def test_fused_residual_unit_through_autograd_matches_the_unfused_module():
     with torch.no_grad():                       # inference: no h / mask are produced at all
         y = ResidualUnitFn.apply(x, w1, None, w2, None, g1, g2, 0.01)
         assert (y - res[True][0]).abs().max() == 0
+
+
+WG_CASES = [  # B, C, T, dilation, K
+    (3, 32, 1000, 1, 3), (3, 32, 1000, 3, 3), (3, 32, 1000, 9, 3), (2, 64, 516, 9, 3), (2, 64, 1280, 3, 3),
+    (3, 32, 1000, 1, 1), (2, 64, 516, 1, 1), (1, 32, 40, 9, 3), (7, 32, 388, 3, 3), (32, 32, 11968, 9, 3),
+    (32, 64, 5984, 3, 3), (32, 32, 11968, 1, 1), (32, 64, 5984, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", WG_CASES, ids=str)
+def test_unit_weight_gradient_kernel_matches_fp64(case):
+    """vbx_ru_wgrad (TMA tile loads, time-reduction MMAs with the accumulators resident in TMEM, fixed-order reduction
+    of the per-CTA partials) vs torch fp64 autograd of the reflect-padded conv (eben_generator.py:295-312), incl. edge
+    tiles, T < 128, accumulation onto an existing gradient, and bit-identical repeats (no atomics)."""
+    from vibravox_b200 import ops
+    B, C, T, d, K = case
+    assert ops.unit_wgrad_workspace(B, C, T, d, K) > 0
+    torch.manual_seed(sum(case))
+    x, dy = torch.randn(B, C, T), torch.randn(B, C, T)
+    xc, dyc = cuda(x, dy)
+    dw = ops.unit_wgrad(xc, dyc, K, d)
+    assert torch.equal(dw, ops.unit_wgrad(xc, dyc, K, d))                       # deterministic
+    acc = torch.full((C, C, K), 0.5, device=DEV)
+    assert (ops.unit_wgrad(xc, dyc, K, d, dw=acc) - (dw + 0.5)).abs().max() <= 1e-5 * float(dw.abs().max())
+    pad = d * (K - 1) // 2
+    g = ops.ConvGeom(C, C, K, 1, d if K == 3 else 1, pad, pad, 1)
+    old = ops.tc_conv1d_wgrad(xc, dyc, g)                                         # the gather-form kernel it replaces
+    assert (dw - old).abs().max() <= 1e-4 * float(old.abs().max())
+    if B * C * T <= 4e6:
+        w64 = torch.zeros(C, C, K, dtype=torch.float64, requires_grad=True)
+        xp = F.pad(x.double(), (pad, pad), mode="reflect") if pad else x.double()
+        y = F.conv1d(xp, w64, None, 1, 0, d if K == 3 else 1)
+        (gw,) = torch.autograd.grad(y, w64, dy.double())
+        assert (dw.cpu().double() - gw).abs().max() < 2e-4 * float(gw.abs().max())
+        assert (dw.cpu().double() - gw).norm() / gw.norm() < 1e-4

@@ -54,6 +54,8 @@ SIGNATURES = {
     "vbx_ru_pack": [c_int, c_p, c_p, c_p, c_p],
     "vbx_ru_set_profile_buffer": [c_p],
     "vbx_ru_fwd": [c_int, c_int, c_int, c_int, c_f, c_p, c_p, c_p, c_p, c_p, c_p],
+    "vbx_ru_wgrad_workspace": [c_int, c_int, c_int, c_int, c_int],
+    "vbx_ru_wgrad": [c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_f, c_p, c_p],
     "vbx_transpose_weight": [c_p, c_p, c_int, c_int, c_int, c_int, c_p],
     "vbx_weight_norm_fwd": [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p],
     "vbx_weight_norm_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_f, c_p],
@@ -87,7 +89,8 @@ SIGNATURES = {
     "vbx_noise_mix_crop": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p],
 }
 _RESTYPES = {"vbx_last_error": ctypes.c_char_p, "vbx_launch_count": ctypes.c_uint64,
-             "vbx_tc_pack_bytes": ctypes.c_int64, "vbx_ru_pack_bytes": ctypes.c_int64}
+             "vbx_tc_pack_bytes": ctypes.c_int64, "vbx_ru_pack_bytes": ctypes.c_int64,
+             "vbx_ru_wgrad_workspace": ctypes.c_int64}
 
 
 class VbxError(RuntimeError):

@@ -479,6 +479,238 @@ static bool plan(RuP& P, int B, int C, int T, int d) {
   return false;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight gradient of the residual-unit convs (stride 1, C -> C, K = 3 dilated with reflect halo or K = 1):
+//     dW[co, ci, k] = sum_{b,t} dy[b, co, t] * x[b, ci, mirror(t + (k-1)*d)]
+// on the same skeleton: TMA tensor-map loads of the fp32 x / dy tiles (128 time positions per tile), conversion to
+// bf16 hi/lo slabs [plane][8-channel group][position] (16-byte units, positions 16 bytes apart), which the tensor core
+// reads MN-major with the reduction running over time: per tap D_k[co (M = 128 lanes, the first C real), ci] +=
+// dy_hi * [x_hi | x_lo] (N = 2C) + dy_lo * x_hi (N = C); the x slab serves every tap through the descriptor start
+// address (+ k*d units).  The accumulators stay in TMEM for the whole life of the persistent CTA; at the end each CTA
+// writes its partial dW to a workspace and a second tiny kernel sums the partials in a FIXED order (deterministic,
+// no atomics).  Two issuing threads (taps 0, 2 / tap 1): one thread cannot issue small-N MMAs faster than one per
+// ~76 cycles (profiles/r1_mma_probe.txt) and 48 of them per tile would be the kernel's limiter.
+struct WgP {
+  int B, C, T, d, K;
+  int Wpos, dA, Wraw;   // x slab positions (128 + (K-1)*d), aligned halo, raw x columns
+  int xu, yu;           // 16-byte units between consecutive 8-channel groups of the x / dy slab (odd: conflict-free MMA fetch)
+  int tpi, ntiles, NR, NA, tmem_cols, wait_ns, nissue;
+  float* partial;       // [gridDim.x][C][C][K]
+};
+static const int kWgThreads = 11 * 32;      // warps: 0 TMA, 1-2 MMA issuers, 3-6 convert x, 7-10 convert dy + final drain
+
+__host__ __device__ inline int wg_x_slab(const WgP& P) { return 2 * (P.C / 8) * P.xu * 16; }
+__host__ __device__ inline int wg_y_slab(const WgP& P) { return 2 * (P.C / 8) * P.yu * 16; }
+__host__ __device__ inline int wg_raw(const WgP& P) { return P.C * (P.Wraw + kRows) * 4; }
+static size_t wg_smem_bytes(const WgP& P) {
+  return (size_t)P.NA * (wg_y_slab(P) + wg_x_slab(P)) + (size_t)P.NR * wg_raw(P) + (size_t)(2 * P.NR + 2 * P.NA + 1) * 8 + 16;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(kWgThreads, MINB) ru_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x,
+                                                                     const __grid_constant__ CUtensorMap tmap_dy, const WgP P) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t wns = (uint32_t)P.wait_ns;
+  const int C = P.C, d = P.d, K = P.K, Wpos = P.Wpos, Wraw = P.Wraw, NR = P.NR, NA = P.NA, nc8 = C / 8;
+  const int ysl = wg_y_slab(P), xsl = wg_x_slab(P), rawb = wg_raw(P), rawx = C * Wraw * 4;
+  unsigned char* y0 = smem;                                   // dy slabs first: their M = 128 descriptor reads run past
+  unsigned char* x0 = y0 + (size_t)NA * ysl;                  // the C real channels into whatever follows
+  unsigned char* raw0 = x0 + (size_t)NA * xsl;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(raw0 + (size_t)NR * rawb);
+  uint64_t* raw_full = bars;                 // [NR] TMA bytes (x + dy tile) landed
+  uint64_t* raw_free = raw_full + NR;        // [NR] 8 convert warps done
+  uint64_t* slab_full = raw_free + NR;       // [NA] 8 convert warps: both slabs staged
+  uint64_t* slab_free = slab_full + NA;      // [NA] every issuing thread's MMAs of the tile retired
+  uint64_t* acc_done = slab_free + NA;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+  const int my_tiles = ((int)blockIdx.x < P.ntiles) ? (P.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (tid == 0) {
+    for (int i = 0; i < NR; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_free[i], 8); }
+    for (int i = 0; i < NA; ++i) { mbar_init(&slab_full[i], 8); mbar_init(&slab_free[i], P.nissue); }
+    mbar_init(acc_done, P.nissue);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && my_tiles > 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_x)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_dy)) : "memory");
+      for (int i = 0; i < my_tiles; ++i) {
+        const int s = i % NR;
+        mbar_wait_hint(&raw_free[s], (uint32_t)((i / NR) & 1) ^ 1u, wns);
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        const int b = tile / P.tpi, t0 = (tile % P.tpi) * kRows;
+        const int start = t0 - P.dA > 0 ? t0 - P.dA : 0;
+        mbar_expect_tx(&raw_full[s], (uint32_t)rawb);
+        tma_load_3d(raw0 + (size_t)s * rawb, &tmap_x, &raw_full[s], start, 0, b);
+        tma_load_3d(raw0 + (size_t)s * rawb + rawx, &tmap_dy, &raw_full[s], t0, 0, b);
+      }
+    }
+  } else if (warp < 3) {
+    // ===================== MMA issuers: issuer j takes taps j, j + 2 =====================
+    const int j = warp - 1;
+    if (my_tiles > 0 && j < P.nissue) {
+      const uint32_t idesc2 = make_idesc_bf16(2 * C, /*a_mn=*/true, /*b_mn=*/true);
+      const uint32_t idesc1 = make_idesc_bf16(C, /*a_mn=*/true, /*b_mn=*/true);
+      const uint64_t dY = make_desc(0, 128, (uint32_t)P.yu * 16), dX = make_desc(0, 128, (uint32_t)P.xu * 16);
+      const uint32_t y_hi32 = (uint32_t)(dY >> 32), y_lo32 = (uint32_t)dY, x_hi32 = (uint32_t)(dX >> 32), x_lo32 = (uint32_t)dX;
+      const uint32_t ypl = (uint32_t)(nc8 * P.yu);            // lo plane of the dy slab, in 16-byte units
+      auto mk = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; };
+      const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem_base);
+      for (int i = 0; i < my_tiles; ++i) {
+        const int sa = i % NA;
+        mbar_wait_hint(&slab_full[sa], (uint32_t)((i / NA) & 1), wns);
+        tc_fence_after();
+        const uint32_t yu0 = y_lo32 + (smem_u32(y0 + (size_t)sa * ysl) >> 4);
+        const uint32_t xu0 = x_lo32 + (smem_u32(x0 + (size_t)sa * xsl) >> 4);
+        if (lane == 0) {
+          for (int tap = j; tap < K; tap += 2) {
+            const uint32_t dcol = tmem_u + (uint32_t)(tap * 2 * C);
+            uint32_t yk = yu0, xk = xu0 + (uint32_t)(tap * d);
+#pragma unroll
+            for (int ks = 0; ks < kRows / 16; ++ks) {
+              const uint64_t db = mk(x_hi32, xk);
+              mma_bf16_ss(dcol, mk(y_hi32, yk), db, idesc2, (i > 0 || ks > 0) ? 1u : 0u);
+              mma_bf16_ss(dcol, mk(y_hi32, yk + ypl), db, idesc1, 1);
+              yk += 16; xk += 16;                             // 16 positions = 16 units further on
+            }
+          }
+          mma_commit(&slab_free[sa]);
+          if (i == my_tiles - 1) mma_commit(acc_done);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== convert: x (warps 3-6, reflect halo folded in) / dy (warps 7-10) =====================
+    const bool is_x = warp < 7;
+    const int ct = (warp - (is_x ? 3 : 7)) * 32 + lane;         // 0..127
+    const int npos = is_x ? Wpos : kRows, gu = is_x ? P.xu : P.yu, rw = is_x ? Wraw : kRows;
+    const int nitems = nc8 * npos;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int sr = i % NR, sa = i % NA;
+      const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+      const int t0 = (tile % P.tpi) * kRows;
+      if (i >= NA) mbar_wait_hint(&slab_free[sa], (uint32_t)(((i / NA) - 1) & 1), wns);
+      mbar_wait_hint(&raw_full[sr], (uint32_t)((i / NR) & 1), wns);
+      const float* raw = reinterpret_cast<const float*>(raw0 + (size_t)sr * rawb + (is_x ? 0 : rawx));
+      unsigned char* slab = is_x ? x0 + (size_t)sa * xsl : y0 + (size_t)sa * ysl;
+      const int halo = (K - 1) * d / 2;                          // positions of the x slab start at t0 - halo
+      const bool edge = is_x && (t0 - halo < 0 || t0 + kRows + halo > P.T);
+      const int start = is_x ? (t0 - P.dA > 0 ? t0 - P.dA : 0) : t0;
+      const int col0 = is_x ? t0 - halo - start : 0;
+      int u = ct, c8 = 0;
+      while (u >= npos) { u -= npos; ++c8; }
+      for (int it = ct; it < nitems; it += 128) {
+        int us = col0 + u;
+        if (edge) {
+          int t = t0 - halo + u;
+          if (t < 0) t = -t;
+          else if (t >= P.T) t = 2 * (P.T - 1) - t;
+          us = t - start;
+          us = us < 0 ? 0 : (us >= rw ? rw - 1 : us);
+        }
+        const float* src = raw + (size_t)(c8 * 8) * rw + us;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = src[e * rw];
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+          const float2 hf = __bfloat1622float2(h2);
+          const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+          hi[e] = *reinterpret_cast<const uint32_t*>(&h2);
+          lo[e] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+        unsigned char* dst = slab + ((size_t)c8 * gu + u) * 16;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(dst + (size_t)nc8 * gu * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        u += 128;
+        while (u >= npos) { u -= npos; ++c8; }
+      }
+      fence_proxy_async();
+      warp_arrive(&slab_full[sa], lane);
+      warp_arrive(&raw_free[sr], lane);
+    }
+    // ===================== final drain (dy warps): this CTA's partial dW -> workspace =====================
+    if (!is_x && my_tiles > 0) {
+      const int q = warp & 3, co = q * 32 + lane;
+      if (q * 32 < C) {                                          // (warp-uniform)
+        mbar_wait_hint(acc_done, 0, wns);
+        tc_fence_after();
+        float* dst = P.partial + (size_t)blockIdx.x * C * C * K + (size_t)co * C * K;
+        for (int tap = 0; tap < K; ++tap) {
+          for (int blk = 0; blk < C / 16; ++blk) {
+            float v[16];
+            const uint32_t col = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tap * 2 * C + blk * 16);
+            tmem_ld16_sum2(col, col + (uint32_t)C, v);
+            if (co < C) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) dst[(size_t)(blk * 16 + e) * K + tap] = v[e];
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+}
+
+// dw[i] = beta * dw[i] + sum over CTAs of partial[cta][i], CTAs in a fixed order
+__global__ void ru_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int n, int nparts, float beta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = 0.f;
+  for (int p = 0; p < nparts; ++p) acc += partial[(size_t)p * n + i];
+  dw[i] = beta != 0.f ? beta * dw[i] + acc : acc;
+}
+
+static bool plan_wg(WgP& P, int B, int C, int T, int d, int K, int* grid_out, int* occ_out) {
+  if (C % 32 || C < 32 || C > 64 || T % 4 || (K != 1 && K != 3) || d < 1 || d > 16 || T < d + 1 || B < 1) return false;
+  if (K == 1) d = 1;
+  P.B = B; P.C = C; P.T = T; P.d = d; P.K = K;
+  const int halo = (K - 1) * d / 2;
+  P.Wpos = kRows + 2 * halo;
+  P.dA = (halo + 3) & ~3;
+  P.Wraw = kRows + 2 * P.dA;
+  P.xu = P.Wpos | 1; P.yu = kRows | 1;
+  P.tpi = (T + kRows - 1) / kRows;
+  if ((long long)B * P.tpi >= (1ll << 31) || (long long)B * C * T >= (1ll << 31)) return false;
+  P.ntiles = B * P.tpi;
+  P.nissue = K == 1 ? 1 : 2;
+  int cols = 32;
+  while (cols < 2 * C * K) cols <<= 1;
+  P.tmem_cols = cols;
+  static const int env_nr = getenv("VBX_RUW_NR") ? atoi(getenv("VBX_RUW_NR")) : 0;
+  static const int env_na = getenv("VBX_RUW_NA") ? atoi(getenv("VBX_RUW_NA")) : 0;
+  static const int order[5][2] = {{2, 1}, {3, 2}, {2, 2}, {2, 1}, {0, 0}};     // first entry: two CTAs per SM
+  for (int i = 0; order[i][0]; ++i) {
+    P.NR = env_nr ? env_nr : order[i][0];
+    P.NA = env_na ? env_na : order[i][1];
+    const bool two = i == 0 && 2 * P.tmem_cols <= 512;
+    const size_t lim = two ? (size_t)(kSmemLimit / 2 - 1024) : (size_t)kSmemLimit;
+    if (i == 0 && !two) continue;
+    if (wg_smem_bytes(P) <= lim) {
+      const int occ = two ? 2 : 1;
+      int grid = 148 * occ;
+      if (grid > P.ntiles) grid = P.ntiles;
+      *grid_out = grid; *occ_out = occ;
+      return true;
+    }
+  }
+  return false;
+}
 }  // namespace ru
 }  // namespace vbx
 
@@ -548,4 +780,56 @@ extern "C" int vbx_ru_fwd(int32_t B, int32_t C, int32_t T, int32_t dil, float sl
   else
     ru_fwd_kernel<4, 4, 4, 2><<<grid, ru_threads(4, 4, 4), smem, (cudaStream_t)stream>>>(tm, P);
   return launched("ru_fwd_kernel");
+}
+
+extern "C" int64_t vbx_ru_wgrad_workspace(int32_t B, int32_t C, int32_t T, int32_t dil, int32_t K) {
+  WgP P; int grid, occ;
+  if (!plan_wg(P, B, C, T, dil, K, &grid, &occ)) return -1;
+  return (int64_t)grid * C * C * K * 4;
+}
+
+extern "C" int vbx_ru_wgrad(int32_t B, int32_t C, int32_t T, int32_t dil, int32_t K, const float* x, const float* dy,
+                            float* dw, float beta, void* workspace, void* stream) {
+  WgP P; int grid, occ;
+  VBX_REQUIRE(plan_wg(P, B, C, T, dil, K, &grid, &occ), VBX_UNSUPPORTED,
+              "ru_wgrad: unsupported shape (C in {32, 64}, K in {1, 3}, T % 4 == 0, 1 <= dil <= 16, T > dil)");
+  VBX_REQUIRE(x && dy && dw && workspace, VBX_BAD_POINTER, "ru_wgrad: null tensor");
+  VBX_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)workspace & 15) == 0, VBX_BAD_POINTER,
+              "ru_wgrad: x, dy and the workspace must be 16-byte aligned");
+  EncodeTiledFn enc = encode_fn();
+  VBX_REQUIRE(enc != nullptr, VBX_UNSUPPORTED, "ru_wgrad: cuTensorMapEncodeTiled is not available from this driver");
+  CUtensorMap tmx, tmy;
+  const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)C, (cuuint64_t)B};
+  const cuuint64_t strides[2] = {(cuuint64_t)T * 4, (cuuint64_t)C * T * 4};
+  const cuuint32_t boxx[3] = {(cuuint32_t)P.Wraw, (cuuint32_t)C, 1}, boxy[3] = {(cuuint32_t)kRows, (cuuint32_t)C, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult cr = enc(&tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(x), dims, strides, boxx, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr == CUDA_SUCCESS)
+    cr = enc(&tmy, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(dy), dims, strides, boxy, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    snprintf(g_err, sizeof(g_err), "ru_wgrad: cuTensorMapEncodeTiled failed (CUresult %d)", (int)cr);
+    return VBX_UNSUPPORTED;
+  }
+  static const int wait_ns = getenv("VBX_RU_WAIT_NS") ? atoi(getenv("VBX_RU_WAIT_NS")) : 20000;
+  P.wait_ns = wait_ns;
+  P.partial = (float*)workspace;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t ce = cudaFuncSetAttribute(ru_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (ce == cudaSuccess)
+      ce = cudaFuncSetAttribute(ru_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (ce != cudaSuccess) return fail((int)ce, "ru_wgrad: cannot raise the dynamic shared memory limit");
+    attr_set = true;
+  }
+  const size_t smem = wg_smem_bytes(P);
+  if (occ == 2) ru_wgrad_kernel<2><<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(tmx, tmy, P);
+  else ru_wgrad_kernel<1><<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(tmx, tmy, P);
+  if (int r = launched("ru_wgrad_kernel")) return r;
+  const int n = C * C * K;
+  ru_wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P.partial, dw, n, grid, beta);
+  return launched("ru_wgrad_reduce_kernel");
 }

@@ -184,10 +184,19 @@ class ResidualUnitFn(Function):
         g1, g2, slope = ctx.g1, ctx.g2, ctx.slope
         g = _c(g)
         T = x.shape[2]
+        B, C = x.shape[0], x.shape[1]
         dz = ops.leaky_relu_bwd(g, None, slope, mask=mask)
-        dw2 = ops.conv_wgrad(h, dz, g2) if ctx.needs_input_grad[3] else None
+        tma_wgrad = (g1.K == 3 and g1.stride == 1 and g1.groups == 1 and g1.refl == g1.pad == g1.dil and g2.K == 1
+                     and g1.Cin == g1.Cout == g2.Cin == g2.Cout == C and ops.unit_wgrad_workspace(B, C, T, g1.dil, 3) > 0)
+        if ctx.needs_input_grad[3]:
+            dw2 = ops.unit_wgrad(h, dz, 1, 1) if tma_wgrad else ops.conv_wgrad(h, dz, g2)
+        else:
+            dw2 = None
         dh = ops.conv_dgrad(dz, w2, wt2, g2, T)
-        dw1 = ops.conv_wgrad(x, dh, g1) if ctx.needs_input_grad[1] else None
+        if ctx.needs_input_grad[1]:
+            dw1 = ops.unit_wgrad(x, dh, 3, g1.dil) if tma_wgrad else ops.conv_wgrad(x, dh, g1)
+        else:
+            dw1 = None
         dx = ops.conv_dgrad(dh, w1, wt1, g1, T, res=g) if ctx.needs_input_grad[0] else None
         return dx, dw1, None, dw2, None, None, None, None
 

@@ -217,6 +217,29 @@ def residual_unit_fwd(x: Tensor, packed: Tensor, dil: int, slope: float, want_h:
     return out, h, mask
 
 
+def unit_wgrad_workspace(B: int, C: int, T: int, dil: int, K: int) -> int:
+    """Workspace bytes of the TMA weight-gradient kernel for a residual-unit conv, or -1 when the shape is not taken."""
+    if not (TC_ENABLED and FUSED_UNIT):
+        return -1
+    return int(_lib.load().vbx_ru_wgrad_workspace(B, C, T, dil, K))
+
+
+def unit_wgrad(x: Tensor, dy: Tensor, K: int, dil: int, dw: Optional[Tensor] = None) -> Tensor:
+    """dw (C, C, K) (+)= sum_{b,t} dy * x for a stride-1 C -> C conv (K = 3 dilated / reflect, or K = 1): vbx_ru_wgrad.
+    Accumulates into `dw` when given, else returns a fresh tensor."""
+    B, C, T = x.shape
+    assert dy.shape == x.shape
+    nbytes = _lib.load().vbx_ru_wgrad_workspace(B, C, T, dil, K)
+    if nbytes <= 0:
+        raise _lib.VbxError("vbx_ru_wgrad: unsupported shape")
+    ws = torch.empty((nbytes // 4,), device=x.device, dtype=torch.float32)
+    beta = 1.0 if dw is not None else 0.0
+    if dw is None:
+        dw = torch.empty((C, C, K), device=x.device, dtype=torch.float32)
+    check(_lib.load().vbx_ru_wgrad(B, C, T, dil, K, _p(x), _p(dy), _p(dw), beta, _p(ws), _stream()), "vbx_ru_wgrad")
+    return dw
+
+
 def transpose_weight(w: Tensor, groups: int) -> Tensor:
     Cout, Cin_g, K = w.shape
     wt = torch.empty_like(w)
