@@ -667,13 +667,24 @@ __global__ void __launch_bounds__(kWgThreads, MINB) ru_wgrad_kernel(const __grid
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
 }
 
-// dw[i] = beta * dw[i] + sum over CTAs of partial[cta][i], CTAs in a fixed order
-__global__ void ru_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int n, int nparts, float beta) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// dw[i] = beta * dw[i] + sum over CTAs of partial[cta][i] in a FIXED order: 32 outputs x 8 slices per block, slice s sums
+// the partials p = s, s + 8, ... (coalesced 128-byte rows), the 8 slice sums are then added in slice order
+__global__ void __launch_bounds__(256) ru_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int n,
+                                                              int nparts, float beta) {
+  __shared__ float sh[8][32];
+  const int o = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + o;
   float acc = 0.f;
-  for (int p = 0; p < nparts; ++p) acc += partial[(size_t)p * n + i];
-  dw[i] = beta != 0.f ? beta * dw[i] + acc : acc;
+  if (i < n)
+    for (int p = sl; p < nparts; p += 8) acc += partial[(size_t)p * n + i];
+  sh[sl][o] = acc;
+  __syncthreads();
+  if (sl == 0 && i < n) {
+    float tot = sh[0][o];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) tot += sh[k][o];
+    dw[i] = beta != 0.f ? beta * dw[i] + tot : tot;
+  }
 }
 
 static bool plan_wg(WgP& P, int B, int C, int T, int d, int K, int* grid_out, int* occ_out) {
@@ -830,6 +841,6 @@ extern "C" int vbx_ru_wgrad(int32_t B, int32_t C, int32_t T, int32_t dil, int32_
   else ru_wgrad_kernel<1><<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(tmx, tmy, P);
   if (int r = launched("ru_wgrad_kernel")) return r;
   const int n = C * C * K;
-  ru_wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P.partial, dw, n, grid, beta);
+  ru_wgrad_reduce_kernel<<<(n + 31) / 32, 256, 0, (cudaStream_t)stream>>>(P.partial, dw, n, grid, beta);
   return launched("ru_wgrad_reduce_kernel");
 }

@@ -344,8 +344,13 @@ def axpby_dev(x: Tensor, y: Tensor, alpha: Tensor, beta: float) -> Tensor:
     return y
 
 
+DETERMINISTIC = False
+
+
 def set_deterministic(on: bool) -> bool:
     """Fixed-order reductions (include/vbx.h: vbx_set_deterministic); returns the previous setting."""
+    global DETERMINISTIC
+    DETERMINISTIC = bool(on)
     return bool(_lib.load().vbx_set_deterministic(1 if on else 0))
 
 

@@ -18,7 +18,7 @@ except Exception:  # pragma: no cover
         pass
 
 from ..utils import normalized_conv1d
-from .melgan_discriminator import DiscriminatorMelGAN, run_stage
+from .melgan_discriminator import DiscriminatorMelGAN, prepare_stage, run_stage
 
 
 class DiscriminatorEBEN(nn.Module):
@@ -75,16 +75,34 @@ class DiscriminatorEBENMultiScales(nn.Module, PyTorchModelHubMixin):
             jobs.append([selected, selected, selected, audio])
         if not (jobs[0][0].is_cuda and _SIDE_STREAMS):
             return [[net(x) for net, x in zip(nets, inputs)] for inputs in jobs]
-        # One stream per SUB-DISCRIMINATOR (not per pass): every pass of network i runs on stream i, so its
-        # effective weights and packed tiles - created lazily by the first pass and shared by the others -
-        # are produced and consumed in one stream's order, and their allocator lifetime is that stream's.
+        # One stream per SUB-DISCRIMINATOR, plus one more per additional PASS (enhanced / reference): what the passes of a
+        # network share - effective weights, packed tensor-core tiles - is produced first on the network's main stream
+        # (`prepare_stage`), the other pass streams wait for that, and then every pass is an independent chain.  The
+        # chains of one network launch the same kernels on different data and can fill each other's half-empty waves.
+        # (VBX_D_PASS_STREAMS=1; default off, see below.)
+        # Deterministic mode keeps all passes of a network on one stream: bias gradients of both passes accumulate into
+        # the same bucket slot and their order must not depend on stream timing.
+        from ... import ops
         cur = torch.cuda.current_stream()
-        streams = self._streams(jobs[0][0].device, len(nets))
+        per_pass = _PASS_STREAMS and len(jobs) > 1 and not ops.DETERMINISTIC
+        npass = len(jobs) if per_pass else 1
+        streams = self._streams(jobs[0][0].device, len(nets) * npass)
         out = [[None] * len(nets) for _ in jobs]
-        for i, (net, st) in enumerate(zip(nets, streams)):
-            st.wait_stream(cur)
-            with torch.cuda.stream(st):
-                for j, inputs in enumerate(jobs):
+        backward = torch.is_grad_enabled()
+        for i, net in enumerate(nets):
+            main = streams[i * npass]
+            main.wait_stream(cur)
+            if per_pass:
+                with torch.cuda.stream(main):
+                    shared = [t for stage in net.discriminator for t in prepare_stage(stage, backward)]
+                for k in range(1, npass):
+                    streams[i * npass + k].wait_stream(main)
+                    streams[i * npass + k].wait_stream(cur)
+                    for t in shared:
+                        t.record_stream(streams[i * npass + k])
+            for j, inputs in enumerate(jobs):
+                st = streams[i * npass + (j if per_pass else 0)]
+                with torch.cuda.stream(st):
                     x = inputs[i]
                     x.record_stream(st)
                     emb = net(x)
@@ -119,6 +137,9 @@ class DiscriminatorEBENMultiScales(nn.Module, PyTorchModelHubMixin):
 
 
 _SIDE_STREAMS = os.environ.get("VBX_D_STREAMS", "1") != "0"
+# one more stream per PASS of a network (off by default: measured 39.77 vs 39.85 ms per step - the step is bound by the
+# kernels' own throughput, not by half-empty waves; kept as a knob)
+_PASS_STREAMS = os.environ.get("VBX_D_PASS_STREAMS", "0") == "1"
 _MELGAN_PRIORITY = os.environ.get("VBX_D_PRIORITY", "0") == "1"
 if _SIDE_STREAMS and hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
     # leaves created on the caller's stream (detached generator outputs) receive gradients from side streams

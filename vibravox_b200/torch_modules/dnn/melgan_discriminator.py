@@ -12,8 +12,7 @@ from ...functional import ConvFn
 from ..utils import conv_geom, effective_weight, normalized_conv1d
 
 
-def run_stage(stage: nn.Module, x: torch.Tensor) -> torch.Tensor:
-    """One entry of a discriminator's ModuleList: [ReflectionPad1d] + wn-Conv1d [+ LeakyReLU]."""
+def _parse_stage(stage: nn.Module):
     extra, slope, conv = 0, 1.0, stage
     if isinstance(stage, nn.Sequential):
         conv = None
@@ -24,8 +23,31 @@ def run_stage(stage: nn.Module, x: torch.Tensor) -> torch.Tensor:
                 conv = mod
             elif isinstance(mod, nn.LeakyReLU):
                 slope = mod.negative_slope
+    return conv, extra, slope
+
+
+def run_stage(stage: nn.Module, x: torch.Tensor) -> torch.Tensor:
+    """One entry of a discriminator's ModuleList: [ReflectionPad1d] + wn-Conv1d [+ LeakyReLU]."""
+    conv, extra, slope = _parse_stage(stage)
     w, wt = effective_weight(conv)
     return ConvFn.apply(x, w, wt, conv.bias, conv_geom(conv, extra), slope)
+
+
+def prepare_stage(stage: nn.Module, backward: bool) -> list:
+    """Everything of a stage that is created lazily and then SHARED by all passes of a step - the effective (weight-normed)
+    weight and the packed tensor-core tiles of the forward and of the input gradient - produced now, on the current
+    stream, so that passes running on other streams only ever read them.  Returns the tensors (for record_stream)."""
+    from ... import ops
+    conv, extra, _ = _parse_stage(stage)
+    geom = conv_geom(conv, extra)
+    w, wt = effective_weight(conv)
+    made = [w] + ([wt] if wt is not None else [])
+    # (the pack cache lives on the tensor OBJECT the passes will hand to the conv ops: `w` itself, not a detached alias)
+    if ops.use_tc(geom, "fwd"):
+        made.append(ops.get_pack(w, geom, ops.TC_FWD))
+    if backward and ops.use_tc(geom, "dgrad"):
+        made.append(ops.get_pack(w, geom, ops.TC_DGRAD))
+    return made
 
 
 class DiscriminatorMelGAN(nn.Module):
