@@ -14,6 +14,7 @@
 #pragma once
 
 static const int kWsTC = 32;                // time positions per stage (two MMA k-steps)
+static const int kWsMaxItems = 4;           // x items (position, 8-channel group) a producer thread carries per stage
 
 struct TcWS {
   GemmP g;
@@ -36,9 +37,15 @@ __host__ __device__ inline int ws_npos_taps(const GemmP& G, int ntap) {
 
 // PW producer warps (+ one MMA warp): 16 when the tile owns all 512 TMEM columns (one CTA per SM: the extra warps
 // are the memory-level parallelism), 8 with two CTAs per SM otherwise.
-template <int PW, int MINB>
-__global__ void __launch_bounds__(PW * 32 + 32, MINB) tc_wslab_kernel(const TcWS P) {
+// NI MMA-issuing warps (one thread each): an N = 64 MMA is 32 tensor-core cycles of work, but ONE thread cannot issue
+// them faster than one per ~76 cycles (profiles/r1_mma_probe.txt: 76 per issuer, 48 aggregate with four issuers), so
+// with a single issuer the tensor pipe idled at 26-42 %.  The taps of a CTA accumulate into separate TMEM columns, so
+// they are dealt round-robin to the issuers and no two threads ever touch the same accumulator.
+static const int kWsIssuers = 4;
+template <int PW, int MINB, int MAXI>
+__global__ void __launch_bounds__(PW * 32 + kWsIssuers * 32, MINB) tc_wslab_kernel(const TcWS P) {
   constexpr int kProd = PW * 32;
+  constexpr int NI = kWsIssuers;
   extern __shared__ __align__(128) unsigned char smem[];
   const GemmP& G = P.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -65,8 +72,8 @@ __global__ void __launch_bounds__(PW * 32 + 32, MINB) tc_wslab_kernel(const TcWS
   const int nstage = (rv_hi - rv_lo + kWsTC - 1) / kWsTC;
 
   if (tid == 0) {
-    for (int i = 0; i < S; ++i) { mbar_init(&full[i], kProd); mbar_init(&empty[i], 1); }
-    mbar_init(acc_full, 1);
+    for (int i = 0; i < S; ++i) { mbar_init(&full[i], kProd); mbar_init(&empty[i], NI); }
+    mbar_init(acc_full, NI);
     fence_barrier_init();
   }
   const int pos0 = tap0 * G.dil;                                // first x position (relative to s*rv) this tile reads
@@ -82,14 +89,17 @@ __global__ void __launch_bounds__(PW * 32 + 32, MINB) tc_wslab_kernel(const TcWS
 
   if (warp < PW) {
     // ===================== producers =====================
-    // dy: one position x (16 / PW) 8-channel groups per thread.  x: TPP threads share a position and interleave its
-    // 8-channel groups, so all threads carry a similar number of loads.
+    // dy: one position x (16 / PW) 8-channel groups per thread.  x: a flat list of (position, 8-channel group) items,
+    // item = group * npos + position, dealt round-robin to the producer threads (lanes walk positions: coalesced rows),
+    // so every thread carries the same number of loads whatever the tap span.
+    // The loads of stage c + 1 are ISSUED before stage c is converted and stored (two register sets, loop unrolled by
+    // two): a stage then costs its conversion + stores, not a global-memory round trip - with the loads issued and
+    // consumed inside one stage this kernel sat at 26 % tensor-pipe activity, all 16 warps waiting on long scoreboards.
     constexpr int NA = 16 / PW;
-    constexpr int TPP = kProd / 128;                            // threads per x position (128 positions per round)
-    constexpr int NU = 8 / TPP;                                 // 8-channel groups per thread and position (NCI <= 64)
-    constexpr int MAXR = 3;                                     // position rounds (host: positions <= 384)
+    // MAXI (template): x items per thread and stage (host: nitems <= MAXI * kProd)
     const int npos = ws_npos_taps(G, ntap);
     const int ncg = NCI / 8;
+    const int nitems = npos * ncg;
     const int tA = tid & 31, cogA = (tid >> 5) * NA;
     const float* dyg = G.DY + (long long)(grp * G.Cout_g + co0) * G.Tout;
     const float* xg = G.X + (long long)(grp * G.Cin_g + ci0) * G.Tin;
@@ -117,30 +127,46 @@ __global__ void __launch_bounds__(PW * 32 + 32, MINB) tc_wslab_kernel(const TcWS
         for (int e = 0; e < 8; ++e) v[e] = e < nvalid ? __ldg(p + e * stride) : 0.f;
       }
     };
-    // running (batch item, offset) of this thread's dy row and x positions: advanced per stage, never divided again
+    // running (batch item, offset) of this thread's dy row and x items: advanced per stage, never divided again
     int ba = (rv_lo + tA) / R, ta = (rv_lo + tA) % R;
-    int bx[MAXR], px[MAXR], sx[MAXR];
+    int bx[MAXI], px[MAXI], sx[MAXI], gx[MAXI];
 #pragma unroll
-    for (int r = 0; r < MAXR; ++r) {
-      const int i = tid / TPP + 128 * r;
-      const unsigned q = (unsigned)rv_lo * (unsigned)s + (unsigned)(pos0 + i);
-      bx[r] = (int)(q / (unsigned)Ppos); px[r] = (int)(q % (unsigned)Ppos);
-      sx[r] = i < npos ? ((i % s) * UB + i / s) * 16 : -1;
+    for (int j = 0; j < MAXI; ++j) {
+      const int i = tid + j * kProd;
+      const int g = i < nitems ? i / npos : 0, pp = i < nitems ? i - g * npos : 0;
+      const unsigned q = (unsigned)rv_lo * (unsigned)s + (unsigned)(pos0 + pp);
+      bx[j] = (int)(q / (unsigned)Ppos); px[j] = (int)(q % (unsigned)Ppos);
+      gx[j] = g;
+      sx[j] = i < nitems ? ((pp % s) * UB + pp / s) * 16 + g * sbo_b : -1;
     }
-    const int cg0 = tid % TPP;
-    int st = 0;
-    uint32_t par = 0;
-    for (int c = 0; c < nstage; ++c) {
-      // ---- dy ----
+    // issue the loads of stage c (call in stage order: advances the running counters)
+    auto issue = [&](int c, float (&a)[NA][8], float (&v)[MAXI][8]) {
       const bool va = rv_lo + c * kWsTC + tA < rv_hi && ba < G.B && ta < G.Tout;
-      float a[NA][8];
-      {
-        const float* pa = dyg + ((long long)ba * G.Cout + (long long)cogA * 8) * G.Tout + ta;
+      const float* pa = dyg + ((long long)ba * G.Cout + (long long)cogA * 8) * G.Tout + ta;
 #pragma unroll
-        for (int h = 0; h < NA; ++h)
-          load8(pa + (long long)h * 8 * G.Tout, G.Tout, va ? rows_a - (cogA + h) * 8 : 0, a[h]);
+      for (int h = 0; h < NA; ++h)
+        load8(pa + (long long)h * 8 * G.Tout, G.Tout, va ? rows_a - (cogA + h) * 8 : 0, a[h]);
+#pragma unroll
+      for (int j = 0; j < MAXI; ++j) {
+        if (sx[j] >= 0) {
+          const int tau = map_pos(px[j] - G.pad, G.Tin, G.refl);
+          const bool vb = bx[j] < G.B && tau >= 0;
+          const float* pb = xg + ((long long)bx[j] * G.Cin * G.Tin + (vb ? tau : 0));
+          load8(pb + (long long)gx[j] * 8 * G.Tin, G.Tin, vb ? cols_b - gx[j] * 8 : 0, v[j]);
+        }
       }
-      mbar_wait(&empty[st], par ^ 1u);
+      ta += kWsTC;
+      while (ta >= R) { ta -= R; ++ba; }
+#pragma unroll
+      for (int j = 0; j < MAXI; ++j) {
+        px[j] += kWsTC * s;
+        while (px[j] >= Ppos) { px[j] -= Ppos; ++bx[j]; }
+      }
+    };
+    // convert + store stage c and hand it to the MMA issuer
+    auto commit = [&](int c, const float (&a)[NA][8], const float (&v)[MAXI][8]) {
+      const int st = c % S;
+      mbar_wait(&empty[st], (uint32_t)((c / S) & 1) ^ 1u);
       unsigned char* sa = smem + (size_t)st * stage_sz;
       unsigned char* sb = sa + a_stage;
 #pragma unroll
@@ -148,36 +174,28 @@ __global__ void __launch_bounds__(PW * 32 + 32, MINB) tc_wslab_kernel(const TcWS
         unsigned char* d0 = sa + (cogA + h) * sbo_a + tA * 16;
         put16(d0, d0 + plane_a, a[h]);
       }
-      // ---- x ----
 #pragma unroll
-      for (int r = 0; r < MAXR; ++r) {
-        if (sx[r] >= 0) {
-          const int tau = map_pos(px[r] - G.pad, G.Tin, G.refl);
-          const bool vb = bx[r] < G.B && tau >= 0;
-          const float* pb = xg + ((long long)bx[r] * G.Cin * G.Tin + (vb ? tau : 0));
-          float v[NU][8];
-#pragma unroll
-          for (int u = 0; u < NU; ++u) {
-            const int cg = cg0 + u * TPP;
-            load8(pb + (long long)cg * 8 * G.Tin, G.Tin, (vb && cg < ncg) ? cols_b - cg * 8 : 0, v[u]);
-          }
-          unsigned char* d0 = sb + sx[r];
-#pragma unroll
-          for (int u = 0; u < NU; ++u) {
-            const int cg = cg0 + u * TPP;
-            if (cg < ncg) put16(d0 + cg * sbo_b, d0 + cg * sbo_b + plane_b, v[u]);
-          }
-        }
-      }
+      for (int j = 0; j < MAXI; ++j)
+        if (sx[j] >= 0) put16(sb + sx[j], sb + sx[j] + plane_b, v[j]);
       fence_proxy_async();
       mbar_arrive(&full[st]);
-      if (++st == S) { st = 0; par ^= 1u; }
-      ta += kWsTC;
-      while (ta >= R) { ta -= R; ++ba; }
-#pragma unroll
-      for (int r = 0; r < MAXR; ++r) {
-        px[r] += kWsTC * s;
-        while (px[r] >= Ppos) { px[r] -= Ppos; ++bx[r]; }
+    };
+    if (PW == 16) {                       // one CTA per SM: registers to spare for the second set
+      float a0[NA][8], v0[MAXI][8], a1[NA][8], v1[MAXI][8];
+      issue(0, a0, v0);
+      for (int c = 0; c < nstage; c += 2) {
+        if (c + 1 < nstage) issue(c + 1, a1, v1);
+        commit(c, a0, v0);
+        if (c + 1 < nstage) {
+          if (c + 2 < nstage) issue(c + 2, a0, v0);
+          commit(c + 1, a1, v1);
+        }
+      }
+    } else {                              // two CTAs per SM (80 registers): loads and stores of a stage back to back
+      float a0[NA][8], v0[MAXI][8];
+      for (int c = 0; c < nstage; ++c) {
+        issue(c, a0, v0);
+        commit(c, a0, v0);
       }
     }
     // ===================== epilogue: TMEM -> fp32 reductions into dW[co][ci][k] =====================
@@ -198,8 +216,9 @@ __global__ void __launch_bounds__(PW * 32 + 32, MINB) tc_wslab_kernel(const TcWS
         if (n0 + j < cols_b) atomicAdd(dst + (long long)(n0 + j) * G.K + tl, acc[j]);
     }
   } else {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuers: issuer `iw` takes taps iw, iw + NI, ... =====================
     if (lane == 0) {
+      const int iw = warp - PW;
       const uint32_t idesc = make_idesc_bf16(NCI, /*a_mn=*/true, /*b_mn=*/true);
       int st = 0;
       uint32_t par = 0;
@@ -208,7 +227,7 @@ __global__ void __launch_bounds__(PW * 32 + 32, MINB) tc_wslab_kernel(const TcWS
         tc_fence_after();
         const uint32_t a_hi = smem_u32(smem + (size_t)st * stage_sz), a_lo = a_hi + plane_a;
         const uint32_t b_base = a_hi + a_stage;
-        for (int tl = 0; tl < ntap; ++tl) {
+        for (int tl = iw; tl < ntap; tl += NI) {
           const uint32_t b_hi = b_base + (uint32_t)tapoff[tl], b_lo = b_hi + plane_b;
           const uint32_t d = tmem_base + (uint32_t)(tl * NCI);
 #pragma unroll
@@ -220,7 +239,7 @@ __global__ void __launch_bounds__(PW * 32 + 32, MINB) tc_wslab_kernel(const TcWS
             mma_bf16_ss(d, da_lo, db_hi, idesc, 1);
           }
         }
-        mma_commit(&empty[st]);
+        mma_commit(&empty[st]);           // (an issuer without taps arrives at once: nothing of its own is in flight)
         if (++st == S) { st = 0; par ^= 1u; }
       }
       mma_commit(acc_full);
@@ -256,7 +275,7 @@ static bool plan_wslab(TcWS& P, const vbx_conv_desc* d) {
   P.TG = (G.K + P.ntg - 1) / P.ntg;
   P.tmem_cols = pow2_cols(P.TG * P.NCI);
   P.UB = ws_UB(G, P.TG);
-  if (ws_npos_taps(G, P.TG) > 3 * 128) return false;
+  if (ws_npos_taps(G, P.TG) * (P.NCI / 8) > kWsMaxItems * (P.tmem_cols > 256 ? 16 : 8) * 32) return false;
   const long long total = (long long)G.B * R;
   const long long tiles = (long long)P.ntg * P.ci_tiles * P.co_tiles * G.groups;
   long long max_split = (total + kWsTC * 8 - 1) / (kWsTC * 8);
@@ -285,9 +304,11 @@ static bool plan_wslab(TcWS& P, const vbx_conv_desc* d) {
 static int launch_wslab(const TcWS& P, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t ce = cudaFuncSetAttribute(tc_wslab_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
-    if (ce == cudaSuccess)
-      ce = cudaFuncSetAttribute(tc_wslab_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+    cudaError_t ce = cudaFuncSetAttribute(tc_wslab_kernel<16, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(tc_wslab_kernel<16, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(tc_wslab_kernel<16, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(tc_wslab_kernel<8, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(tc_wslab_kernel<8, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
     if (ce != cudaSuccess) return fail((int)ce, "tc_wslab: cannot raise the dynamic shared memory limit");
     attr_set = true;
   }
@@ -295,7 +316,15 @@ static int launch_wslab(const TcWS& P, cudaStream_t st) {
   dim3 grid((unsigned)(P.ntg * P.ci_tiles), (unsigned)(P.co_tiles * P.g.groups),
             (unsigned)((total + P.rows_per - 1) / P.rows_per));
   if (grid.y > 65535 || grid.z > 65535) return fail(VBX_UNSUPPORTED, "tc_wslab: grid too large");
-  if (P.tmem_cols > 256) tc_wslab_kernel<16, 1><<<grid, 16 * 32 + 32, ws_smem_bytes(P), st>>>(P);
-  else tc_wslab_kernel<8, 2><<<grid, 8 * 32 + 32, ws_smem_bytes(P), st>>>(P);
+  const int prod = (P.tmem_cols > 256 ? 16 : 8) * 32;
+  const int need = (ws_npos_taps(P.g, P.TG) * (P.NCI / 8) + prod - 1) / prod;        // x items per producer thread
+  if (P.tmem_cols > 256) {
+    if (need <= 1) tc_wslab_kernel<16, 1, 1><<<grid, 16 * 32 + kWsIssuers * 32, ws_smem_bytes(P), st>>>(P);
+    else if (need <= 3) tc_wslab_kernel<16, 1, 3><<<grid, 16 * 32 + kWsIssuers * 32, ws_smem_bytes(P), st>>>(P);
+    else tc_wslab_kernel<16, 1, 4><<<grid, 16 * 32 + kWsIssuers * 32, ws_smem_bytes(P), st>>>(P);
+  } else {
+    if (need <= 2) tc_wslab_kernel<8, 2, 2><<<grid, 8 * 32 + kWsIssuers * 32, ws_smem_bytes(P), st>>>(P);
+    else tc_wslab_kernel<8, 2, 4><<<grid, 8 * 32 + kWsIssuers * 32, ws_smem_bytes(P), st>>>(P);
+  }
   return launched("tc_wslab_kernel");
 }
