@@ -130,6 +130,25 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (M = 128 lanes x 16 bf16 = 8 columns, K-major: lane = row, two
+// consecutive k per 32-bit column, even k in the low half) is read from tensor memory - no shared-memory bandwidth
+__device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 4 consecutive 32-bit columns of this thread's TMEM lane (lane = 32 * (warp % 4) + lane id)
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2),
+               "r"(r3)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // Shared-memory matrix descriptor, SWIZZLE_NONE.  lbo / sbo in bytes (multiples of 16).
 //   K-major operand : 8-row x 16-byte core matrices; sbo = stride between 8-row groups,
 //                     lbo = stride between the two 16-byte K units of one MMA.

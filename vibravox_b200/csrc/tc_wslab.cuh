@@ -22,13 +22,16 @@ struct TcWS {
   int R;            // virtual rows per batch item
   int UB;           // x units per stride phase in a stage
   int rows_per;     // virtual rows per blockIdx.z (multiple of kWsTC)
+  int ts;           // 1: dy (the A operand) is staged in TENSOR memory (two buffers of 32 columns behind the accumulators)
 };
+static const int kWsTsCols = 64;            // TMEM columns of the A ring in ts mode: 2 buffers x (hi | lo) x 2 k-steps x 8
 __host__ __device__ inline int ws_UB(const GemmP& G, int TG) { return kWsTC + ((TG - 1) * G.dil) / G.stride + 1; }
 // bytes between consecutive 8-channel groups of a slab: an odd number of 16-byte units, so that the 16 (or NCI/8)
 // units the tensor core fetches for one time position fall in different shared-memory banks
 __host__ __device__ inline int ws_sbo_a() { return kWsTC * 16 + 16; }
 __host__ __device__ inline int ws_sbo_b(const GemmP& G, int UB) { return (G.stride * UB | 1) * 16; }
-__host__ __device__ inline int ws_a_stage() { return 2 * (kRows / 8) * ws_sbo_a(); }                  // hi + lo
+// (ts mode: the A part of a stage is the fp32 transpose scratch [128 channels][32 positions, row pitch 36 floats])
+__host__ __device__ inline int ws_a_stage(int ts = 0) { return ts ? kRows * 36 * 4 : 2 * (kRows / 8) * ws_sbo_a(); }   // hi + lo
 __host__ __device__ inline int ws_b_stage(const GemmP& G, int NCI, int UB) { return 2 * (NCI / 8) * ws_sbo_b(G, UB); }
 // positions of x a tile with `ntap` taps stages per time chunk (its own tap span only)
 __host__ __device__ inline int ws_npos_taps(const GemmP& G, int ntap) {
@@ -50,7 +53,8 @@ __global__ void __launch_bounds__(PW * 32 + kWsIssuers * 32, MINB) tc_wslab_kern
   const GemmP& G = P.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = P.stages, NCI = P.NCI, s = G.stride, UB = P.UB;
-  const int a_stage = ws_a_stage(), b_stage = ws_b_stage(G, NCI, UB), stage_sz = a_stage + b_stage;
+  const int a_stage = ws_a_stage(P.ts), b_stage = ws_b_stage(G, NCI, UB), stage_sz = a_stage + b_stage;
+  const uint32_t acol0 = (uint32_t)(P.TG * NCI);                  // ts mode: first TMEM column of the A ring
   const int plane_a = a_stage / 2, plane_b = b_stage / 2;
   const int sbo_a = ws_sbo_a(), sbo_b = ws_sbo_b(G, UB);            // bytes between 8-channel groups
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_sz);
@@ -101,6 +105,9 @@ __global__ void __launch_bounds__(PW * 32 + kWsIssuers * 32, MINB) tc_wslab_kern
     const int ncg = NCI / 8;
     const int nitems = npos * ncg;
     const int tA = tid & 31, cogA = (tid >> 5) * NA;
+    // ts mode: thread = TMEM lane (output channel co0 + 32 * (warp % 4) + lane); the PW / 4 warps of a lane quadrant
+    // split the stage's 32 time positions (8 * NA each)
+    const int rowT = (warp & 3) * 32 + lane, partT = warp >> 2;
     const float* dyg = G.DY + (long long)(grp * G.Cout_g + co0) * G.Tout;
     const float* xg = G.X + (long long)(grp * G.Cin_g + ci0) * G.Tin;
     const int rows_a = min(kRows, G.Cout_g - co0), cols_b = min(NCI, G.Cin_g - ci0);
@@ -169,10 +176,44 @@ __global__ void __launch_bounds__(PW * 32 + kWsIssuers * 32, MINB) tc_wslab_kern
       mbar_wait(&empty[st], (uint32_t)((c / S) & 1) ^ 1u);
       unsigned char* sa = smem + (size_t)st * stage_sz;
       unsigned char* sb = sa + a_stage;
+      if (P.ts) {
+        // The loads are coalesced along time (lane = position, 8 channels each); tensor memory wants lane = channel.
+        // Transpose through the stage's fp32 scratch (row pitch 36 floats: conflict-free both ways), then each thread
+        // packs 8 * NA consecutive positions of ITS channel into bf16 hi / lo pairs and stores them to its TMEM lane:
+        // column = buffer + (hi | lo) * 16 + position / 2.
+        float* scr = reinterpret_cast<float*>(sa);
 #pragma unroll
-      for (int h = 0; h < NA; ++h) {
-        unsigned char* d0 = sa + (cogA + h) * sbo_a + tA * 16;
-        put16(d0, d0 + plane_a, a[h]);
+        for (int h = 0; h < NA; ++h)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) scr[((cogA + h) * 8 + e) * 36 + tA] = a[h][e];
+        asm volatile("bar.sync 1, %0;" ::"r"(kProd) : "memory");          // producer warps only
+        const uint32_t tcol = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acol0 + (uint32_t)((c & 1) * 32) +
+                              (uint32_t)(partT * 4 * NA);
+        const float4* row = reinterpret_cast<const float4*>(scr + rowT * 36 + partT * 8 * NA);
+#pragma unroll
+        for (int h = 0; h < NA; ++h) {
+          const float4 p0 = row[2 * h], p1 = row[2 * h + 1];
+          const float v[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+            const float2 hf = __bfloat1622float2(h2);
+            const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+            hi[e] = *reinterpret_cast<const uint32_t*>(&h2);
+            lo[e] = *reinterpret_cast<const uint32_t*>(&l2);
+          }
+          tmem_st4(tcol + (uint32_t)(h * 4), hi[0], hi[1], hi[2], hi[3]);
+          tmem_st4(tcol + 16u + (uint32_t)(h * 4), lo[0], lo[1], lo[2], lo[3]);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+      } else {
+#pragma unroll
+        for (int h = 0; h < NA; ++h) {
+          unsigned char* d0 = sa + (cogA + h) * sbo_a + tA * 16;
+          put16(d0, d0 + plane_a, a[h]);
+        }
       }
 #pragma unroll
       for (int j = 0; j < MAXI; ++j)
@@ -219,7 +260,7 @@ __global__ void __launch_bounds__(PW * 32 + kWsIssuers * 32, MINB) tc_wslab_kern
     // ===================== MMA issuers: issuer `iw` takes taps iw, iw + NI, ... =====================
     if (lane == 0) {
       const int iw = warp - PW;
-      const uint32_t idesc = make_idesc_bf16(NCI, /*a_mn=*/true, /*b_mn=*/true);
+      const uint32_t idesc = make_idesc_bf16(NCI, /*a_mn=*/P.ts == 0, /*b_mn=*/true);
       int st = 0;
       uint32_t par = 0;
       for (int c = 0; c < nstage; ++c) {
@@ -232,11 +273,18 @@ __global__ void __launch_bounds__(PW * 32 + kWsIssuers * 32, MINB) tc_wslab_kern
           const uint32_t d = tmem_base + (uint32_t)(tl * NCI);
 #pragma unroll
           for (int ks = 0; ks < kWsTC / 16; ++ks) {
-            const uint64_t da_hi = make_desc(a_hi + ks * 256, 128, sbo_a), da_lo = make_desc(a_lo + ks * 256, 128, sbo_a);
             const uint64_t db_hi = make_desc(b_hi + ks * 256, 128, sbo_b), db_lo = make_desc(b_lo + ks * 256, 128, sbo_b);
-            mma_bf16_ss(d, da_hi, db_hi, idesc, (c > 0 || ks > 0) ? 1u : 0u);
-            mma_bf16_ss(d, da_hi, db_lo, idesc, 1);
-            mma_bf16_ss(d, da_lo, db_hi, idesc, 1);
+            if (P.ts) {
+              const uint32_t ta_hi = tmem_base + acol0 + (uint32_t)((c & 1) * 32 + ks * 8), ta_lo = ta_hi + 16u;
+              mma_bf16_ts(d, ta_hi, db_hi, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+              mma_bf16_ts(d, ta_hi, db_lo, idesc, 1);
+              mma_bf16_ts(d, ta_lo, db_hi, idesc, 1);
+            } else {
+              const uint64_t da_hi = make_desc(a_hi + ks * 256, 128, sbo_a), da_lo = make_desc(a_lo + ks * 256, 128, sbo_a);
+              mma_bf16_ss(d, da_hi, db_hi, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+              mma_bf16_ss(d, da_hi, db_lo, idesc, 1);
+              mma_bf16_ss(d, da_lo, db_hi, idesc, 1);
+            }
           }
         }
         mma_commit(&empty[st]);           // (an issuer without taps arrives at once: nothing of its own is in flight)
@@ -251,7 +299,7 @@ __global__ void __launch_bounds__(PW * 32 + kWsIssuers * 32, MINB) tc_wslab_kern
 }
 
 static size_t ws_smem_bytes(const TcWS& P) {
-  return (size_t)P.stages * (ws_a_stage() + ws_b_stage(P.g, P.NCI, P.UB)) + (2 * P.stages + 1) * sizeof(uint64_t) + 16 +
+  return (size_t)P.stages * (ws_a_stage(P.ts) + ws_b_stage(P.g, P.NCI, P.UB)) + (2 * P.stages + 1) * sizeof(uint64_t) + 16 +
          (size_t)P.TG * sizeof(int) + 16;
 }
 
@@ -269,11 +317,18 @@ static bool plan_wslab(TcWS& P, const vbx_conv_desc* d) {
   P.NCI = G.Cin_g >= 64 ? 64 : (G.Cin_g + 15) / 16 * 16;
   P.ci_tiles = (G.Cin_g + P.NCI - 1) / P.NCI;
   P.co_tiles = (G.Cout_g + kRows - 1) / kRows;
+  // ts mode (VBX_WS_TS=1, off by default): dy - the A operand, shared by every tap - staged in TENSOR memory
+  // (tcgen05.st after a shared-memory transpose, tcgen05.mma with A from TMEM): an N = 64 SS MMA reads 4 KB of A + 2 KB
+  // of B from shared memory per 32 cycles of tensor work, A from TMEM leaves 2 KB.  Correct (same tests), but measured
+  // SLOWER on the B200: MelGAN stage 4 0.97 ms against 0.76 ms - the kernel is bound by the ~26 thread instructions it
+  // spends per staged element (ncu: issue slots 43 % busy, tensor pipe 21 %), not by operand bandwidth.
+  static const bool ts_on = getenv("VBX_WS_TS") && atoi(getenv("VBX_WS_TS")) == 1;
+  P.ts = ts_on && G.K * P.NCI > 256 ? 1 : 0;
   const int cols = G.K * P.NCI <= 256 ? 256 : 512;
-  int tgmax = cols / P.NCI;
+  int tgmax = (cols - (P.ts ? kWsTsCols : 0)) / P.NCI;
   P.ntg = (G.K + tgmax - 1) / tgmax;
   P.TG = (G.K + P.ntg - 1) / P.ntg;
-  P.tmem_cols = pow2_cols(P.TG * P.NCI);
+  P.tmem_cols = pow2_cols(P.TG * P.NCI + (P.ts ? kWsTsCols : 0));
   P.UB = ws_UB(G, P.TG);
   if (ws_npos_taps(G, P.TG) * (P.NCI / 8) > kWsMaxItems * (P.tmem_cols > 256 ? 16 : 8) * 32) return false;
   const long long total = (long long)G.B * R;
@@ -289,7 +344,7 @@ static bool plan_wslab(TcWS& P, const vbx_conv_desc* d) {
   long long per = (total + want - 1) / want;
   per = (per + kWsTC - 1) / kWsTC * kWsTC;
   P.rows_per = (int)per;
-  const int stage = ws_a_stage() + ws_b_stage(G, P.NCI, P.UB);
+  const int stage = ws_a_stage(P.ts) + ws_b_stage(G, P.NCI, P.UB);
   int stg = (P.tmem_cols <= 256 ? 100 * 1024 : 200 * 1024) / stage;
   if (stg > 4) stg = 4;
   if (stg < 2) {
@@ -297,7 +352,7 @@ static bool plan_wslab(TcWS& P, const vbx_conv_desc* d) {
     if (stg < 2) return false;
     if (stg > 2) stg = 2;
   }
-  P.stages = stg;
+  P.stages = P.ts ? 2 : stg;           // (ts: the two A buffers in TMEM pace the ring)
   return ws_smem_bytes(P) <= (size_t)kSmemMax;
 }
 
