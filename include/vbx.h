@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define VBX_ABI_VERSION 3
+#define VBX_ABI_VERSION 4
 #if defined(__GNUC__)
 #define VBX_API __attribute__((visibility("default")))
 #else
@@ -40,13 +40,25 @@ typedef struct {
 
 /* Fused output stage shared by the conv entry points:
  *   v = acc + bias[ch];  mask[idx] = v > 0;  v = v > 0 ? v : slope*v;  v += res[idx];
- *   out[idx] = v + beta*out[idx]            (each step skipped when its pointer is NULL / slope==1 / beta==0) */
+ *   if gate:  y = gate[idx];
+ *             if fm_other: v += fm_coef[0]*sign(y - fm_other[idx]) - fm_coef[1]*sign(y);
+ *             v *= (y > 0 ? 1 : gate_slope);
+ *   out[idx] = v + beta*out[idx]            (each step skipped when its pointer is NULL / slope==1 / beta==0)
+ * The gate stage is the backward of the PRODUCER of this kernel's output, folded into an input-gradient epilogue:
+ * `gate` is the post-LeakyReLU activation y the gradient belongs to (melgan_discriminator.py:89-156 /
+ * eben_discriminator.py:66-157 keep every stage output for the feature-matching loss), gate_slope its negative slope,
+ * and fm_other / fm_coef add the feature-matching gradient of that activation (feature_loss.py:37-50; fm_coef from
+ * vbx_fm_coef) before the gate - replacing an aten::add, an aten::leaky_relu_backward and the L1-pair backward pass. */
 typedef struct {
   const float* bias;
   const float* res;
   uint8_t* mask;
   float slope;
   float beta;
+  const float* gate;
+  const float* fm_other;
+  const float* fm_coef;
+  float gate_slope;
 } vbx_epilogue;
 
 VBX_API int vbx_abi_version(void);
@@ -186,6 +198,14 @@ VBX_API int vbx_fm_finalize(const double* sums, int32_t npairs, float scale, flo
  * (either may be NULL); go is a device scalar. */
 VBX_API int vbx_l1_pair_bwd(const float* a, const float* b, int64_t n, const double* sums, const float* go,
                     float scale, float* da, float* db, void* stream);
+/* coef[2i] = go*scale/S_a_i, coef[2i+1] = go*scale*S_ab_i/S_a_i^2 for npairs layers (sums as vbx_l1_pair_sums left
+ * them): the two scalars of the line above, for the conv epilogue's fm_coef and for vbx_fm_gate_bwd. */
+VBX_API int vbx_fm_coef(const double* sums, int32_t npairs, const float* go, float scale, float* coef, void* stream);
+/* out = ((g ? g : 0) + coef[0]*sign(y-other) - coef[1]*sign(y)) * (y > 0 ? 1 : gate_slope): the epilogue's gate stage
+ * as a stand-alone pass, for a feature whose consumer's input gradient is not part of the backward pass being run
+ * (other / coef may be NULL: plain LeakyReLU backward from the activation). */
+VBX_API int vbx_fm_gate_bwd(const float* y, const float* other, const float* coef, float gate_slope, const float* g,
+                    int64_t n, float* out, void* stream);
 /* Hinge (losses/hinge_loss.py:35-43): acc[0] += scale * sum relu(1 - target*c) ; acc is a double. */
 VBX_API int vbx_hinge_fwd(const float* c, int64_t n, float target, float scale, double* acc, void* stream);
 /* dc = go * scale * (1 - target*c > 0 ? -target : 0) */

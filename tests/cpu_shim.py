@@ -44,11 +44,36 @@ def _untranspose(wt, g):
     return wt.reshape(g.groups, Cin_g, Cout_g, g.K).permute(0, 2, 1, 3).reshape(g.Cout, Cin_g, g.K)
 
 
-def conv1d_dgrad(dy, wt, g, Tin, res=None, slope=1.0, out=None, beta=0.0, bias=None, nsplit=2):
+def conv1d_dgrad(dy, wt, g, Tin, res=None, slope=1.0, out=None, beta=0.0, bias=None, nsplit=2, gate=None):
     with torch.enable_grad():
         x0 = torch.zeros(dy.shape[0], g.Cin, Tin, requires_grad=True)
         (dx,) = torch.autograd.grad(_conv(x0, _untranspose(wt, g), g), x0, dy)
-    return _epi(dx, bias, res, slope, False, out, beta)
+    if gate is None:
+        return _epi(dx, bias, res, slope, False, out, beta)
+    assert out is None and not beta
+    y, gslope, other, coef = gate
+    return fm_gate_bwd(y, other, coef, gslope, _epi(dx, bias, res, slope, False, None, 0.0))
+
+
+def fm_coef(sums, n, go, scale):
+    s = sums.view(n, 2)
+    g = go.view(()).float() * scale
+    return torch.stack([(1.0 / s[:, 1]).float() * g, (s[:, 0] / (s[:, 1] * s[:, 1])).float() * g], 1).reshape(-1)
+
+
+def fm_gate_bwd(y, other, coef, gate_slope, g):
+    v = g if g is not None else torch.zeros_like(y)
+    if other is not None:
+        v = v + (coef[0] * torch.sign(y - other) - coef[1] * torch.sign(y))
+    return v * torch.where(y > 0, 1.0, gate_slope)
+
+
+def record_event():
+    return None
+
+
+def wait_event(ev):
+    return None
 
 
 def conv1d_wgrad(x, dy, g, dw=None):

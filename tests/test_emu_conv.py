@@ -63,6 +63,30 @@ def test_emulated_kernels_match_torch(case):
     assert (dx2.double() - gx).abs().max() < 2e-5
 
 
+def test_dgrad_gate_stage_matches_the_unfused_passes():
+    """vbx_epilogue's gate stage: (dgrad + res + feature-matching gradient of y) * LeakyReLU'(y), bit for bit what the three
+    separate passes it replaces compute (aten::add, L1-pair backward, LeakyReLU backward)."""
+    torch.manual_seed(3)
+    B, Cin, Cout, Tin, K, groups = 2, 12, 24, 50, 7, 4
+    To = tout(Tin, K, 2, 1, 3)
+    desc = ConvDesc(B, Cin, Cout, Tin, To, K, 2, 1, 3, 0, groups)
+    w, dy = torch.randn(Cout, Cin // groups, K), torch.randn(B, Cout, To)
+    y, other = torch.randn(B, Cin, Tin), torch.randn(B, Cin, Tin)
+    y[0, 0, :5] = other[0, 0, :5]                         # sign(0) terms
+    y[0, 1, :5] = 0.0
+    coef = torch.tensor([0.37, 0.011])
+    plain = torch.empty(B, Cin, Tin)
+    emu(1, desc, dy, transpose_weight(w, groups), plain)
+    fm = coef[0] * torch.sign(y - other) - coef[1] * torch.sign(y)
+    want_fm = (plain + fm) * torch.where(y > 0, 1.0, 0.2)
+    want_plain = plain * torch.where(y > 0, 1.0, 0.2)
+    got = torch.empty(B, Cin, Tin)
+    emu(1, desc, dy, transpose_weight(w, groups), got, gate=(y, 0.2, other, coef))
+    assert torch.equal(got, want_fm)
+    emu(1, desc, dy, transpose_weight(w, groups), got, gate=(y, 0.2, None, None))
+    assert torch.equal(got, want_plain)
+
+
 def test_dgrad_accumulates_with_beta():
     torch.manual_seed(0)
     B, Cin, Cout, Tin, K = 1, 8, 8, 64, 3

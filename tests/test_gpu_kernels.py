@@ -312,6 +312,44 @@ TC_CASES = [
 ]
 
 
+GATE_CASES = CASES[:6] + DIRECT_CASES + TC_CASES
+
+
+@pytest.mark.parametrize("case", GATE_CASES, ids=[str(c) for c in GATE_CASES])
+def test_input_gradient_gate_stage_equals_the_separate_passes(case):
+    """vbx_epilogue gate stage on every input-gradient kernel form (fp32 FMA, direct, tensor-core gather / slab / persistent
+    / merged phases): dgrad with gate == LeakyReLU'(y) * (dgrad + L1-pair backward of y), BIT FOR BIT the result of the
+    passes it replaces (vbx_l1_pair_bwd, aten::add, vbx_leaky_relu_bwd), with and without the feature-matching term."""
+    from vibravox_b200 import ops
+    B, Cin, Cout, Tin, K, s, d, pad, refl, groups = case
+    geom = ops.ConvGeom(Cin, Cout, K, s, d, pad, refl, groups)
+    torch.manual_seed(sum(case) + 1)
+    To = tout(Tin, K, s, d, pad)
+    w = (torch.randn(Cout, Cin // groups, K) / (Cin // groups * K) ** 0.5).to(DEV)
+    dy = torch.randn(B, Cout, To, device=DEV)
+    y, other = torch.randn(B, Cin, Tin, device=DEV), torch.randn(B, Cin, Tin, device=DEV)
+    y[0, 0, :3] = other[0, 0, :3]
+    y[0, 0, 3:6] = 0.0
+    sums = torch.tensor([float((y - other).abs().sum()), float(y.abs().sum())], device=DEV, dtype=torch.float64)
+    go = torch.tensor([0.7], device=DEV)
+    coef = ops.fm_coef(sums, 1, go, 0.125)
+    da, _ = ops.l1_pair_bwd(y, other, sums, go, 0.125, True, False)
+    wt = ops.transpose_weight(w, groups)
+    for tc in ([False, True] if ops.use_tc(geom, "dgrad") else [False]):
+        def dgrad(gate=None):
+            if tc:
+                return ops.tc_conv1d_dgrad(dy, ops.tc_pack(w, geom, 1), geom, Tin, gate=gate)
+            return ops.conv1d_dgrad(dy, wt, geom, Tin, gate=gate)
+        plain = dgrad()
+        want_fm = ops.leaky_relu_bwd(plain + da, y, 0.2)
+        want = ops.leaky_relu_bwd(plain, y, 0.2)
+        assert torch.equal(dgrad((y, 0.2, other, coef)), want_fm), tc
+        assert torch.equal(dgrad((y, 0.2, None, None)), want), tc
+    assert torch.equal(ops.fm_gate_bwd(y, other, coef, 0.2, plain), want_fm)
+    assert torch.equal(ops.fm_gate_bwd(y, other, coef, 0.2, None), ops.leaky_relu_bwd(da, y, 0.2))
+    assert torch.equal(ops.fm_gate_bwd(y, None, None, 0.2, plain), want)
+
+
 @pytest.mark.parametrize("case", TC_CASES, ids=[str(c) for c in TC_CASES])
 def test_tensor_core_conv_family_matches_fp64(case):
     """tcgen05 kernels (bf16x3 split operands, fp32 TMEM accumulate) vs torch fp64: forward with the fused

@@ -321,6 +321,45 @@ def test_graph_replay_is_bit_identical_to_eager_in_deterministic_mode(golden_dir
             assert torch.equal(a, b), (name, k)
 
 
+def test_fused_chain_backward_is_bit_identical_to_the_separate_passes(golden_dir, monkeypatch):
+    """functional.Flags chain contract on the GPU: with vbx_set_deterministic(1) the step with the discriminator backward
+    fused into the input-gradient epilogues (LeakyReLU', feature-matching gradient, gradient accumulation) and the step
+    with the separate passes (VBX_CHAIN_FUSION=0) must produce the same bits - losses, output, every parameter - over 3
+    steps, and the fused one launches fewer kernels."""
+    import vibravox_b200
+    from oracle import eben_oracle as O
+    from vibravox_b200 import _lib, ops
+    from vibravox_b200.lightning_modules import eben as eben_mod
+    gold = torch.load(os.path.join(golden_dir, "train_step.pt"))
+    body, air = O.synthetic_pairs(gold["B"], gold["S"], seed=gold["data_seed"])
+    batch = {"audio_body_conducted": body.to(DEV), "audio_airborne": air.to(DEV)}
+
+    def run(fused):
+        monkeypatch.setattr(eben_mod, "_CHAIN_FUSION", fused)
+        lm = vibravox_b200.build_model(seed=gold["model_seed"], device=DEV)
+        tr = []
+        n0 = _lib.load().vbx_launch_count()
+        for it in range(3):
+            out = lm.training_step(batch)
+            tr.append([v.clone() for k, v in sorted(lm.logged.items())] + [out["enhanced"].clone()])
+        torch.cuda.synchronize()
+        return lm, tr, _lib.load().vbx_launch_count() - n0
+
+    prev = ops.set_deterministic(True)
+    try:
+        lm_f, tr_f, n_f = run(True)
+        lm_u, tr_u, n_u = run(False)
+    finally:
+        ops.set_deterministic(prev)
+    assert n_f < n_u - 3 * 60, (n_f, n_u)
+    for it in range(3):
+        for a, b in zip(tr_f[it], tr_u[it]):
+            assert torch.equal(a, b), (it, (a - b).abs().max())
+    for name in ("generator", "discriminator"):
+        for (k, a), (_, b) in zip(getattr(lm_f, name).state_dict().items(), getattr(lm_u, name).state_dict().items()):
+            assert torch.equal(a, b), (name, k)
+
+
 def _rel(a, b, floor=1e-3):
     return abs(a - b) / max(abs(b), floor)
 

@@ -75,6 +75,55 @@ def test_training_step_schedule_matches_reference_golden(golden_dir, schedule):
         assert abs(float(gsd[k].double().sum()) - v) <= 5e-3 * n ** 0.5 + 1e-3, k
 
 
+def test_fused_discriminator_chain_backward_equals_the_separate_passes(golden_dir, monkeypatch):
+    """functional.Flags chain contract: with the fusion on, no L1-pair backward and no LeakyReLU backward with an input
+    gradient run for the discriminator stages (the conv input-gradient epilogues do that work), every registered
+    feature-matching term is consumed, and the step lands on the same parameters as with the fusion off."""
+    import vibravox_b200
+    from vibravox_b200 import ops
+    from vibravox_b200.lightning_modules import eben as eben_mod
+    gold = torch.load(os.path.join(golden_dir, "train_step.pt"))
+    body, air = O.synthetic_pairs(gold["B"], gold["S"], seed=gold["data_seed"])
+    results = {}
+    for fused in (True, False):
+        monkeypatch.setattr(eben_mod, "_CHAIN_FUSION", fused)
+        with cpu_ops():
+            calls = {"l1_pair_bwd": 0, "lrelu_dx_from_y": 0, "gate": 0, "fm_gate_bwd": 0}
+            real_l1, real_lr, real_dg, real_fg = ops.l1_pair_bwd, ops.leaky_relu_bwd, ops.conv1d_dgrad, ops.fm_gate_bwd
+
+            def l1(*a, **k):
+                calls["l1_pair_bwd"] += 1
+                return real_l1(*a, **k)
+
+            def lr(dy, ref, slope, mask=None, dbias=None, want_dx=True):
+                calls["lrelu_dx_from_y"] += int(want_dx and ref is not None and slope == 0.2)
+                return real_lr(dy, ref, slope, mask=mask, dbias=dbias, want_dx=want_dx)
+
+            def dg(*a, gate=None, **k):
+                calls["gate"] += int(gate is not None)
+                return real_dg(*a, gate=gate, **k)
+
+            def fg(*a, **k):
+                calls["fm_gate_bwd"] += 1
+                return real_fg(*a, **k)
+            ops.l1_pair_bwd, ops.leaky_relu_bwd, ops.conv1d_dgrad, ops.fm_gate_bwd = l1, lr, dg, fg
+            lm = vibravox_b200.build_model(seed=gold["model_seed"], device="cpu")
+            lm.schedule = "shared"
+            lm.training_step({"audio_body_conducted": body, "audio_airborne": air})
+            results[fused] = (calls, {k: v.clone() for k, v in lm.state_dict().items()},
+                              {k: float(v) for k, v in lm.logged.items()})
+    on, off = results[True][0], results[False][0]
+    assert off["gate"] == 0 and off["l1_pair_bwd"] > 0 and off["lrelu_dx_from_y"] > 0
+    assert on["l1_pair_bwd"] == 0 and on["lrelu_dx_from_y"] == 0 and on["gate"] > 0
+    # 4 chains: in the feature-matching pass the last feature of each chain has no downstream conv in the pass
+    assert on["fm_gate_bwd"] == 4
+    for k, v in results[False][1].items():
+        if v.is_floating_point():
+            assert relerr(results[True][1][k], v) < 2e-5, k
+    for k, v in results[False][2].items():
+        assert results[True][2][k] == pytest.approx(v, rel=1e-5, abs=1e-6), k
+
+
 def test_flat_adam_state_dict_is_torch_adam_compatible():
     """FlatAdam.state_dict() is the layout torch.optim.Adam writes: a torch Adam loaded from it takes the same next
     step, and FlatAdam loaded from a torch Adam state continues that optimizer's trajectory."""

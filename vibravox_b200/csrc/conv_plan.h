@@ -52,10 +52,13 @@ inline void fill(GemmP& P, const vbx_conv_desc* d) {
   P.mtiles = 1; P.split = 0;
   P.W = nullptr; P.X = nullptr; P.DY = nullptr; P.Y = nullptr;
   P.bias = nullptr; P.res = nullptr; P.mask = nullptr; P.slope = 1.f; P.beta = 0.f;
+  P.gate = nullptr; P.fm_other = nullptr; P.fm_coef = nullptr; P.gate_slope = 1.f;
 }
 inline void fill_epi(GemmP& P, const vbx_epilogue* e) {
   if (!e) return;
   P.bias = e->bias; P.res = e->res; P.mask = e->mask; P.slope = e->slope; P.beta = e->beta;
+  P.gate = e->gate; P.gate_slope = e->gate_slope;
+  P.fm_other = e->gate ? e->fm_other : nullptr; P.fm_coef = P.fm_other ? e->fm_coef : nullptr;
 }
 
 struct Plan { int tm; bool bk; int grid[3]; };

@@ -18,6 +18,11 @@ __device__ __forceinline__ float dir_finish(const GemmP& P, float v, int ch, lon
   if (P.mask) P.mask[idx] = v > 0.f ? 1 : 0;
   if (P.slope != 1.f) v = v > 0.f ? v : v * P.slope;
   if (P.res) v += P.res[idx];
+  if (P.gate) {
+    const bool fm = P.fm_other != nullptr;
+    v = gate_apply(v, P.gate[idx], fm, fm ? P.fm_other[idx] : 0.f, fm ? P.fm_coef[0] : 0.f, fm ? P.fm_coef[1] : 0.f,
+                   P.gate_slope);
+  }
   if (P.beta != 0.f) v += P.beta * P.Y[idx];
   return v;
 }

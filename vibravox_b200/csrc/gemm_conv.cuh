@@ -52,7 +52,27 @@ struct GemmP {
   unsigned char* mask;    // optional: 1 where pre-activation > 0
   float slope;            // LeakyReLU slope on the output (1 = identity)
   float beta;             // Y = beta*Y_old + result (0 = overwrite)
+  const float* gate;      // optional (vbx_epilogue): activation y the output is a gradient of; v *= y > 0 ? 1 : gate_slope
+  const float* fm_other;  // optional, with gate: v += fm_coef[0]*sign(y - fm_other) - fm_coef[1]*sign(y) before the gate
+  const float* fm_coef;
+  float gate_slope;
 };
+
+// the gate stage of vbx_epilogue on one value (exact products: sign() is -1/0/1, so the sum below rounds exactly like
+// the unfused  grad_fm = c1*sd - c2*sg;  g = dgrad + grad_fm;  g * lrelu'(y)  it replaces)
+VBX_HD float gate_apply(float v, float y, bool fm, float other, float c1, float c2, float gslope) {
+  if (fm) {
+    const float d = y - other;
+    const float sd = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+    const float sg = y > 0.f ? 1.f : (y < 0.f ? -1.f : 0.f);
+#ifdef __CUDA_ARCH__
+    v = __fadd_rn(v, __fsub_rn(__fmul_rn(c1, sd), __fmul_rn(c2, sg)));
+#else
+    { volatile float f = c1 * sd - c2 * sg; v = v + f; }
+#endif
+  }
+  return y > 0.f ? v : v * gslope;
+}
 
 struct Blk { int x, y, z; };
 
@@ -406,6 +426,11 @@ VBX_UNROLL
     if (P.mask) P.mask[idx] = v > 0.f ? 1 : 0;
     if (P.slope != 1.f) v = v > 0.f ? v : v * P.slope;
     if (P.res) v += P.res[idx];
+    if (P.gate) {
+      const bool fm = P.fm_other != nullptr;
+      v = gate_apply(v, P.gate[idx], fm, fm ? P.fm_other[idx] : 0.f, fm ? P.fm_coef[0] : 0.f, fm ? P.fm_coef[1] : 0.f,
+                     P.gate_slope);
+    }
     if (P.beta != 0.f) v += P.beta * P.Y[idx];
     return v;
   }

@@ -378,6 +378,25 @@ __global__ void l1_pair_bwd_kernel(const float* __restrict__ a, const float* __r
     if (db) db[i] = -c1 * sd;
   }
 }
+// the two scalars of l1_pair_bwd_kernel per layer, for the conv epilogue's gate stage and fm_gate_bwd_kernel
+__global__ void fm_coef_kernel(const double* __restrict__ sums, int n, const float* __restrict__ go, float scale,
+                               float* __restrict__ coef) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double s_ab = sums[2 * i], s_a = sums[2 * i + 1];
+  const float gsc = go[0] * scale;
+  coef[2 * i] = (float)(1.0 / s_a) * gsc;
+  coef[2 * i + 1] = (float)(s_ab / (s_a * s_a)) * gsc;
+}
+__global__ void fm_gate_bwd_kernel(const float* __restrict__ y, const float* __restrict__ other,
+                                   const float* __restrict__ coef, float gslope, const float* __restrict__ g,
+                                   long long n, float* __restrict__ out) {
+  const bool fm = other != nullptr;
+  const float c1 = fm ? coef[0] : 0.f, c2 = fm ? coef[1] : 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = vbx::gate_apply(g ? g[i] : 0.f, y[i], fm, fm ? other[i] : 0.f, c1, c2, gslope);
+}
 __global__ void __launch_bounds__(256) hinge_fwd_kernel(const float* __restrict__ c, long long n, float target, float scale,
                                  double* __restrict__ acc) {
   __shared__ double sh[32];
@@ -730,6 +749,19 @@ extern "C" int vbx_l1_pair_bwd(const float* a, const float* b, int64_t n, const 
   VBX_REQUIRE(n > 0, VBX_BAD_SHAPE, "l1_pair_bwd: empty");
   l1_pair_bwd_kernel<<<stream_blocks(n, 1024), 256, 0, ST>>>(a, b, n, sums, go, scale, da, db);
   return launched("l1_pair_bwd_kernel");
+}
+extern "C" int vbx_fm_coef(const double* sums, int32_t npairs, const float* go, float scale, float* coef, void* stream) {
+  VBX_REQUIRE(sums && go && coef, VBX_BAD_POINTER, "fm_coef: null tensor");
+  VBX_REQUIRE(npairs > 0, VBX_BAD_SHAPE, "fm_coef: no layers");
+  fm_coef_kernel<<<cdiv(npairs, 64), 64, 0, ST>>>(sums, npairs, go, scale, coef);
+  return launched("fm_coef_kernel");
+}
+extern "C" int vbx_fm_gate_bwd(const float* y, const float* other, const float* coef, float gate_slope, const float* g,
+                               int64_t n, float* out, void* stream) {
+  VBX_REQUIRE(y && out && (!other || coef), VBX_BAD_POINTER, "fm_gate_bwd: null tensor");
+  VBX_REQUIRE(n > 0, VBX_BAD_SHAPE, "fm_gate_bwd: empty");
+  fm_gate_bwd_kernel<<<stream_blocks(n, 1024), 256, 0, ST>>>(y, other, coef, gate_slope, g, n, out);
+  return launched("fm_gate_bwd_kernel");
 }
 extern "C" int vbx_hinge_fwd(const float* c, int64_t n, float target, float scale, double* acc, void* stream) {
   VBX_REQUIRE(c && acc, VBX_BAD_POINTER, "hinge_fwd: null tensor");

@@ -110,8 +110,33 @@ __device__ __forceinline__ float finish(const GemmP& P, float v, int ch, long lo
   if (P.mask) P.mask[idx] = v > 0.f ? 1 : 0;
   if (P.slope != 1.f) v = v > 0.f ? v : v * P.slope;
   if (P.res) v += P.res[idx];
+  if (P.gate) {
+    const bool fm = P.fm_other != nullptr;
+    v = gate_apply(v, P.gate[idx], fm, fm ? P.fm_other[idx] : 0.f, fm ? P.fm_coef[0] : 0.f, fm ? P.fm_coef[1] : 0.f,
+                   P.gate_slope);
+  }
   if (P.beta != 0.f) v += P.beta * P.Y[idx];
   return v;
+}
+
+// gate stage of the full-block epilogue paths: 16 channel rows of one time column, loads issued before use
+__device__ __forceinline__ void gate_block16(const GemmP& G, long long o, long long Tlen, float (&acc)[16]) {
+  const bool fm = G.fm_other != nullptr;
+  const float c1 = fm ? __ldg(G.fm_coef) : 0.f, c2 = fm ? __ldg(G.fm_coef + 1) : 0.f;
+#pragma unroll
+  for (int h = 0; h < 16; h += 8) {                     // (two halves: 16 more live registers, not 32)
+    const float* gp = G.gate + o + (long long)h * Tlen;
+    float y[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = gp[(long long)j * Tlen];
+    if (fm) {
+      const float* op = G.fm_other + o + (long long)h * Tlen;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b[j] = op[(long long)j * Tlen];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[h + j] = gate_apply(acc[h + j], y[j], fm, fm ? b[j] : 0.f, c1, c2, G.gate_slope);
+  }
 }
 
 // MODE FWD  : rows (b,t),  cols co, reduction (ci,k):  A = x[b,ci,map(t*s + k*d - pad)]
@@ -359,6 +384,7 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const TcP P) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) acc[j] += r[j];
         }
+        if (MODE == DGRAD && G.gate) gate_block16(G, o, Tlen, acc);    // (the gate stage belongs to input gradients)
         float* yp = G.Y + o;
 #pragma unroll
         for (int j = 0; j < 16; ++j) yp[(long long)j * Tlen] = acc[j];

@@ -87,6 +87,7 @@ __device__ __forceinline__ void slab_epilogue(const TcP& P, uint32_t tmem_base, 
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[j] += r[j];
       }
+      if (G.gate) gate_block16(G, o, Tlen, acc);
       float* yp = G.Y + o;
 #pragma unroll
       for (int j = 0; j < 16; ++j) yp[(long long)j * Tlen] = acc[j];

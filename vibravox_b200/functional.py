@@ -30,6 +30,36 @@ class Flags:
     w.r.t. graph-leaf inputs (the detached generator outputs) OFF."""
     param_grads = True
     skip_leaf_input_grad = False
+    # Fused backward of a discriminator chain (ConvFn -> ConvFn -> ..., every stage output also read by the
+    # feature-matching loss).  While `gated_chain` is set, the discriminator forwards tell each stage the slope of the stage
+    # that produced its input; in the backward pass the stage's input-gradient epilogue then multiplies by LeakyReLU'(x)
+    # and adds x's feature-matching gradient itself, instead of leaving an aten::add (gradient accumulation), an L1-pair
+    # backward pass and a LeakyReLU backward pass to run between the two convs.  The hand-over between backward nodes goes
+    # through the two tables below, keyed by the activation's storage: `pending` = feature-matching terms registered by
+    # FeatureMatchingFn.backward and not yet applied, `gated` = activations whose incoming gradient already carries their
+    # LeakyReLU'.  CONTRACT: a tensor produced under `gated_chain` may only be consumed by the next stage of its chain and
+    # by FeatureMatchingFn (vibravox_b200.lightning_modules.eben sets the flag around its discriminator calls only).
+    gated_chain = False
+    pending: dict = {}
+    gated: set = set()
+
+    @classmethod
+    def chain_reset(cls) -> None:
+        cls.pending.clear()
+        cls.gated.clear()
+
+    @classmethod
+    def chain_check(cls) -> None:
+        """After a backward pass: every registered feature-matching term must have been applied by some stage."""
+        left = len(cls.pending)
+        cls.chain_reset()
+        if left:
+            raise RuntimeError(f"{left} feature-matching gradient terms were registered for fused application but no "
+                               "ConvFn stage consumed them")
+
+
+def _key(t: Tensor):
+    return (t.data_ptr(), t.numel())
 
 
 def grad_slot(p: Tensor) -> Optional[Tensor]:
@@ -79,18 +109,22 @@ class TransposeWeightFn(Function):
 
 
 class ConvFn(Function):
-    """y = LeakyReLU_slope(conv1d(x, w) + bias), halo (reflect and/or zero) folded into the kernel."""
+    """y = LeakyReLU_slope(conv1d(x, w) + bias), halo (reflect and/or zero) folded into the kernel.
+    `in_slope` != 1 (set by the discriminator forwards under Flags.gated_chain): x is the LeakyReLU_in_slope output of the
+    previous ConvFn of a chain, and this stage's input-gradient kernel finishes that stage's backward (see Flags)."""
 
     @staticmethod
     def forward(ctx, x: Tensor, w: Tensor, wt: Optional[Tensor], bias: Optional[Tensor], geom: ConvGeom,
-                slope: float):
+                slope: float, in_slope: float = 1.0):
         x_leaf = x.is_leaf                      # before any copy: is x a graph leaf (e.g. a detached G output)?
         x, w = _c(x), _c(w)
         y = ops.conv_fwd(x, w, geom, bias=bias, slope=slope)
         ctx.geom, ctx.slope, ctx.has_bias = geom, slope, bias is not None
+        ctx.in_slope = in_slope
         ctx.w_slot = grad_slot(w)
         ctx.b_slot = grad_slot(bias) if bias is not None else None
         ctx.x_leaf = x_leaf
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(x, w, wt, y if slope != 1.0 else None)
         return y
 
@@ -99,25 +133,58 @@ class ConvFn(Function):
     def backward(ctx, gy):
         x, w, wt, y = ctx.saved_tensors
         geom, slope = ctx.geom, ctx.slope
-        gy = _c(gy)
+        # hand-over from the stages downstream (Flags): is gy already multiplied by this stage's LeakyReLU', and is there a
+        # feature-matching term of y that nobody applied (its consumer's input gradient is not part of this pass)?
+        pre_gated, pend = False, None
+        if y is not None and (Flags.gated or Flags.pending):
+            ky = _key(y)
+            pre_gated = ky in Flags.gated
+            Flags.gated.discard(ky)
+            pend = Flags.pending.pop(ky, None)
+        if gy is None and pend is None:
+            return (None,) * 7
+        gy = _c(gy) if gy is not None else None
         need_x, need_w, _, need_b = ctx.needs_input_grad[:4]
         need_w, need_b = need_w and Flags.param_grads, need_b and Flags.param_grads
         need_x = need_x and not (Flags.skip_leaf_input_grad and ctx.x_leaf)
         dbias = None
         if ctx.has_bias and need_b:
             dbias = ctx.b_slot if ctx.b_slot is not None else \
-                torch.zeros((geom.Cout,), device=gy.device, dtype=torch.float32)
-        gp = gy
-        if slope != 1.0 or dbias is not None:
-            out = ops.leaky_relu_bwd(gy, y, slope, dbias=dbias, want_dx=slope != 1.0)
-            gp = out if out is not None else gy
+                torch.zeros((geom.Cout,), device=x.device, dtype=torch.float32)
+        if pend is not None:
+            other, coef, ev = pend
+            ops.wait_event(ev)
+            # (a gy that arrives here came from consumers outside the chain contract and is not gated yet)
+            assert not pre_gated
+            gp = ops.fm_gate_bwd(y, other, coef, slope, gy)
+            if dbias is not None:
+                ops.leaky_relu_bwd(gp, None, 1.0, dbias=dbias, want_dx=False)
+        elif pre_gated:
+            gp = gy
+            if dbias is not None:
+                ops.leaky_relu_bwd(gp, None, 1.0, dbias=dbias, want_dx=False)
+        else:
+            gp = gy
+            if slope != 1.0 or dbias is not None:
+                out = ops.leaky_relu_bwd(gy, y, slope, dbias=dbias, want_dx=slope != 1.0)
+                gp = out if out is not None else gy
         dx = dw = None
         if need_x:
-            dx = ops.conv_dgrad(gp, w, wt, geom, x.shape[2])
+            gate = None
+            if ctx.in_slope != 1.0:
+                kx = _key(x)
+                term = Flags.pending.pop(kx, None)
+                if term is not None:
+                    ops.wait_event(term[2])
+                    gate = (x, ctx.in_slope, term[0], term[1])
+                else:
+                    gate = (x, ctx.in_slope, None, None)
+                Flags.gated.add(kx)
+            dx = ops.conv_dgrad(gp, w, wt, geom, x.shape[2], gate=gate)
         if need_w:
             dw = ops.conv_wgrad(x, gp, geom, dw=ctx.w_slot)
         return (dx, None if ctx.w_slot is not None else dw, None,
-                None if ctx.b_slot is not None else dbias, None, None)
+                None if ctx.b_slot is not None else dbias, None, None, None)
 
 
 class ConvTransposeFn(Function):
@@ -276,16 +343,18 @@ class PQMFSynthesisFn(Function):
 
 
 class FeatureMatchingFn(Function):
-    """sum_i mean|a_i - b_i| / mean|a_i|, times `scale`   (losses/feature_loss.py:37-50)."""
+    """sum_i mean|a_i - b_i| / mean|a_i|, times `scale`   (losses/feature_loss.py:37-50).
+    `fused` (every a_i is a stage output of a discriminator chain run under Flags.gated_chain): the backward hands the
+    gradient terms of the a_i to the conv stages (Flags.pending) instead of materialising them."""
 
     @staticmethod
-    def forward(ctx, scale: float, n: int, *tensors: Tensor):
+    def forward(ctx, scale: float, n: int, fused: bool, *tensors: Tensor):
         a, b = [_c(t) for t in tensors[:n]], [_c(t) for t in tensors[n:]]
         sums = torch.zeros((2 * n,), device=a[0].device, dtype=torch.float64)
         for i in range(n):
             ops.l1_pair_sums(a[i], b[i], sums[2 * i:2 * i + 2])
         loss = ops.fm_finalize(sums, n, scale)
-        ctx.scale, ctx.n, ctx.sums = scale, n, sums
+        ctx.scale, ctx.n, ctx.sums, ctx.fused = scale, n, sums, fused
         ctx.save_for_backward(*a, *b)
         return loss
 
@@ -296,11 +365,24 @@ class FeatureMatchingFn(Function):
         a, b = ctx.saved_tensors[:n], ctx.saved_tensors[n:]
         go = _c(go).float()
         grads: List[Optional[Tensor]] = [None] * (2 * n)
+        need_a = [ctx.needs_input_grad[3 + i] for i in range(n)]
+        need_b = [ctx.needs_input_grad[3 + n + i] and Flags.param_grads for i in range(n)]
+        if ctx.fused:
+            if any(need_b):
+                raise NotImplementedError("fused feature-matching backward: gradients w.r.t. the second (reference) "
+                                          "feature list are not part of the shared-schedule step")
+            if any(need_a):
+                coef = ops.fm_coef(sums, n, go, ctx.scale)
+                ev = ops.record_event()
+                for i in range(n):
+                    if need_a[i]:
+                        Flags.pending[_key(a[i])] = (b[i], coef[2 * i:2 * i + 2], ev)
+            return (None, None, None, *grads)
         for i in range(n):
-            na, nb = ctx.needs_input_grad[2 + i], ctx.needs_input_grad[2 + n + i] and Flags.param_grads
-            if na or nb:
-                grads[i], grads[n + i] = ops.l1_pair_bwd(a[i], b[i], sums[2 * i:2 * i + 2], go, ctx.scale, na, nb)
-        return (None, None, *grads)
+            if need_a[i] or need_b[i]:
+                grads[i], grads[n + i] = ops.l1_pair_bwd(a[i], b[i], sums[2 * i:2 * i + 2], go, ctx.scale, need_a[i],
+                                                         need_b[i])
+        return (None, None, None, *grads)
 
 
 class HingeFn(Function):

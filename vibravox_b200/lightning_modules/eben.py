@@ -21,6 +21,10 @@ from ..optim import FlatAdam
 from ..parallel import allreduce_sum_
 from ..torch_modules.utils import share_weight_norm
 
+# fused backward of the discriminator chains (functional.Flags); VBX_CHAIN_FUSION=0 restores the separate aten::add /
+# L1-pair backward / LeakyReLU backward passes between the conv stages
+_CHAIN_FUSION = __import__("os").environ.get("VBX_CHAIN_FUSION", "1") != "0"
+
 
 class _SegmentedStep:
     """A training step captured as consecutive CUDA graphs; after graph i the i-th gradient bucket is sum-all-reduced
@@ -298,20 +302,30 @@ class EBENLightningModule(torch.nn.Module):
                 losses = OrderedDict()
                 if self.reconstructive_loss_freq_fn:
                     losses["reconstructive_loss_freq"] = self.reconstructive_loss_freq_fn(enh, reference_speech)
-                if hasattr(D, "forward_multi"):
-                    enhanced_embeddings, reference_embeddings = D.forward_multi(
-                        [(bands, enh), (reference_bands, reference_speech)])
-                else:
-                    enhanced_embeddings = D(bands=bands, audio=enh)
-                    reference_embeddings = D(bands=reference_bands, audio=reference_speech)
+                # the stage outputs below are consumed by the next stage, the feature-matching loss and (last one) the hinge
+                # loss only: the chain contract of functional.Flags, which lets every input-gradient kernel finish the
+                # LeakyReLU / feature-matching backward of the stage before it
+                Flags.gated_chain = _CHAIN_FUSION
+                try:
+                    if hasattr(D, "forward_multi"):
+                        enhanced_embeddings, reference_embeddings = D.forward_multi(
+                            [(bands, enh), (reference_bands, reference_speech)])
+                    else:
+                        enhanced_embeddings = D(bands=bands, audio=enh)
+                        reference_embeddings = D(bands=reference_bands, audio=reference_speech)
+                finally:
+                    Flags.gated_chain = False
                 losses["feature_matching_loss"] = self.feature_matching_loss_fn(enhanced_embeddings,
                                                                                 reference_embeddings)
                 losses["adv_loss_gen"] = self.adversarial_loss_fn(embeddings=enhanced_embeddings, target=1)
                 for key, value in losses.items():
                     self.log(f"train/generator/{key}", value, sync_dist=True)
                 # each loss once, down to the generator outputs
-                grads = [torch.autograd.grad(l, (enh, bands), retain_graph=True, allow_unused=True)
-                         for l in losses.values()]
+                grads = []
+                for l in losses.values():
+                    Flags.chain_reset()
+                    grads.append(torch.autograd.grad(l, (enh, bands), retain_graph=True, allow_unused=True))
+                    Flags.chain_check()
                 self._join(D)
                 lambdas = self._balance_from_output_grads(enhanced, enhanced_bands, grads)
                 total_e = torch.empty_like(enh)
@@ -346,10 +360,12 @@ class EBENLightningModule(torch.nn.Module):
                 backprop_loss_discriminator = WeightedSumFn.apply(None, real_loss, fake_loss)
                 self.log("train/discriminator/backprop_loss", backprop_loss_discriminator, sync_dist=True)
                 Flags.skip_leaf_input_grad = True          # nothing upstream of the detached G outputs
+                Flags.chain_reset()
                 try:
                     torch.autograd.backward(backprop_loss_discriminator, inputs=d_params)
                 finally:
                     Flags.skip_leaf_input_grad = False
+                Flags.chain_check()
                 self._join(D)
                 self._sync_grads(d_opt)
                 d_opt.step()

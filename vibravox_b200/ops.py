@@ -66,8 +66,15 @@ class ConvGeom:
                         self.pad, self.refl, self.groups)
 
 
-def _epi(bias=None, res=None, mask=None, slope=1.0, beta=0.0) -> Epilogue:
-    return Epilogue(_p(bias), _p(res), _p(mask, torch.uint8), float(slope), float(beta))
+def _epi(bias=None, res=None, mask=None, slope=1.0, beta=0.0, gate=None) -> Epilogue:
+    """`gate` = (y, gate_slope, fm_other, fm_coef): the producer-side LeakyReLU' (+ feature-matching gradient) stage of an
+    input-gradient epilogue (include/vbx.h: vbx_epilogue)."""
+    if gate is None:
+        return Epilogue(_p(bias), _p(res), _p(mask, torch.uint8), float(slope), float(beta), None, None, None, 1.0)
+    y, gslope, other, coef = gate
+    assert (other is None) == (coef is None)
+    return Epilogue(_p(bias), _p(res), _p(mask, torch.uint8), float(slope), float(beta), _p(y), _p(other), _p(coef),
+                    float(gslope))
 
 
 # ------------------------------------------------------------------ conv family
@@ -89,7 +96,7 @@ def conv1d_fwd(x: Tensor, w: Tensor, g: ConvGeom, bias: Optional[Tensor] = None,
 
 def conv1d_dgrad(dy: Tensor, wt: Tensor, g: ConvGeom, Tin: int, res: Optional[Tensor] = None,
                  slope: float = 1.0, out: Optional[Tensor] = None, beta: float = 0.0,
-                 bias: Optional[Tensor] = None) -> Tensor:
+                 bias: Optional[Tensor] = None, gate=None) -> Tensor:
     """dx (B,Cin,Tin) from dy (B,Cout,Tout); also the forward of ConvTranspose1d."""
     B, Cout, Tout = dy.shape
     d = g.desc(B, Tin)
@@ -98,7 +105,9 @@ def conv1d_dgrad(dy: Tensor, wt: Tensor, g: ConvGeom, Tin: int, res: Optional[Te
     dx = out if out is not None else torch.empty((B, g.Cin, Tin), device=dy.device, dtype=torch.float32)
     if res is not None:
         assert res.shape == dx.shape
-    e = _epi(bias, res, None, slope, beta)
+    if gate is not None:
+        assert gate[0].shape == dx.shape and gate[0].is_contiguous() and (gate[2] is None or gate[2].shape == dx.shape)
+    e = _epi(bias, res, None, slope, beta, gate)
     check(_lib.load().vbx_conv1d_dgrad(ctypes.byref(d), _p(dy), _p(wt), ctypes.byref(e), _p(dx), _stream()),
           "vbx_conv1d_dgrad")
     return dx
@@ -159,14 +168,16 @@ def tc_conv1d_fwd(x: Tensor, packed: Tensor, g: ConvGeom, bias: Optional[Tensor]
 
 
 def tc_conv1d_dgrad(dy: Tensor, packed: Tensor, g: ConvGeom, Tin: int, res: Optional[Tensor] = None,
-                    slope: float = 1.0, nsplit: int = 2) -> Tensor:
+                    slope: float = 1.0, nsplit: int = 2, gate=None) -> Tensor:
     B, Cout, Tout = dy.shape
     d = g.desc(B, Tin)
     assert Cout == g.Cout and Tout == d.Tout, (dy.shape, g, Tin, d.Tout)
     dx = torch.empty((B, g.Cin, Tin), device=dy.device, dtype=torch.float32)
     if res is not None:
         assert res.shape == dx.shape
-    e = _epi(None, res, None, slope, 0.0)
+    if gate is not None:
+        assert gate[0].shape == dx.shape and gate[0].is_contiguous() and (gate[2] is None or gate[2].shape == dx.shape)
+    e = _epi(None, res, None, slope, 0.0, gate)
     check(_lib.load().vbx_tc_conv1d_dgrad(ctypes.byref(d), _p(dy), packed.data_ptr(), ctypes.byref(e), _p(dx),
                                           nsplit, _stream()), "vbx_tc_conv1d_dgrad")
     return dx
@@ -392,6 +403,33 @@ def l1_pair_bwd(a: Tensor, b: Tensor, sums: Tensor, go: Tensor, scale: float, wa
     return da, db
 
 
+def record_event():
+    """An event on the current stream (hand-over of side-channel tensors between backward nodes on different streams)."""
+    ev = torch.cuda.Event()
+    ev.record()
+    return ev
+
+
+def wait_event(ev) -> None:
+    torch.cuda.current_stream().wait_event(ev)
+
+
+def fm_coef(sums: Tensor, n: int, go: Tensor, scale: float) -> Tensor:
+    """(2n,) floats: per layer the two scalars of the feature-matching gradient (vbx_fm_coef)."""
+    coef = torch.empty((2 * n,), device=sums.device, dtype=torch.float32)
+    check(_lib.load().vbx_fm_coef(sums.data_ptr(), n, _p(go), scale, _p(coef), _stream()), "vbx_fm_coef")
+    return coef
+
+
+def fm_gate_bwd(y: Tensor, other: Optional[Tensor], coef: Optional[Tensor], gate_slope: float,
+                g: Optional[Tensor]) -> Tensor:
+    """((g or 0) + feature-matching gradient of y) * LeakyReLU'(y) as one pass (vbx_fm_gate_bwd)."""
+    out = torch.empty_like(y)
+    check(_lib.load().vbx_fm_gate_bwd(_p(y), _p(other), _p(coef), gate_slope, _p(g), y.numel(), _p(out), _stream()),
+          "vbx_fm_gate_bwd")
+    return out
+
+
 def hinge_fwd(c: Tensor, target: float, scale: float, acc: Tensor) -> None:
     check(_lib.load().vbx_hinge_fwd(_p(c), c.numel(), target, scale, _p(acc, torch.float64), _stream()),
           "vbx_hinge_fwd")
@@ -559,12 +597,15 @@ def conv_fwd(x: Tensor, w: Tensor, g: ConvGeom, bias=None, res=None, slope: floa
 
 
 def conv_dgrad(dy: Tensor, w: Tensor, wt: Optional[Tensor], g: ConvGeom, Tin: int, res=None, slope: float = 1.0,
-               nsplit: int = 2):
+               nsplit: int = 2, gate=None):
+    """`gate` = (y, gate_slope, fm_other | None, fm_coef | None): dx is the gradient of the activation y; the epilogue
+    adds y's feature-matching gradient and applies LeakyReLU'(y) (include/vbx.h: vbx_epilogue)."""
     if use_tc(g, "dgrad"):
-        return tc_conv1d_dgrad(dy, get_pack(w, g, TC_DGRAD, nsplit), g, Tin, res=res, slope=slope, nsplit=nsplit)
+        return tc_conv1d_dgrad(dy, get_pack(w, g, TC_DGRAD, nsplit), g, Tin, res=res, slope=slope, nsplit=nsplit,
+                               gate=gate)
     if wt is None:
         wt = transpose_weight(w, g.groups)
-    return conv1d_dgrad(dy, wt, g, Tin, res=res, slope=slope)
+    return conv1d_dgrad(dy, wt, g, Tin, res=res, slope=slope, gate=gate)
 
 
 def conv_wgrad(x: Tensor, dy: Tensor, g: ConvGeom, dw: Optional[Tensor] = None) -> Tensor:

@@ -18,7 +18,7 @@ except Exception:  # pragma: no cover
         pass
 
 from ..utils import normalized_conv1d
-from .melgan_discriminator import DiscriminatorMelGAN, prepare_stage, run_stage
+from .melgan_discriminator import DiscriminatorMelGAN, prepare_stage, run_chain
 
 
 class DiscriminatorEBEN(nn.Module):
@@ -44,10 +44,7 @@ class DiscriminatorEBEN(nn.Module):
         self.discriminator = nn.ModuleList(stages)
 
     def forward(self, bands: torch.Tensor) -> List[torch.Tensor]:
-        embeddings = [bands]
-        for stage in self.discriminator:
-            embeddings.append(run_stage(stage, embeddings[-1]))
-        return embeddings
+        return run_chain(self.discriminator, bands)
 
 
 class DiscriminatorEBENMultiScales(nn.Module, PyTorchModelHubMixin):

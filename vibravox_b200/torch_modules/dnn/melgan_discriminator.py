@@ -8,7 +8,7 @@ from typing import List
 import torch
 from torch import nn
 
-from ...functional import ConvFn
+from ...functional import ConvFn, Flags
 from ..utils import conv_geom, effective_weight, normalized_conv1d
 
 
@@ -31,6 +31,24 @@ def run_stage(stage: nn.Module, x: torch.Tensor) -> torch.Tensor:
     conv, extra, slope = _parse_stage(stage)
     w, wt = effective_weight(conv)
     return ConvFn.apply(x, w, wt, conv.bias, conv_geom(conv, extra), slope)
+
+
+def run_chain(stages, x: torch.Tensor) -> List[torch.Tensor]:
+    """[x, stage_1(x), stage_2(stage_1(x)), ...] - the embeddings list of the reference forwards.  Under
+    functional.Flags.gated_chain (the training step's discriminator calls) every stage is told the slope of the stage before
+    it, so that its input-gradient kernel finishes that stage's LeakyReLU / feature-matching backward, and the outputs are
+    tagged for the feature-matching loss."""
+    chain = Flags.gated_chain and torch.is_grad_enabled()
+    embeddings, prev_slope = [x], 1.0
+    for stage in stages:
+        conv, extra, slope = _parse_stage(stage)
+        w, wt = effective_weight(conv)
+        y = ConvFn.apply(embeddings[-1], w, wt, conv.bias, conv_geom(conv, extra), slope, prev_slope if chain else 1.0)
+        if chain and slope != 1.0:
+            y._vbx_chain = True
+        embeddings.append(y)
+        prev_slope = slope
+    return embeddings
 
 
 def prepare_stage(stage: nn.Module, backward: bool) -> list:
@@ -69,7 +87,4 @@ class DiscriminatorMelGAN(nn.Module):
         ])
 
     def forward(self, audio: torch.Tensor) -> List[torch.Tensor]:
-        embeddings = [audio]
-        for stage in self.discriminator:
-            embeddings.append(run_stage(stage, embeddings[-1]))
-        return embeddings
+        return run_chain(self.discriminator, audio)

@@ -17,4 +17,7 @@ class FeatureLossForDiscriminatorMelganMultiScales(torch.nn.Module):
                 b.append(layer_b)
         # reference divisor: number of scales x inner layers of the LAST scale (feature_loss.py:48)
         scale = 1.0 / (len(embeddings_a) * len(embeddings_a[-1][1:-1]))
-        return FeatureMatchingFn.apply(scale, len(a), *a, *b)
+        # stage outputs of a discriminator chain run under functional.Flags.gated_chain carry this tag: their gradient
+        # terms are then applied inside the conv stages' input-gradient kernels
+        fused = all(getattr(t, "_vbx_chain", False) for t in a)
+        return FeatureMatchingFn.apply(scale, len(a), fused, *a, *b)
