@@ -351,7 +351,7 @@ def test_fused_chain_backward_is_bit_identical_to_the_separate_passes(golden_dir
         lm_u, tr_u, n_u = run(False)
     finally:
         ops.set_deterministic(prev)
-    assert n_f < n_u - 3 * 60, (n_f, n_u)
+    assert n_f < n_u - 3 * 25, (n_f, n_u)       # at least the 27 L1-pair backward passes per step are gone
     for it in range(3):
         for a, b in zip(tr_f[it], tr_u[it]):
             assert torch.equal(a, b), (it, (a - b).abs().max())

@@ -88,9 +88,15 @@ extern "C" int vbx_conv1d_dgrad(const vbx_conv_desc* d, const float* dy, const f
   VBX_REQUIRE(dy && wt && dx, VBX_BAD_POINTER, "conv1d_dgrad: null tensor");
   GemmP P; fill(P, d); fill_epi(P, e);
   P.W = wt; P.X = dy; P.Y = dx;
-  if (direct_dgrad_ok(P)) return direct_dgrad(P, (cudaStream_t)stream);
-  Plan pl = plan_conv(DGRAD, P);
-  return launch_cfg<DGRAD, false>(pl, P, (cudaStream_t)stream);
+  VBX_REQUIRE(!P.gate || P.beta == 0.f, VBX_UNSUPPORTED, "conv1d_dgrad: gate stage with beta != 0");
+  const GateArgs gate(P, 8);
+  int rc;
+  if (direct_dgrad_ok(P)) rc = direct_dgrad(P, (cudaStream_t)stream);
+  else {
+    Plan pl = plan_conv(DGRAD, P);
+    rc = launch_cfg<DGRAD, false>(pl, P, (cudaStream_t)stream);
+  }
+  return gate.finish(rc, dx, (long long)d->B * d->Cin * d->Tin, stream);
 }
 
 extern "C" int vbx_conv1d_wgrad(const vbx_conv_desc* d, const float* x, const float* dy, float* dw,

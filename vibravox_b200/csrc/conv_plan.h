@@ -11,6 +11,32 @@ inline int plan_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); 
 // vbx_set_deterministic: one CTA per output tile walks a whole reduction in a fixed order (no split-K atomics)
 inline int& deterministic_flag() { static int flag = 0; return flag; }
 
+// Where the gate stage of vbx_epilogue runs, per input-gradient kernel form (bit mask; VBX_GATE_EPILOGUE, default 1|8):
+// 1 = gather-form tensor-core kernel, 2 = streaming slab kernel, 4 = persistent slab kernel, 8 = fp32 FMA / direct
+// kernels.  A form whose bit is clear runs its kernel without the gate and then vbx_fm_gate_bwd in place on the same
+// stream (same bits).  The slab kernels run one tile at a time per CTA and their epilogue is not overlapped with another
+// tile's main loop, so the two extra global loads per element are exposed latency there.  Measured on the bs=32 step
+// (ms per step; separate aten::add + L1-pair backward + LeakyReLU backward passes = 41.36): all forms in the epilogue
+// 43.31, all but the streaming slab 40.87, gather + FMA 40.59, gather only 40.57, none (in-place pass everywhere) 40.67.
+int gate_epilogue_forms();
+int launch_fm_gate(const float* y, const float* other, const float* coef, float gslope, const float* g, long long n,
+                   float* out, void* stream);
+
+struct GateArgs {
+  const float* y; const float* other; const float* coef; float slope;
+  // takes the gate stage out of P when `form` does not run it in its epilogue
+  GateArgs(GemmP& P, int form) : y(nullptr), other(P.fm_other), coef(P.fm_coef), slope(P.gate_slope) {
+    if (P.gate && !(gate_epilogue_forms() & form)) {
+      y = P.gate;
+      P.gate = nullptr; P.fm_other = nullptr; P.fm_coef = nullptr;
+    }
+  }
+  int finish(int rc, float* out, long long n, void* stream) const {
+    if (rc != 0 || !y) return rc;
+    return launch_fm_gate(y, other, coef, slope, out, n, out, stream);
+  }
+};
+
 inline int pick_tm(int M) {
   if (M > 64) return 128;
   if (M > 32) return 64;

@@ -756,12 +756,22 @@ extern "C" int vbx_fm_coef(const double* sums, int32_t npairs, const float* go, 
   fm_coef_kernel<<<cdiv(npairs, 64), 64, 0, ST>>>(sums, npairs, go, scale, coef);
   return launched("fm_coef_kernel");
 }
+namespace vbx {
+int gate_epilogue_forms() {
+  static const int forms = getenv("VBX_GATE_EPILOGUE") ? atoi(getenv("VBX_GATE_EPILOGUE")) : (1 | 8);
+  return forms;
+}
+int launch_fm_gate(const float* y, const float* other, const float* coef, float gslope, const float* g, long long n,
+                   float* out, void* stream) {
+  fm_gate_bwd_kernel<<<stream_blocks(n, 1024), 256, 0, ST>>>(y, other, coef, gslope, g, n, out);
+  return launched("fm_gate_bwd_kernel");
+}
+}  // namespace vbx
 extern "C" int vbx_fm_gate_bwd(const float* y, const float* other, const float* coef, float gate_slope, const float* g,
                                int64_t n, float* out, void* stream) {
   VBX_REQUIRE(y && out && (!other || coef), VBX_BAD_POINTER, "fm_gate_bwd: null tensor");
   VBX_REQUIRE(n > 0, VBX_BAD_SHAPE, "fm_gate_bwd: empty");
-  fm_gate_bwd_kernel<<<stream_blocks(n, 1024), 256, 0, ST>>>(y, other, coef, gate_slope, g, n, out);
-  return launched("fm_gate_bwd_kernel");
+  return launch_fm_gate(y, other, coef, gate_slope, g, n, out, stream);
 }
 extern "C" int vbx_hinge_fwd(const float* c, int64_t n, float target, float scale, double* acc, void* stream) {
   VBX_REQUIRE(c && acc, VBX_BAD_POINTER, "hinge_fwd: null tensor");

@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const TcP P) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) acc[j] += r[j];
         }
-        if (MODE == DGRAD && G.gate) gate_block16(G, o, Tlen, acc);    // (the gate stage belongs to input gradients)
+        if (G.gate) gate_block16(G, o, Tlen, acc);
         float* yp = G.Y + o;
 #pragma unroll
         for (int j = 0; j < 16; ++j) yp[(long long)j * Tlen] = acc[j];
@@ -1188,9 +1188,13 @@ extern "C" int vbx_tc_conv1d_dgrad(const vbx_conv_desc* d, const float* dy, cons
   fill_epi(P.g, e);
   P.g.X = dy; P.g.Y = dx;
   P.packed = (const unsigned char*)packed;
-  if (P.slab) return P.ps ? launch_pslab(P, (cudaStream_t)stream) : launch_slab(P, (cudaStream_t)stream);
-  if (P.merged) return launch_tc<FWD>(P, (cudaStream_t)stream);
-  return launch_tc<DGRAD>(P, (cudaStream_t)stream);
+  VBX_REQUIRE(!P.g.gate || P.g.beta == 0.f, VBX_UNSUPPORTED, "tc_conv1d_dgrad: gate stage with beta != 0");
+  const GateArgs gate(P.g, P.slab ? (P.ps ? 4 : 2) : 1);
+  int rc;
+  if (P.slab) rc = P.ps ? launch_pslab(P, (cudaStream_t)stream) : launch_slab(P, (cudaStream_t)stream);
+  else if (P.merged) rc = launch_tc<FWD>(P, (cudaStream_t)stream);
+  else rc = launch_tc<DGRAD>(P, (cudaStream_t)stream);
+  return gate.finish(rc, dx, (long long)d->B * d->Cin * d->Tin, stream);
 }
 
 #include "tc_wslab.cuh"
