@@ -22,6 +22,8 @@ DIRECT_CASES = [
     (2, 1, 16, 2500, 15, 1, 1, 7, 7, 1),      # MelGAN L0, 3 forward tiles / 5 gradient tiles
     (3, 1, 1, 2100, 101, 1, 1, 50, 0, 1),     # A-weighting FIR
     (2, 3, 12, 1100, 5, 2, 1, 2, 2, 3),       # strided: direct forward, GEMM input gradient
+    (3, 768, 1, 375, 3, 1, 1, 1, 0, 1),       # certainty conv: streaming-dot weight gradient (skinny_wgrad_kernel)
+    (2, 32, 4, 1001, 3, 1, 1, 1, 1, 1),       # generator last conv: 4 output channels, ragged quads, reflect halo
 ]
 
 
@@ -53,6 +55,19 @@ def test_conv_family_matches_torch(case):
     assert (dx.cpu().double() - (gx + r2.double())).abs().max() < 2e-5
     dw = ops.conv1d_wgrad(xc, dyc, geom)
     assert (dw.cpu().double() - gw).abs().max() / gw.abs().max() < 5e-6
+    # accumulates onto what the bucket holds; one writer per output in deterministic mode (bit-reproducible)
+    prev = ops.set_deterministic(True)
+    try:
+        base = torch.randn_like(dw)
+        d1 = ops.conv1d_wgrad(xc, dyc, geom, dw=base.clone())
+        d2 = ops.conv1d_wgrad(xc, dyc, geom, dw=base.clone())
+    finally:
+        ops.set_deterministic(prev)
+    assert torch.equal(d1, d2)
+    assert ((d1 - base).cpu().double() - gw).abs().max() / gw.abs().max() < 5e-6
+    if ops.use_tc(geom, "wgrad"):
+        dwt = ops.tc_conv1d_wgrad(xc, dyc, geom)
+        assert (dwt.cpu().double() - gw).abs().max() / gw.abs().max() < 2e-4
     dx2 = ops.conv1d_dgrad_scatter(dyc, scatter_weight(w, groups).to(DEV), geom, Tin)
     assert (dx2.cpu().double() - gx).abs().max() < 2e-5
 

@@ -59,6 +59,8 @@ bool direct_fwd_ok(const GemmP& P);
 bool direct_dgrad_ok(const GemmP& P);
 int direct_fwd(const GemmP& P, cudaStream_t st);
 int direct_dgrad(const GemmP& P, cudaStream_t st);
+bool skinny_wgrad_ok(const GemmP& P);
+int skinny_wgrad(const GemmP& P, cudaStream_t st);
 
 static int check_desc(const vbx_conv_desc* d) {
   int code = 0;
@@ -105,6 +107,7 @@ extern "C" int vbx_conv1d_wgrad(const vbx_conv_desc* d, const float* x, const fl
   VBX_REQUIRE(x && dy && dw, VBX_BAD_POINTER, "conv1d_wgrad: null tensor");
   GemmP P; fill(P, d);
   P.X = x; P.DY = dy; P.Y = dw;
+  if (skinny_wgrad_ok(P)) return skinny_wgrad(P, (cudaStream_t)stream);
   Plan pl = plan_conv(WGRAD, P);
   return launch_cfg<WGRAD, true>(pl, P, (cudaStream_t)stream);
 }

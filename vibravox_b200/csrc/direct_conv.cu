@@ -147,6 +147,118 @@ __global__ void __launch_bounds__(kDirThreads) direct_dgrad_kernel(const GemmP P
   }
 }
 
+// Weight gradient of a conv with a handful of outputs per input row - the certainty convs (C -> 1, k3), the generator's
+// last conv (32 -> 4, k3), the one-input-channel-per-group first stages (4 -> 24 g4 k3, 1 -> 16 k15) - as what it is: a
+// streaming dot product.  dW[co, ci_g, k] += sum_{b,t} dy[b, co, t] * x[b, ci, map(t + k*d - pad)]  (stride 1).
+// One block per (block of NCO output channels, input channel of the group) and batch slice: every thread walks quads of
+// 4 consecutive t, keeps NCO x K partial sums in registers, and the block reduces them in a fixed order; one writer per
+// output when the batch is not sliced (deterministic mode), fp32 atomics across slices otherwise.  x and dy are read
+// once from HBM (the K shifted reads of x hit L1); the implicit-GEMM kernels spent a 128-row tile on 1-24 useful rows
+// here (7-20x their HBM roofline).
+template <int NCO, int K, bool WINDOW>
+__global__ void __launch_bounds__(kDirThreads) skinny_wgrad_kernel(const GemmP P, int bper) {
+  constexpr int R = 4;
+  __shared__ float red[kDirThreads / 32][NCO * K];
+  const int cob = blockIdx.x / P.Cin_g, cig = blockIdx.x % P.Cin_g;
+  const int co0 = cob * NCO;
+  const int ci = (co0 / P.Cout_g) * P.Cin_g + cig;
+  const int b0 = blockIdx.y * bper, b1 = min(b0 + bper, P.B);
+  const int d = P.dil, pad = P.pad, Tin = P.Tin, Tout = P.Tout;
+  float acc[NCO][K];
+#pragma unroll
+  for (int i = 0; i < NCO; ++i)
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[i][k] = 0.f;
+  const int nq = (Tout + R - 1) / R;
+  {
+    // (batch item, quad) pairs as ONE index space: short rows (T = 187 ... 375 on the certainty convs) would otherwise
+    // leave most of the block idle in every per-item pass
+    for (int idx = threadIdx.x; idx < (b1 - b0) * nq; idx += kDirThreads) {
+      const int b = b0 + idx / nq, q = idx % nq;
+      const float* __restrict__ xr = P.X + ((long long)b * P.Cin + ci) * Tin;
+      const float* __restrict__ dyr = P.DY + ((long long)b * P.Cout + co0) * Tout;
+      const int t0 = q * R;
+      float dyv[NCO][R];
+#pragma unroll
+      for (int i = 0; i < NCO; ++i)
+#pragma unroll
+        for (int r = 0; r < R; ++r) dyv[i][r] = t0 + r < Tout ? dyr[(long long)i * Tout + t0 + r] : 0.f;
+      const int p0 = t0 - pad;
+      const bool interior = p0 >= 0 && p0 + (R - 1) + (K - 1) * d < Tin;
+      if (WINDOW) {                                       // d == 1: one sliding window of R + K - 1 values
+        float w[R + K - 1];
+#pragma unroll
+        for (int j = 0; j < R + K - 1; ++j) {
+          if (interior) w[j] = xr[p0 + j];
+          else { const int p = map_pos(p0 + j, Tin, P.refl); w[j] = p >= 0 ? xr[p] : 0.f; }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int i = 0; i < NCO; ++i) acc[i][k] = fmaf(dyv[i][r], w[k + r], acc[i][k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            float xv;
+            if (interior) xv = xr[p0 + r + k * d];
+            else { const int p = map_pos(p0 + r + k * d, Tin, P.refl); xv = p >= 0 ? xr[p] : 0.f; }
+#pragma unroll
+            for (int i = 0; i < NCO; ++i) acc[i][k] = fmaf(dyv[i][r], xv, acc[i][k]);
+          }
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NCO; ++i)
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      float v = acc[i][k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[warp][i * K + k] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < NCO * K) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < kDirThreads / 32; ++w) v += red[w][threadIdx.x];
+    const int i = threadIdx.x / K, k = threadIdx.x % K;
+    float* out = P.Y + ((long long)(co0 + i) * P.Cin_g + cig) * K + k;
+    if (gridDim.y == 1) *out += v;
+    else atomicAdd(out, v);
+  }
+}
+
+bool skinny_wgrad_ok(const GemmP& P) {
+  static const bool off = getenv("VBX_SKINNY_WGRAD") && atoi(getenv("VBX_SKINNY_WGRAD")) == 0;
+  if (off || P.stride != 1 || P.refl > P.pad) return false;
+  if (P.Cin_g == 1) return P.K == 3 || (P.K == 15 && P.dil == 1);
+  return P.groups == 1 && P.K == 3 && (P.Cout == 1 || P.Cout == 4);
+}
+
+int skinny_wgrad(const GemmP& P, cudaStream_t st) {
+  const int nco = P.Cin_g == 1 ? 1 : P.Cout;
+  const long long gx = (long long)(P.Cout / nco) * P.Cin_g;
+  if (gx > 0x7fffffffLL) return fail(VBX_UNSUPPORTED, "skinny_wgrad: grid too large");
+  long long split = (148 * 8 + gx - 1) / gx;              // ~8 blocks per SM in total
+  if (split > P.B) split = P.B;
+  if (split > 65535) split = 65535;
+  if (split < 1 || deterministic_flag()) split = 1;
+  const int bper = (int)((P.B + split - 1) / split);
+  dim3 grid((unsigned)gx, (unsigned)((P.B + bper - 1) / bper));
+  if (P.K == 15) skinny_wgrad_kernel<1, 15, true><<<grid, kDirThreads, 0, st>>>(P, bper);
+  else if (nco == 1 && P.dil == 1) skinny_wgrad_kernel<1, 3, true><<<grid, kDirThreads, 0, st>>>(P, bper);
+  else if (nco == 1) skinny_wgrad_kernel<1, 3, false><<<grid, kDirThreads, 0, st>>>(P, bper);
+  else if (P.dil == 1) skinny_wgrad_kernel<4, 3, true><<<grid, kDirThreads, 0, st>>>(P, bper);
+  else skinny_wgrad_kernel<4, 3, false><<<grid, kDirThreads, 0, st>>>(P, bper);
+  return launched("skinny_wgrad_kernel");
+}
+
 bool direct_fwd_ok(const GemmP& P) {
   return P.Cin_g == 1 && P.Cout_g <= 16 && P.K <= 128 && P.stride <= 2 &&
          (long long)P.B * P.groups * ((P.Tout + 1023) / 1024) < (1ll << 31);

@@ -831,6 +831,10 @@ static int pack_tc(const TcP& P, const float* w, void* packed, cudaStream_t st) 
 }  // namespace tc
 }  // namespace vbx
 
+namespace vbx {
+bool skinny_wgrad_ok(const GemmP& P);
+int skinny_wgrad(const GemmP& P, cudaStream_t st);
+}
 using namespace vbx;
 using namespace vbx::tc;
 
@@ -1205,6 +1209,14 @@ extern "C" int vbx_tc_conv1d_wgrad(const vbx_conv_desc* d, const float* x, const
   const char* msg = check_desc_msg(d, &code);
   if (msg) return fail(code, msg);
   VBX_REQUIRE(x && dy && dw, VBX_BAD_POINTER, "tc_conv1d_wgrad: null tensor");
+  {
+    GemmP S;                       // a handful of outputs per input row: streaming dot products (direct_conv.cu), exact fp32
+    fill(S, d);
+    if (skinny_wgrad_ok(S)) {
+      S.X = x; S.DY = dy; S.Y = dw;
+      return skinny_wgrad(S, (cudaStream_t)stream);
+    }
+  }
   {
     TcWS W;
     if (plan_wslab(W, d)) {
