@@ -22,7 +22,9 @@ DIRECT_CASES = [
     (2, 1, 16, 2500, 15, 1, 1, 7, 7, 1),      # MelGAN L0, 3 forward tiles / 5 gradient tiles
     (3, 1, 1, 2100, 101, 1, 1, 50, 0, 1),     # A-weighting FIR
     (2, 3, 12, 1100, 5, 2, 1, 2, 2, 3),       # strided: direct forward, GEMM input gradient
-    (3, 768, 1, 375, 3, 1, 1, 1, 0, 1),       # certainty conv: streaming-dot weight gradient (skinny_wgrad_kernel)
+    (2, 1, 16, 2503, 15, 1, 1, 7, 7, 1),      # quad kernels: ragged last quad (scalar stores; old input-gradient kernel)
+    (2, 1, 16, 1000, 15, 1, 1, 7, 0, 1),      # quad kernels with a zero halo
+    (3, 768, 1, 375, 3, 1, 1, 1, 0, 1),       # certainty conv: skinny_fwd_kernel (8 channel slices) / skinny_wgrad_kernel
     (2, 32, 4, 1001, 3, 1, 1, 1, 1, 1),       # generator last conv: 4 output channels, ragged quads, reflect halo
 ]
 

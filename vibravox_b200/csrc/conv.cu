@@ -61,6 +61,8 @@ int direct_fwd(const GemmP& P, cudaStream_t st);
 int direct_dgrad(const GemmP& P, cudaStream_t st);
 bool skinny_wgrad_ok(const GemmP& P);
 int skinny_wgrad(const GemmP& P, cudaStream_t st);
+bool skinny_fwd_ok(const GemmP& P);
+int skinny_fwd(const GemmP& P, cudaStream_t st);
 
 static int check_desc(const vbx_conv_desc* d) {
   int code = 0;
@@ -79,6 +81,7 @@ extern "C" int vbx_conv1d_fwd(const vbx_conv_desc* d, const float* x, const floa
   GemmP P; fill(P, d); fill_epi(P, e);
   P.W = w; P.X = x; P.Y = y;
   if (direct_fwd_ok(P)) return direct_fwd(P, (cudaStream_t)stream);
+  if (skinny_fwd_ok(P)) return skinny_fwd(P, (cudaStream_t)stream);
   Plan pl = plan_conv(FWD, P);
   if (pl.bk) return launch_cfg<FWD, true>(pl, P, (cudaStream_t)stream);
   return launch_cfg<FWD, false>(pl, P, (cudaStream_t)stream);

@@ -259,6 +259,236 @@ int skinny_wgrad(const GemmP& P, cudaStream_t st) {
   return launched("skinny_wgrad_kernel");
 }
 
+// ---- quad kernels: 4 consecutive positions per thread, a register window over the taps (stride 1, dilation 1) --------
+// MelGAN stage 0 (1 -> 16, k 15, reflect 7): the generic direct kernels above index their shared-memory window and
+// weights with run-time K / Cg and executed 7.8 instructions per FMA (ncu: 89.7 M warp instructions for 11.5 M warp
+// FMAs, 168 us for a 98 MB output).  Here K and the channel count are compile-time, the 18-value input window of a quad is
+// loaded once for all 16 output channels, the weights come as 16-byte shared-memory broadcasts, and a quad's outputs are
+// stored as one float4 per channel.
+template <int CG, int K>
+__global__ void __launch_bounds__(kDirThreads) direct_fwd4_kernel(const GemmP P, long long nquads, int nq) {
+  constexpr int R = 4, KP = (K + 3) / 4 * 4;
+  __shared__ __align__(16) float ws[CG * KP];
+  const int Cg = P.Cout_g;
+  const long long idx = (long long)blockIdx.x * kDirThreads + threadIdx.x;
+  // (a block may straddle groups: the weights are staged per thread-group below only when groups == 1)
+  for (int i = threadIdx.x; i < CG * KP; i += kDirThreads) {
+    const int j = i / KP, k = i % KP;
+    ws[i] = (j < Cg && k < K) ? P.W[j * K + k] : 0.f;
+  }
+  __syncthreads();
+  if (idx >= nquads) return;
+  const int b = (int)(idx / nq), q = (int)(idx % nq);
+  const int t0 = q * R;
+  const float* __restrict__ xr = P.X + (long long)b * P.Tin;
+  float w[R + K - 1];
+  const int p0 = t0 - P.pad;
+  if (p0 >= 0 && p0 + R + K - 2 < P.Tin) {
+#pragma unroll
+    for (int j = 0; j < R + K - 1; ++j) w[j] = xr[p0 + j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < R + K - 1; ++j) {
+      const int p = map_pos(p0 + j, P.Tin, P.refl);
+      w[j] = p >= 0 ? xr[p] : 0.f;
+    }
+  }
+  const bool vec = (P.Tout & 3) == 0 && t0 + R <= P.Tout && !P.mask && !P.res && P.beta == 0.f &&
+                   (reinterpret_cast<uintptr_t>(P.Y) & 15) == 0;
+#pragma unroll
+  for (int j = 0; j < CG; ++j) {
+    if (j < Cg) {
+      float wt[KP];
+#pragma unroll
+      for (int k4 = 0; k4 < KP; k4 += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(ws + j * KP + k4);
+        wt[k4] = v.x; wt[k4 + 1] = v.y; wt[k4 + 2] = v.z; wt[k4 + 3] = v.w;
+      }
+      float acc[R] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = fmaf(wt[k], w[k + r], acc[r]);
+      const long long o = ((long long)b * P.Cout + j) * P.Tout + t0;
+      if (vec) {
+        float4 v;
+        v.x = dir_finish(P, acc[0], j, o); v.y = dir_finish(P, acc[1], j, o + 1);
+        v.z = dir_finish(P, acc[2], j, o + 2); v.w = dir_finish(P, acc[3], j, o + 3);
+        *reinterpret_cast<float4*>(P.Y + o) = v;
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (t0 + r < P.Tout) P.Y[o + r] = dir_finish(P, acc[r], j, o + r);
+      }
+    }
+  }
+}
+
+// Input gradient of the same layer:  dx[u] = sum_j sum_k w[j, k] * dy[j, u + pad - k]  (+ the mirror terms of the reflect
+// halo on the <= 2*refl edge positions, as in direct_dgrad_kernel).  Per channel the 18-value window of a quad is read as
+// six ALIGNED float4s starting at (u0 + pad - (K-1)) rounded down to a multiple of 4; OFF is that rounding, a
+// compile-time constant per geometry, so the window stays in registers.
+template <int CG, int K, int OFF>
+__global__ void __launch_bounds__(kDirThreads) direct_dgrad4_kernel(const GemmP P, long long nquads, int nq) {
+  constexpr int R = 4, KP = (K + 3) / 4 * 4, NW = (OFF + R + K - 1 + 3) / 4 * 4;
+  __shared__ __align__(16) float ws[CG * KP];
+  const int Cg = P.Cout_g;
+  for (int i = threadIdx.x; i < CG * KP; i += kDirThreads) {
+    const int j = i / KP, k = i % KP;
+    ws[i] = (j < Cg && k < K) ? P.W[j * K + (K - 1 - k)] : 0.f;      // flipped: window index = k' + r
+  }
+  __syncthreads();
+  const long long idx = (long long)blockIdx.x * kDirThreads + threadIdx.x;
+  const bool live = idx < nquads;
+  const int b = live ? (int)(idx / nq) : 0, q = live ? (int)(idx % nq) : 0;
+  const int u0 = q * R;
+  const int a0 = u0 + P.pad - (K - 1) - OFF;                       // multiple of 4 by construction
+  const float* __restrict__ dyb = P.X + (long long)b * P.Cout * P.Tout;
+  const bool interior = a0 >= 0 && a0 + NW <= P.Tout;
+  float acc[R] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+  for (int j = 0; j < CG; ++j) {
+    if (live && j < Cg) {
+      const float* __restrict__ row = dyb + (long long)j * P.Tout;
+      float w[NW];
+      if (interior) {
+#pragma unroll
+        for (int i = 0; i < NW; i += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(row + a0 + i);
+          w[i] = v.x; w[i + 1] = v.y; w[i + 2] = v.z; w[i + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+          const int t = a0 + i;
+          w[i] = (t >= 0 && t < P.Tout) ? row[t] : 0.f;
+        }
+      }
+      float wt[KP];
+#pragma unroll
+      for (int k4 = 0; k4 < KP; k4 += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(ws + j * KP + k4);
+        wt[k4] = v.x; wt[k4 + 1] = v.y; wt[k4 + 2] = v.z; wt[k4 + 3] = v.w;
+      }
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = fmaf(wt[k], w[OFF + k + r], acc[r]);
+    }
+  }
+  if (P.refl > 0) {
+    // mirror terms of the <= 2*refl edge positions per item: the WARP sums the Cg*K products of one such position
+    // together (a single thread walking them is a 240-long chain of dependent cache misses that set the kernel's duration)
+    const int lane = threadIdx.x & 31;
+    const bool edge = live && (u0 <= P.refl || u0 + R - 1 >= P.Tin - 1 - P.refl);
+    unsigned need = __ballot_sync(0xffffffffu, edge);
+    while (need) {
+      const int src = __ffs(need) - 1;
+      need &= need - 1;
+      const int sb = __shfl_sync(0xffffffffu, b, src), su0 = __shfl_sync(0xffffffffu, u0, src);
+      const float* __restrict__ sdy = P.X + (long long)sb * P.Cout * P.Tout;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int u = su0 + r;
+        if (u >= P.Tin) continue;
+        for (int side = 0; side < 2; ++side) {
+          const bool hit = side == 0 ? (u >= 1 && u <= P.refl) : (u <= P.Tin - 2 && u >= P.Tin - 1 - P.refl);
+          if (!hit) continue;                                       // (warp-uniform)
+          const int p = side == 0 ? -u : 2 * (P.Tin - 1) - u;
+          float v = 0.f;
+          for (int i = lane; i < Cg * K; i += 32) {
+            const int j = i / K, k = i % K;
+            const int t = p + P.pad - k * P.dil;
+            if (t >= 0 && t < P.Tout) v = fmaf(P.W[j * K + k], sdy[(long long)j * P.Tout + t], v);
+          }
+#pragma unroll
+          for (int o2 = 16; o2 > 0; o2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
+          if (lane == src) acc[r] += v;
+        }
+      }
+    }
+  }
+  if (!live) return;
+  const long long o = (long long)b * P.Tin + u0;                    // Cin == groups == 1
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    if (u0 + r < P.Tin) P.Y[o + r] = dir_finish(P, acc[r], 0, o + r);
+}
+
+static bool quad_geometry(const GemmP& P) {
+  static const bool off = getenv("VBX_DIRECT_QUAD") && atoi(getenv("VBX_DIRECT_QUAD")) == 0;
+  return !off && P.groups == 1 && P.Cin == 1 && P.Cout == 16 && P.K == 15 && P.stride == 1 && P.dil == 1 &&
+         P.refl <= P.pad && (long long)P.B * ((P.Tout + 3) / 4) < (1ll << 40);
+}
+
+// ---- a handful of OUTPUT channels over many input channels (certainty convs C -> 1 k3, generator last conv 32 -> 4 k3):
+// y[b, co, t] = sum_ci sum_k w[co, ci, k] * x[b, ci, map(t + k*d - pad)], one thread per position and input-channel slice
+// (coalesced loads: consecutive lanes = consecutive t), the slices of a block summed through shared memory in a fixed
+// order.  The implicit-GEMM kernels gave these layers a 128-row x 16-column tile with ONE useful column (10-19x their HBM
+// roofline).
+template <int NCO>
+__global__ void __launch_bounds__(kDirThreads) skinny_fwd_kernel(const GemmP P, int nslice, int tiles) {
+  __shared__ float red[kDirThreads * NCO];
+  const int ppb = kDirThreads / nslice;
+  const int pos = threadIdx.x % ppb, slice = threadIdx.x / ppb;
+  const int b = blockIdx.x / tiles, t = (blockIdx.x % tiles) * ppb + pos;
+  const int cper = (P.Cin + nslice - 1) / nslice;
+  const int c0 = slice * cper, c1 = min(c0 + cper, P.Cin);
+  float acc[NCO];
+#pragma unroll
+  for (int i = 0; i < NCO; ++i) acc[i] = 0.f;
+  if (t < P.Tout) {
+    int p[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) p[k] = map_pos(t + k * P.dil - P.pad, P.Tin, P.refl);
+    const float* __restrict__ xb = P.X + (long long)b * P.Cin * P.Tin;
+#pragma unroll 4
+    for (int c = c0; c < c1; ++c) {
+      const float* __restrict__ xr = xb + (long long)c * P.Tin;
+      float xv[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) xv[k] = p[k] >= 0 ? xr[p[k]] : 0.f;
+#pragma unroll
+      for (int i = 0; i < NCO; ++i) {
+        const float* __restrict__ wr = P.W + ((long long)i * P.Cin + c) * 3;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc[i] = fmaf(__ldg(wr + k), xv[k], acc[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NCO; ++i) red[(slice * NCO + i) * ppb + pos] = acc[i];
+  __syncthreads();
+  if (slice == 0 && t < P.Tout) {
+#pragma unroll
+    for (int i = 0; i < NCO; ++i) {
+      float v = 0.f;
+      for (int s2 = 0; s2 < nslice; ++s2) v += red[(s2 * NCO + i) * ppb + pos];
+      const long long o = ((long long)b * P.Cout + i) * P.Tout + t;
+      P.Y[o] = dir_finish(P, v, i, o);
+    }
+  }
+}
+
+bool skinny_fwd_ok(const GemmP& P) {
+  static const bool off = getenv("VBX_SKINNY_FWD") && atoi(getenv("VBX_SKINNY_FWD")) == 0;
+  return !off && P.groups == 1 && P.K == 3 && P.stride == 1 && (P.Cout == 1 || P.Cout == 4) && P.Cin >= 8 &&
+         P.refl <= P.pad;
+}
+
+int skinny_fwd(const GemmP& P, cudaStream_t st) {
+  // slices of the input channels per block: enough blocks to fill the machine on the short certainty maps
+  int nslice = 1;
+  while (nslice < 8 && (long long)P.B * P.Tout * nslice < 148LL * 8 * kDirThreads && P.Cin / (2 * nslice) >= 8) nslice *= 2;
+  const int ppb = kDirThreads / nslice;
+  const int tiles = (P.Tout + ppb - 1) / ppb;
+  const long long grid = (long long)P.B * tiles;
+  if (grid > 0x7fffffffLL) return fail(VBX_UNSUPPORTED, "skinny_fwd: grid too large");
+  if (P.Cout == 1) skinny_fwd_kernel<1><<<(unsigned)grid, kDirThreads, 0, st>>>(P, nslice, tiles);
+  else skinny_fwd_kernel<4><<<(unsigned)grid, kDirThreads, 0, st>>>(P, nslice, tiles);
+  return launched("skinny_fwd_kernel");
+}
+
 bool direct_fwd_ok(const GemmP& P) {
   return P.Cin_g == 1 && P.Cout_g <= 16 && P.K <= 128 && P.stride <= 2 &&
          (long long)P.B * P.groups * ((P.Tout + 1023) / 1024) < (1ll << 31);
@@ -269,6 +499,12 @@ bool direct_dgrad_ok(const GemmP& P) {
 }
 
 int direct_fwd(const GemmP& P, cudaStream_t st) {
+  if (quad_geometry(P)) {
+    const int nq = (P.Tout + 3) / 4;
+    const long long nquads = (long long)P.B * nq;
+    direct_fwd4_kernel<16, 15><<<(unsigned)((nquads + kDirThreads - 1) / kDirThreads), kDirThreads, 0, st>>>(P, nquads, nq);
+    return launched("direct_fwd4_kernel");
+  }
   const int PT = 4, TT = PT * kDirThreads;
   const int tiles = (P.Tout + TT - 1) / TT;
   const int win = (TT - 1) * P.stride + (P.K - 1) * P.dil + 1;
@@ -282,6 +518,18 @@ int direct_fwd(const GemmP& P, cudaStream_t st) {
 }
 
 int direct_dgrad(const GemmP& P, cudaStream_t st) {
+  if (quad_geometry(P) && (P.Tout & 3) == 0 && (reinterpret_cast<uintptr_t>(P.X) & 15) == 0) {
+    const int nq = (P.Tin + 3) / 4;
+    const long long nquads = (long long)P.B * nq;
+    const unsigned grid = (unsigned)((nquads + kDirThreads - 1) / kDirThreads);
+    switch (((P.pad - (P.K - 1)) % 4 + 4) % 4) {                    // distance of a window start above a multiple of 4
+      case 0: direct_dgrad4_kernel<16, 15, 0><<<grid, kDirThreads, 0, st>>>(P, nquads, nq); break;
+      case 1: direct_dgrad4_kernel<16, 15, 1><<<grid, kDirThreads, 0, st>>>(P, nquads, nq); break;
+      case 2: direct_dgrad4_kernel<16, 15, 2><<<grid, kDirThreads, 0, st>>>(P, nquads, nq); break;
+      default: direct_dgrad4_kernel<16, 15, 3><<<grid, kDirThreads, 0, st>>>(P, nquads, nq); break;
+    }
+    return launched("direct_dgrad4_kernel");
+  }
   const int PT = 2, TT = PT * kDirThreads;
   const int tiles = (P.Tin + TT - 1) / TT;
   const int win = TT + (P.K - 1) * P.dil;

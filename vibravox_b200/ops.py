@@ -565,8 +565,10 @@ def use_tc(g: ConvGeom, kind: str) -> bool:
     cin_g, cout_g = g.Cin // g.groups, g.Cout // g.groups
     if kind == "fwd" and cin_g == 1 and cout_g <= 16 and g.K <= 128 and g.stride <= 2:
         return False                                  # one input channel per group: direct kernel (direct_conv.cu)
+    if kind == "fwd" and g.groups == 1 and g.Cout in (1, 4) and g.K == 3 and g.stride == 1 and g.Cin >= 8:
+        return False                                  # certainty convs / last conv: streaming kernel (skinny_fwd_kernel)
     if kind == "fwd":
-        return cout_g >= 8 or cin_g * g.K >= 512      # incl. the 1-channel certainty convs (K*Cin = 2-3k)
+        return cout_g >= 8 or cin_g * g.K >= 512
     if kind == "dgrad":
         return cin_g >= 4
     if cin_g * g.K <= WGRAD_FMA_MAX_CK:
