@@ -44,5 +44,28 @@ print("time (ms) with k kernels in flight:", {k: round(v / 1e3, 2) for k, v in s
 print("longest 40 kernels: start(ms) dur(us) stream name")
 for e in sorted(ev, key=lambda e: -e["dur"])[:40]:
     print(f"  {(e['ts'] - t0) / 1e3:7.2f} {e['dur']:8.1f} {e['args'].get('stream')} {e['name'][:70]} grid={e['args'].get('grid')}")
+# time each kernel spends as the ONLY kernel in flight, grouped by (name, grid): the exposed part of the critical path
+evs = sorted(ev, key=lambda e: e["ts"])
+bounds = sorted(set([e["ts"] for e in evs] + [e["ts"] + e["dur"] for e in evs]))
+alone = collections.Counter()
+total = collections.Counter()
+count = collections.Counter()
+import bisect
+starts = [e["ts"] for e in evs]
+active = []
+j = 0
+for a, b in zip(bounds[:-1], bounds[1:]):
+    while j < len(evs) and evs[j]["ts"] <= a:
+        active.append(evs[j]); j += 1
+    active = [e for e in active if e["ts"] + e["dur"] > a]
+    if len(active) == 1:
+        e = active[0]
+        alone[(e["name"][:60], str(e["args"].get("grid")))] += b - a
+for e in evs:
+    k = (e["name"][:60], str(e["args"].get("grid")))
+    total[k] += e["dur"]; count[k] += 1
+print("exposed (alone in flight) time by kernel and grid: alone_ms total_ms n name grid")
+for k, v in sorted(alone.items(), key=lambda kv: -kv[1])[:45]:
+    print(f"  {v / 1e3:7.3f} {total[k] / 1e3:7.3f} {count[k]:4d} {k[0]} {k[1]}")
 # gaps on the whole device (no kernel running)
 print("idle gaps > 20 us:", [(round((a - t0) / 1e3, 2), round(b - a)) for a, b in []])

@@ -665,6 +665,19 @@ static void plan_slab(TcP& P, const vbx_conv_desc* d) {
     P.sl_SB = total_b < 2 ? total_b : 2;
     if (slab_smem_bytes(P) > 200 * 1024) return;
   }
+  {
+    // A third CTA per SM beats a deeper weight ring where a tile is a latency chain (stage -> K small MMAs -> drain) and
+    // the weight tiles are small: ncu on MelGAN stage 1 (N = 64) showed 2 CTAs per SM, 30 % of the warp slots, long-
+    // scoreboard stalls, tensor pipe 24 %.  Measured with a 2-deep ring and 3 CTAs: MelGAN stages 1-2 forward 205 -> 155 us,
+    // input gradients 244 -> 193 us, PQMF-discriminator stages and C = 128 generator convs -15..-20 %; NOT for N = 256
+    // tiles (MelGAN stages 3-4 input gradients 342 -> 396 us: those are bound by the weight stream).
+    static const int sb3 = getenv("VBX_TC_SLAB_SB3") ? atoi(getenv("VBX_TC_SLAB_SB3")) : 1;
+    if (sb3 > 0 && P.NT <= 128 && P.sl_SB > 2 && slab_smem_bytes(P) + 1024 > (227 * 1024) / 3) {
+      TcP Q = P;
+      Q.sl_SB = 2;
+      if (slab_smem_bytes(Q) + 1024 <= (227 * 1024) / 3) P.sl_SB = 2;
+    }
+  }
   P.slab = 1;
   plan_pslab(P);
   if (!P.ps && !P.merged) {
@@ -681,6 +694,16 @@ static void plan_slab(TcP& P, const vbx_conv_desc* d) {
       Q.sl_rt = 2;
       if (slab_smem_bytes(Q) > 200 * 1024) { Q.sl_SB = total_b < 2 ? total_b : 2; }
       if (slab_smem_bytes(Q) <= 200 * 1024) { P.sl_rt = 2; P.sl_SB = Q.sl_SB; }
+    }
+    // Narrow column tiles with many taps (MelGAN stages 1-2: N = 64, k 41): every 128-row tile pulls K x 4 KB of weight
+    // tiles through the bulk-copy ring for 123 small MMAs; two row tiles per CTA halve that stream and the per-tile
+    // fixed costs.
+    static const int n64 = getenv("VBX_TC_SLAB_RT2_N64") ? atoi(getenv("VBX_TC_SLAB_RT2_N64")) : 0;
+    if (n64 > 0 && P.sl_rt == 1 && P.NT <= 64 && G.K >= 32 && row_tiles >= 4 * 148 &&
+        slab_npos(G, 2) <= kSlabMaxU * kProducers) {
+      TcP Q = P;
+      Q.sl_rt = 2;
+      if (slab_smem_bytes(Q) <= 200 * 1024) P.sl_rt = 2;
     }
   }
 }
