@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define VBX_ABI_VERSION 4
+#define VBX_ABI_VERSION 5
 #if defined(__GNUC__)
 #define VBX_API __attribute__((visibility("default")))
 #else
@@ -198,6 +198,15 @@ VBX_API int vbx_fm_finalize(const double* sums, int32_t npairs, float scale, flo
  * (either may be NULL); go is a device scalar. */
 VBX_API int vbx_l1_pair_bwd(const float* a, const float* b, int64_t n, const double* sums, const float* go,
                     float scale, float* da, float* db, void* stream);
+/* ---- ResidualUnit backward through the composed conv ----
+ * z = w2 * (w1 (*) x) is ONE k-tap conv with wf[co][ci][k] = sum_m w2[co][m] w1[m][ci][k] (vbx_unit_combine; w1 is
+ * (C, C, K), w2 is (C, C)), so the unit's backward (eben_generator.py:314-316 under autograd) needs a single input
+ * gradient and a single weight gradient - dx = dgrad(dz, wf) + g and dwf = wgrad(x, dz) - from which
+ * vbx_unit_split_grads recovers  dw1 = w2^T dwf  and  dw2[co][m] = <dwf[co], w1[m]>  (either may be NULL; beta scales
+ * what the outputs hold).  The intermediate activation h of the forward pass is not needed by the backward pass. */
+VBX_API int vbx_unit_combine(const float* w1, const float* w2, int32_t C, int32_t K, float* wf, void* stream);
+VBX_API int vbx_unit_split_grads(const float* dwf, const float* w1, const float* w2, int32_t C, int32_t K, float* dw1,
+                         float* dw2, float beta, void* stream);
 /* coef[2i] = go*scale/S_a_i, coef[2i+1] = go*scale*S_ab_i/S_a_i^2 for npairs layers (sums as vbx_l1_pair_sums left
  * them): the two scalars of the line above, for the conv epilogue's fm_coef and for vbx_fm_gate_bwd. */
 VBX_API int vbx_fm_coef(const double* sums, int32_t npairs, const float* go, float scale, float* coef, void* stream);

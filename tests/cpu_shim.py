@@ -68,6 +68,17 @@ def fm_gate_bwd(y, other, coef, gate_slope, g):
     return v * torch.where(y > 0, 1.0, gate_slope)
 
 
+def unit_combine(w1, w2):
+    return torch.einsum("om,mik->oik", w2.reshape(w2.shape[0], w2.shape[1]), w1).contiguous()
+
+
+def unit_split_grads(dwf, w1, w2, want1, want2):
+    w2m = w2.reshape(w2.shape[0], w2.shape[1])
+    dw1 = torch.einsum("om,oik->mik", w2m, dwf).contiguous() if want1 else None
+    dw2 = torch.einsum("oik,mik->om", dwf, w1).reshape(w2.shape).contiguous() if want2 else None
+    return dw1, dw2
+
+
 def record_event():
     return None
 

@@ -574,6 +574,48 @@ def test_fused_residual_unit_through_autograd_matches_the_unfused_module():
         assert (y - res[True][0]).abs().max() == 0
 
 
+@pytest.mark.parametrize("C,T,d", [(32, 700, 3), (64, 516, 9), (128, 300, 1)])
+def test_residual_unit_composed_backward_matches_fp64_and_the_layerwise_backward(C, T, d):
+    """Backward of the unit through the composed conv (wf = w2 . w1: one input gradient, one weight gradient, dw1 / dw2 from
+    C x C x 3C products) against torch fp64 autograd of the reference formula (eben_generator.py:314-316) and against the
+    layer-by-layer backward; the small kernels (vbx_unit_combine / vbx_unit_split_grads) against einsum."""
+    from vibravox_b200 import functional, ops
+    from vibravox_b200.functional import ResidualUnitFn
+    torch.manual_seed(C + d)
+    B = 3
+    x = torch.randn(B, C, T, device=DEV, requires_grad=True)
+    w1 = (torch.randn(C, C, 3, device=DEV) / (3 * C) ** 0.5).requires_grad_(True)
+    w2 = (torch.randn(C, C, 1, device=DEV) / C ** 0.5).requires_grad_(True)
+    g1, g2 = ops.ConvGeom(C, C, 3, 1, d, d, d, 1), ops.ConvGeom(C, C, 1, 1, 1, 0, 0, 1)
+    go = torch.randn(B, C, T, device=DEV)
+    wf = ops.unit_combine(w1.detach(), w2.detach())
+    want_wf = torch.einsum("om,mik->oik", w2.detach()[:, :, 0].double(), w1.detach().double())
+    assert (wf.double() - want_wf).abs().max() < 1e-6
+    dwf = torch.randn(C, C, 3, device=DEV)
+    dw1, dw2 = ops.unit_split_grads(dwf, w1.detach(), w2.detach(), True, True)
+    assert (dw1.double() - torch.einsum("om,oik->mik", w2.detach()[:, :, 0].double(), dwf.double())).abs().max() < 2e-5
+    assert (dw2[:, :, 0].double() - torch.einsum("oik,mik->om", dwf.double(), w1.detach().double())).abs().max() < 2e-5
+    x64, w164, w264 = (t.detach().double().requires_grad_(True) for t in (x, w1, w2))
+    h64 = F.conv1d(F.pad(x64, (d, d), mode="reflect"), w164, None, 1, 0, d)
+    y64 = x64 + F.leaky_relu(F.conv1d(h64, w264), 0.01)
+    want = torch.autograd.grad(y64, (x64, w164, w264), go.double())
+    res = {}
+    for composed in (True, False):
+        old, functional.UNIT_COMPOSED = functional.UNIT_COMPOSED, composed
+        try:
+            y = ResidualUnitFn.apply(x, w1, ops.transpose_weight(w1.detach(), 1), w2, ops.transpose_weight(w2.detach(), 1),
+                                     g1, g2, 0.01)
+            res[composed] = torch.autograd.grad(y, (x, w1, w2), go)
+        finally:
+            functional.UNIT_COMPOSED = old
+        assert (y.double() - y64).abs().max() < 2e-4 * float(y64.abs().max())
+    for a, b, w in zip(res[True], res[False], want):
+        scale = float(w.abs().max())
+        assert (a.double() - w).abs().max() < 3e-4 * scale, (C, (a.double() - w).abs().max() / scale)
+        assert (b.double() - w).abs().max() < 3e-4 * scale
+        assert (a.double() - w).norm() / w.norm() < 1e-4
+
+
 WG_CASES = [  # B, C, T, dilation, K
     (3, 32, 1000, 1, 3), (3, 32, 1000, 3, 3), (3, 32, 1000, 9, 3), (2, 64, 516, 9, 3), (2, 64, 1280, 3, 3),
     (3, 32, 1000, 1, 1), (2, 64, 516, 1, 1), (1, 32, 40, 9, 3), (7, 32, 388, 3, 3), (32, 32, 11968, 9, 3),

@@ -378,6 +378,39 @@ __global__ void l1_pair_bwd_kernel(const float* __restrict__ a, const float* __r
     if (db) db[i] = -c1 * sd;
   }
 }
+// ResidualUnit backward through the COMPOSED conv (include/vbx.h: vbx_unit_combine / vbx_unit_split_grads).
+// wf[co][ci][k] = sum_m w2[co][m] * w1[m][ci][k]
+__global__ void unit_combine_kernel(const float* __restrict__ w1, const float* __restrict__ w2, int C, int K,
+                                    float* __restrict__ wf) {
+  const int n = C * C * K;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int co = i / (C * K), r = i % (C * K);
+    float v = 0.f;
+    for (int m = 0; m < C; ++m) v = fmaf(w2[co * C + m], w1[m * C * K + r], v);
+    wf[i] = v;
+  }
+}
+// dw1[m][ci][k] = beta*dw1 + sum_co w2[co][m] * dwf[co][ci][k];   dw2[co][m] = beta*dw2 + sum_{ci,k} dwf[co][ci][k] * w1[m][ci][k]
+__global__ void unit_split_grads_kernel(const float* __restrict__ dwf, const float* __restrict__ w1,
+                                        const float* __restrict__ w2, int C, int K, float* __restrict__ dw1,
+                                        float* __restrict__ dw2, float beta) {
+  const int n1 = dw1 ? C * C * K : 0, n2 = dw2 ? C * C : 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2; i += gridDim.x * blockDim.x) {
+    if (i < n1) {
+      const int m = i / (C * K), r = i % (C * K);
+      float v = 0.f;
+      for (int co = 0; co < C; ++co) v = fmaf(w2[co * C + m], dwf[co * C * K + r], v);
+      dw1[i] = beta != 0.f ? fmaf(beta, dw1[i], v) : v;
+    } else {
+      const int j = i - n1, co = j / C, m = j % C;
+      const float* a = dwf + (long long)co * C * K;
+      const float* b = w1 + (long long)m * C * K;
+      float v = 0.f;
+      for (int r = 0; r < C * K; ++r) v = fmaf(a[r], b[r], v);
+      dw2[j] = beta != 0.f ? fmaf(beta, dw2[j], v) : v;
+    }
+  }
+}
 // the two scalars of l1_pair_bwd_kernel per layer, for the conv epilogue's gate stage and fm_gate_bwd_kernel
 __global__ void fm_coef_kernel(const double* __restrict__ sums, int n, const float* __restrict__ go, float scale,
                                float* __restrict__ coef) {
@@ -749,6 +782,20 @@ extern "C" int vbx_l1_pair_bwd(const float* a, const float* b, int64_t n, const 
   VBX_REQUIRE(n > 0, VBX_BAD_SHAPE, "l1_pair_bwd: empty");
   l1_pair_bwd_kernel<<<stream_blocks(n, 1024), 256, 0, ST>>>(a, b, n, sums, go, scale, da, db);
   return launched("l1_pair_bwd_kernel");
+}
+extern "C" int vbx_unit_combine(const float* w1, const float* w2, int32_t C, int32_t K, float* wf, void* stream) {
+  VBX_REQUIRE(w1 && w2 && wf, VBX_BAD_POINTER, "unit_combine: null tensor");
+  VBX_REQUIRE(C > 0 && K > 0 && (long long)C * C * K < (1 << 30), VBX_BAD_SHAPE, "unit_combine: bad shape");
+  unit_combine_kernel<<<cdiv(C * C * K, 128), 128, 0, ST>>>(w1, w2, C, K, wf);
+  return launched("unit_combine_kernel");
+}
+extern "C" int vbx_unit_split_grads(const float* dwf, const float* w1, const float* w2, int32_t C, int32_t K,
+                                    float* dw1, float* dw2, float beta, void* stream) {
+  VBX_REQUIRE(dwf && w1 && w2 && (dw1 || dw2), VBX_BAD_POINTER, "unit_split_grads: null tensor");
+  VBX_REQUIRE(C > 0 && K > 0 && (long long)C * C * K < (1 << 30), VBX_BAD_SHAPE, "unit_split_grads: bad shape");
+  const int n = (dw1 ? C * C * K : 0) + (dw2 ? C * C : 0);
+  unit_split_grads_kernel<<<cdiv(n, 128), 128, 0, ST>>>(dwf, w1, w2, C, K, dw1, dw2, beta);
+  return launched("unit_split_grads_kernel");
 }
 extern "C" int vbx_fm_coef(const double* sums, int32_t npairs, const float* go, float scale, float* coef, void* stream) {
   VBX_REQUIRE(sums && go && coef, VBX_BAD_POINTER, "fm_coef: null tensor");

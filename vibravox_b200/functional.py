@@ -19,6 +19,9 @@ from .ops import ConvGeom
 Tensor = torch.Tensor
 
 
+UNIT_COMPOSED = __import__("os").environ.get("VBX_UNIT_COMPOSED", "1") != "0"
+
+
 def _c(t: Tensor) -> Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
@@ -222,25 +225,34 @@ class ConvTransposeFn(Function):
 
 class ResidualUnitFn(Function):
     """out = x + LeakyReLU(pointwise(dilated(x)))   (ResidualUnit.forward, eben_generator.py:314-316).
-    The pointwise kernel's epilogue does the activation and the residual add and emits the
-    1-byte activation mask the backward needs (the mask is not recoverable from `out`)."""
+    Forward: one fused kernel where the shape allows (ops.residual_unit_fwd), else two conv kernels whose second epilogue
+    does the activation and the residual add; either way the 1-bit / 1-byte activation mask is kept for the backward (it is
+    not recoverable from `out`).
+    Backward, through the COMPOSED conv (include/vbx.h: vbx_unit_combine): the two bias-free convs are one k-tap conv with
+    wf = w2 . w1, so  dx = dgrad(dz, wf) + g  and  dwf = wgrad(x, dz)  are all the heavy work - one input gradient and one
+    weight gradient per unit instead of two each - and dw1 = w2^T dwf, dw2 = <dwf, w1> are C x C x 3C products.  The
+    intermediate activation h is neither saved nor re-read.  VBX_UNIT_COMPOSED=0 restores the layer-by-layer backward."""
 
     @staticmethod
     def forward(ctx, x: Tensor, w1: Tensor, wt1: Tensor, w2: Tensor, wt2: Tensor, g1: ConvGeom, g2: ConvGeom,
                 slope: float):
         x = _c(x)
         B, C, T = x.shape
-        fused = (g1.K == 3 and g1.stride == 1 and g1.groups == 1 and g1.refl == g1.pad == g1.dil and g2.K == 1
-                 and g1.Cin == g1.Cout == g2.Cin == g2.Cout == C and ops.use_fused_unit(C, T, g1.dil, B))
+        unit = (g1.K == 3 and g1.stride == 1 and g1.groups == 1 and g1.refl == g1.pad == g1.dil and g2.K == 1
+                and g1.Cin == g1.Cout == g2.Cin == g2.Cout == C)
+        fused = unit and ops.use_fused_unit(C, T, g1.dil, B)
+        train = any(ctx.needs_input_grad)
+        composed = unit and UNIT_COMPOSED
         if fused:
             # one kernel: x read once, out written once; h / mask only when a backward pass will need them
-            train = any(ctx.needs_input_grad)
             pk = ops.residual_unit_pack(_c(w1), _c(w2))
-            out, h, mask = ops.residual_unit_fwd(x, pk, g1.dil, slope, want_h=train, want_mask=train)
+            out, h, mask = ops.residual_unit_fwd(x, pk, g1.dil, slope, want_h=train and not composed, want_mask=train)
         else:
             h = ops.conv_fwd(x, w1, g1)
             out, mask = ops.conv_fwd(h, w2, g2, res=x, slope=slope, want_mask=True)
-        ctx.g1, ctx.g2, ctx.slope = g1, g2, slope
+            if composed:
+                h = None
+        ctx.g1, ctx.g2, ctx.slope, ctx.composed = g1, g2, slope, composed
         ctx.save_for_backward(x, h, mask, wt1, wt2, w1, w2)
         return out
 
@@ -253,14 +265,25 @@ class ResidualUnitFn(Function):
         T = x.shape[2]
         B, C = x.shape[0], x.shape[1]
         dz = ops.leaky_relu_bwd(g, None, slope, mask=mask)
-        tma_wgrad = (g1.K == 3 and g1.stride == 1 and g1.groups == 1 and g1.refl == g1.pad == g1.dil and g2.K == 1
-                     and g1.Cin == g1.Cout == g2.Cin == g2.Cout == C and ops.unit_wgrad_workspace(B, C, T, g1.dil, 3) > 0)
-        if ctx.needs_input_grad[3]:
+        unit = (g1.K == 3 and g1.stride == 1 and g1.groups == 1 and g1.refl == g1.pad == g1.dil and g2.K == 1
+                and g1.Cin == g1.Cout == g2.Cin == g2.Cout == C)
+        tma_wgrad = unit and ops.unit_wgrad_workspace(B, C, T, g1.dil, 3) > 0
+        need_w1, need_w2 = ctx.needs_input_grad[1], ctx.needs_input_grad[3]
+        if ctx.composed:
+            w1c, w2c = _c(w1), _c(w2)
+            wf = ops.unit_combine(w1c, w2c)
+            dw1 = dw2 = None
+            if need_w1 or need_w2:
+                dwf = ops.unit_wgrad(x, dz, 3, g1.dil) if tma_wgrad else ops.conv_wgrad(x, dz, g1)
+                dw1, dw2 = ops.unit_split_grads(dwf, w1c, w2c, need_w1, need_w2)
+            dx = ops.conv_dgrad(dz, wf, None, g1, T, res=g) if ctx.needs_input_grad[0] else None
+            return dx, dw1, None, dw2, None, None, None, None
+        if need_w2:
             dw2 = ops.unit_wgrad(h, dz, 1, 1) if tma_wgrad else ops.conv_wgrad(h, dz, g2)
         else:
             dw2 = None
         dh = ops.conv_dgrad(dz, w2, wt2, g2, T)
-        if ctx.needs_input_grad[1]:
+        if need_w1:
             dw1 = ops.unit_wgrad(x, dh, 3, g1.dil) if tma_wgrad else ops.conv_wgrad(x, dh, g1)
         else:
             dw1 = None

@@ -403,6 +403,24 @@ def l1_pair_bwd(a: Tensor, b: Tensor, sums: Tensor, go: Tensor, scale: float, wa
     return da, db
 
 
+def unit_combine(w1: Tensor, w2: Tensor) -> Tensor:
+    """wf (C, C, K) = w2 (C, C[, 1]) composed with w1 (C, C, K): the residual unit's two convs as one (vbx_unit_combine)."""
+    C, _, K = w1.shape
+    wf = torch.empty_like(w1)
+    check(_lib.load().vbx_unit_combine(_p(w1), _p(w2), C, K, _p(wf), _stream()), "vbx_unit_combine")
+    return wf
+
+
+def unit_split_grads(dwf: Tensor, w1: Tensor, w2: Tensor, want1: bool, want2: bool):
+    """(dw1, dw2) of the unit's two convs from the gradient of the composed weight (vbx_unit_split_grads)."""
+    C, _, K = w1.shape
+    dw1 = torch.empty_like(w1) if want1 else None
+    dw2 = torch.empty_like(w2) if want2 else None
+    check(_lib.load().vbx_unit_split_grads(_p(dwf), _p(w1), _p(w2), C, K, _p(dw1), _p(dw2), 0.0, _stream()),
+          "vbx_unit_split_grads")
+    return dw1, dw2
+
+
 def record_event():
     """An event on the current stream (hand-over of side-channel tensors between backward nodes on different streams)."""
     ev = torch.cuda.Event()
