@@ -24,6 +24,8 @@ from ..torch_modules.utils import share_weight_norm
 # fused backward of the discriminator chains (functional.Flags); VBX_CHAIN_FUSION=0 restores the separate aten::add /
 # L1-pair backward / LeakyReLU backward passes between the conv stages
 _CHAIN_FUSION = __import__("os").environ.get("VBX_CHAIN_FUSION", "1") != "0"
+# discriminator-phase backward enqueued on a forked stream before the generator's backward (independent work)
+_PHASE_OVERLAP = __import__("os").environ.get("VBX_PHASE_OVERLAP", "1") != "0"
 
 
 class _SegmentedStep:
@@ -343,33 +345,60 @@ class EBENLightningModule(torch.nn.Module):
                 self.log("train/generator/backprop_loss", backprop_loss_generator, sync_dist=True)
             finally:
                 Flags.param_grads = True
-            torch.autograd.backward((enhanced, enhanced_bands), (total_e, total_b))
-            self._sync_grads(g_opt)
-            g_opt.step()
-            g_opt.zero_grad()
-
-            # discriminator phase on the same graph
+            # The discriminator phase reads only what exists by now (the detached generator outputs, the stored D
+            # activations, D's parameters), and the generator's backward / update touches none of that: the two are
+            # independent, so the D-phase backward is ENQUEUED FIRST, on a forked stream, and the generator's backward - a
+            # serial chain of small kernels that leaves most SMs idle - runs underneath it.  Same arithmetic, same results
+            # (the reference runs them back to back, eben.py:107-130); the coin flip of update_discriminator_ratio keeps its
+            # place in the RNG sequence (nothing between here and the reference's draw consumes random numbers).
             update = True
             if self.update_discriminator_ratio < 1:
                 update = bool(torch.rand(1) < self.update_discriminator_ratio)
+            overlap = update and _PHASE_OVERLAP and enh.is_cuda
+            if overlap:
+                cur = torch.cuda.current_stream()
+                side = self._phase_stream(enh.device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    self._discriminator_backward(D, reference_embeddings, enhanced_embeddings, d_params)
+            torch.autograd.backward((enhanced, enhanced_bands), (total_e, total_b))
+            if overlap:
+                cur.wait_stream(side)
+            self._sync_grads(g_opt)
+            g_opt.step()
+            g_opt.zero_grad()
             if update:
-                real_loss = self.adversarial_loss_fn(embeddings=reference_embeddings, target=1)
-                fake_loss = self.adversarial_loss_fn(embeddings=enhanced_embeddings, target=-1)
-                self.log("train/discriminator/real_loss", real_loss, sync_dist=True)
-                self.log("train/discriminator/fake_loss", fake_loss, sync_dist=True)
-                backprop_loss_discriminator = WeightedSumFn.apply(None, real_loss, fake_loss)
-                self.log("train/discriminator/backprop_loss", backprop_loss_discriminator, sync_dist=True)
-                Flags.skip_leaf_input_grad = True          # nothing upstream of the detached G outputs
-                Flags.chain_reset()
-                try:
-                    torch.autograd.backward(backprop_loss_discriminator, inputs=d_params)
-                finally:
-                    Flags.skip_leaf_input_grad = False
-                Flags.chain_check()
-                self._join(D)
+                if not overlap:
+                    self._discriminator_backward(D, reference_embeddings, enhanced_embeddings, d_params)
                 self._sync_grads(d_opt)
                 d_opt.step()
                 d_opt.zero_grad()
+        return {"corrupted": corrupted_speech, "enhanced": enhanced.detach(), "reference": reference_speech}
+
+    def _discriminator_backward(self, D, reference_embeddings, enhanced_embeddings, d_params) -> None:
+        """Discriminator phase on the graph of the generator phase (eben.py:116-124): the two hinge losses and D's
+        parameter gradients, accumulated into the discriminator's flat bucket; joined onto the current stream."""
+        real_loss = self.adversarial_loss_fn(embeddings=reference_embeddings, target=1)
+        fake_loss = self.adversarial_loss_fn(embeddings=enhanced_embeddings, target=-1)
+        self.log("train/discriminator/real_loss", real_loss, sync_dist=True)
+        self.log("train/discriminator/fake_loss", fake_loss, sync_dist=True)
+        backprop_loss_discriminator = WeightedSumFn.apply(None, real_loss, fake_loss)
+        self.log("train/discriminator/backprop_loss", backprop_loss_discriminator, sync_dist=True)
+        Flags.skip_leaf_input_grad = True          # nothing upstream of the detached G outputs
+        Flags.chain_reset()
+        try:
+            torch.autograd.backward(backprop_loss_discriminator, inputs=d_params)
+        finally:
+            Flags.skip_leaf_input_grad = False
+        Flags.chain_check()
+        self._join(D)
+
+    def _phase_stream(self, device):
+        cache = self.__dict__.setdefault("_phase_streams", {})
+        if device not in cache:
+            cache[device] = torch.cuda.Stream(device=device)
+        return cache[device]
+
         return {"corrupted": corrupted_speech, "enhanced": enhanced.detach(), "reference": reference_speech}
 
     def _balance_from_output_grads(self, enhanced, enhanced_bands, grads) -> torch.Tensor:
