@@ -393,22 +393,26 @@ __global__ void unit_combine_kernel(const float* __restrict__ w1, const float* _
 // dw1[m][ci][k] = beta*dw1 + sum_co w2[co][m] * dwf[co][ci][k];   dw2[co][m] = beta*dw2 + sum_{ci,k} dwf[co][ci][k] * w1[m][ci][k]
 __global__ void unit_split_grads_kernel(const float* __restrict__ dwf, const float* __restrict__ w1,
                                         const float* __restrict__ w2, int C, int K, float* __restrict__ dw1,
-                                        float* __restrict__ dw2, float beta) {
-  const int n1 = dw1 ? C * C * K : 0, n2 = dw2 ? C * C : 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2; i += gridDim.x * blockDim.x) {
-    if (i < n1) {
-      const int m = i / (C * K), r = i % (C * K);
-      float v = 0.f;
-      for (int co = 0; co < C; ++co) v = fmaf(w2[co * C + m], dwf[co * C * K + r], v);
-      dw1[i] = beta != 0.f ? fmaf(beta, dw1[i], v) : v;
-    } else {
-      const int j = i - n1, co = j / C, m = j % C;
-      const float* a = dwf + (long long)co * C * K;
-      const float* b = w1 + (long long)m * C * K;
-      float v = 0.f;
-      for (int r = 0; r < C * K; ++r) v = fmaf(a[r], b[r], v);
-      dw2[j] = beta != 0.f ? fmaf(beta, dw2[j], v) : v;
-    }
+                                        float* __restrict__ dw2, float beta, int nb1) {
+  if ((int)blockIdx.x < nb1) {                            // dw1: one thread per output, coalesced over (ci, k)
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C * C * K) return;
+    const int m = i / (C * K), r = i % (C * K);
+    float v = 0.f;
+#pragma unroll 4
+    for (int co = 0; co < C; ++co) v = fmaf(w2[co * C + m], dwf[co * C * K + r], v);
+    dw1[i] = beta != 0.f ? fmaf(beta, dw1[i], v) : v;
+  } else {                                                // dw2: one warp per output, lanes over the (ci, k) products
+    const int j = ((int)blockIdx.x - nb1) * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (j >= C * C) return;
+    const int co = j / C, m = j % C;
+    const float* a = dwf + (long long)co * C * K;
+    const float* b = w1 + (long long)m * C * K;
+    float v = 0.f;
+    for (int r = lane; r < C * K; r += 32) v = fmaf(a[r], b[r], v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) dw2[j] = beta != 0.f ? fmaf(beta, dw2[j], v) : v;
   }
 }
 // the two scalars of l1_pair_bwd_kernel per layer, for the conv epilogue's gate stage and fm_gate_bwd_kernel
@@ -793,8 +797,8 @@ extern "C" int vbx_unit_split_grads(const float* dwf, const float* w1, const flo
                                     float* dw1, float* dw2, float beta, void* stream) {
   VBX_REQUIRE(dwf && w1 && w2 && (dw1 || dw2), VBX_BAD_POINTER, "unit_split_grads: null tensor");
   VBX_REQUIRE(C > 0 && K > 0 && (long long)C * C * K < (1 << 30), VBX_BAD_SHAPE, "unit_split_grads: bad shape");
-  const int n = (dw1 ? C * C * K : 0) + (dw2 ? C * C : 0);
-  unit_split_grads_kernel<<<cdiv(n, 128), 128, 0, ST>>>(dwf, w1, w2, C, K, dw1, dw2, beta);
+  const int nb1 = dw1 ? cdiv(C * C * K, 128) : 0, nb2 = dw2 ? cdiv(C * C, 4) : 0;      // 4 warps per block
+  unit_split_grads_kernel<<<nb1 + nb2, 128, 0, ST>>>(dwf, w1, w2, C, K, dw1, dw2, beta, nb1);
   return launched("unit_split_grads_kernel");
 }
 extern "C" int vbx_fm_coef(const double* sums, int32_t npairs, const float* go, float scale, float* coef, void* stream) {
