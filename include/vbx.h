@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define VBX_ABI_VERSION 5
+#define VBX_ABI_VERSION 6
 #if defined(__GNUC__)
 #define VBX_API __attribute__((visibility("default")))
 #else
@@ -59,6 +59,9 @@ typedef struct {
   const float* fm_other;
   const float* fm_coef;
   float gate_slope;
+  float* gate_dbias;   /* with gate, input-gradient entries only: gate_dbias[c] += sum over (b, t) of out[b, c, t] - the
+                        * bias gradient of the stage that produced `gate` (its dy IS this output), reduced in the same
+                        * in-place pass where the gate runs as one, else in one read-only pass */
 } vbx_epilogue;
 
 VBX_API int vbx_abi_version(void);

@@ -51,8 +51,11 @@ def conv1d_dgrad(dy, wt, g, Tin, res=None, slope=1.0, out=None, beta=0.0, bias=N
     if gate is None:
         return _epi(dx, bias, res, slope, False, out, beta)
     assert out is None and not beta
-    y, gslope, other, coef = gate
-    return fm_gate_bwd(y, other, coef, gslope, _epi(dx, bias, res, slope, False, None, 0.0))
+    y, gslope, other, coef = gate[:4]
+    got = fm_gate_bwd(y, other, coef, gslope, _epi(dx, bias, res, slope, False, None, 0.0))
+    if len(gate) > 4 and gate[4] is not None:
+        gate[4].add_(got.sum((0, 2)))
+    return got
 
 
 def fm_coef(sums, n, go, scale):

@@ -20,7 +20,7 @@ class Epilogue(ctypes.Structure):
     _fields_ = [("bias", ctypes.c_void_p), ("res", ctypes.c_void_p), ("mask", ctypes.c_void_p),
                 ("slope", ctypes.c_float), ("beta", ctypes.c_float),
                 ("gate", ctypes.c_void_p), ("fm_other", ctypes.c_void_p), ("fm_coef", ctypes.c_void_p),
-                ("gate_slope", ctypes.c_float)]
+                ("gate_slope", ctypes.c_float), ("gate_dbias", ctypes.c_void_p)]
 
 
 def build():
@@ -70,7 +70,7 @@ def emu(mode, desc, a, b, out, bias=None, res=None, mask=None, slope=1.0, beta=0
     def ptr(t):
         return t.data_ptr() if t is not None else None
     y, gslope, other, coef = gate if gate is not None else (None, 1.0, None, None)
-    e = Epilogue(ptr(bias), ptr(res), ptr(mask), slope, beta, ptr(y), ptr(other), ptr(coef), gslope)
+    e = Epilogue(ptr(bias), ptr(res), ptr(mask), slope, beta, ptr(y), ptr(other), ptr(coef), gslope, None)
     r = lib().emu_conv(mode, ctypes.byref(desc), ctypes.c_void_p(a.data_ptr()),
                        ctypes.c_void_p(b.data_ptr()), ctypes.byref(e), ctypes.c_void_p(out.data_ptr()))
     assert r == 0, r

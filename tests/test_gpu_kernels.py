@@ -362,6 +362,13 @@ def test_input_gradient_gate_stage_equals_the_separate_passes(case):
         want = ops.leaky_relu_bwd(plain, y, 0.2)
         assert torch.equal(dgrad((y, 0.2, other, coef)), want_fm), tc
         assert torch.equal(dgrad((y, 0.2, None, None)), want), tc
+        # + the bias gradient of the stage that produced y, reduced with the gate (accumulates onto the slot)
+        for gate_args, ref in (((y, 0.2, None, None), want), ((y, 0.2, other, coef), want_fm)):
+            db = torch.full((Cin,), 0.5, device=DEV)
+            got = dgrad(gate_args + (db,))
+            assert torch.equal(got, ref), tc
+            wdb = ref.double().sum((0, 2)) + 0.5
+            assert (db.double() - wdb).abs().max() <= 1e-5 * float(ref.double().abs().sum((0, 2)).max() + 1), tc
     assert torch.equal(ops.fm_gate_bwd(y, other, coef, 0.2, plain), want_fm)
     assert torch.equal(ops.fm_gate_bwd(y, other, coef, 0.2, None), ops.leaky_relu_bwd(da, y, 0.2))
     assert torch.equal(ops.fm_gate_bwd(y, None, None, 0.2, plain), want)

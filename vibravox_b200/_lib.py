@@ -14,7 +14,7 @@ import torch  # noqa: F401  (must precede the CDLL load, see module docstring)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvbx_b200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 c_int, c_i64, c_f, c_d, c_p = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double, ctypes.c_void_p
 
@@ -28,7 +28,7 @@ class ConvDesc(ctypes.Structure):
 class Epilogue(ctypes.Structure):
     """vbx_epilogue"""
     _fields_ = [("bias", c_p), ("res", c_p), ("mask", c_p), ("slope", c_f), ("beta", c_f),
-                ("gate", c_p), ("fm_other", c_p), ("fm_coef", c_p), ("gate_slope", c_f)]
+                ("gate", c_p), ("fm_other", c_p), ("fm_coef", c_p), ("gate_slope", c_f), ("gate_dbias", c_p)]
 
 
 _PD, _PE = ctypes.POINTER(ConvDesc), ctypes.POINTER(Epilogue)

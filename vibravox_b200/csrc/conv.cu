@@ -101,7 +101,7 @@ extern "C" int vbx_conv1d_dgrad(const vbx_conv_desc* d, const float* dy, const f
     Plan pl = plan_conv(DGRAD, P);
     rc = launch_cfg<DGRAD, false>(pl, P, (cudaStream_t)stream);
   }
-  return gate.finish(rc, dx, (long long)d->B * d->Cin * d->Tin, stream);
+  return gate.finish(rc, dx, d->B, d->Cin, d->Tin, stream);
 }
 
 extern "C" int vbx_conv1d_wgrad(const vbx_conv_desc* d, const float* x, const float* dy, float* dw,

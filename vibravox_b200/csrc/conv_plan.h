@@ -21,19 +21,28 @@ inline int& deterministic_flag() { static int flag = 0; return flag; }
 int gate_epilogue_forms();
 int launch_fm_gate(const float* y, const float* other, const float* coef, float gslope, const float* g, long long n,
                    float* out, void* stream);
+// dx = dy * (ref > 0 ? 1 : slope) (dx may alias dy, or be NULL) and dbias[c] += sum of it: misc.cu
+int launch_lrelu_bwd_bias(const float* dy, const float* ref, float* dx, float* dbias, int B, int C, int T, float slope,
+                          void* stream);
 
 struct GateArgs {
-  const float* y; const float* other; const float* coef; float slope;
+  const float* y; const float* other; const float* coef; float slope; float* dbias;
   // takes the gate stage out of P when `form` does not run it in its epilogue
-  GateArgs(GemmP& P, int form) : y(nullptr), other(P.fm_other), coef(P.fm_coef), slope(P.gate_slope) {
+  GateArgs(GemmP& P, int form) : y(nullptr), other(P.fm_other), coef(P.fm_coef), slope(P.gate_slope), dbias(P.gate_dbias) {
     if (P.gate && !(gate_epilogue_forms() & form)) {
       y = P.gate;
       P.gate = nullptr; P.fm_other = nullptr; P.fm_coef = nullptr;
     }
   }
-  int finish(int rc, float* out, long long n, void* stream) const {
-    if (rc != 0 || !y) return rc;
-    return launch_fm_gate(y, other, coef, slope, out, n, out, stream);
+  // out is (B, C, T)
+  int finish(int rc, float* out, int B, int C, int T, void* stream) const {
+    if (rc != 0) return rc;
+    const long long n = (long long)B * C * T;
+    if (y && dbias && !other)                     // gate and bias gradient in ONE in-place pass
+      return launch_lrelu_bwd_bias(out, y, out, dbias, B, C, T, slope, stream);
+    if (y) rc = launch_fm_gate(y, other, coef, slope, out, n, out, stream);
+    if (rc == 0 && dbias) rc = launch_lrelu_bwd_bias(out, nullptr, nullptr, dbias, B, C, T, 1.f, stream);
+    return rc;
   }
 };
 
@@ -78,13 +87,14 @@ inline void fill(GemmP& P, const vbx_conv_desc* d) {
   P.mtiles = 1; P.split = 0;
   P.W = nullptr; P.X = nullptr; P.DY = nullptr; P.Y = nullptr;
   P.bias = nullptr; P.res = nullptr; P.mask = nullptr; P.slope = 1.f; P.beta = 0.f;
-  P.gate = nullptr; P.fm_other = nullptr; P.fm_coef = nullptr; P.gate_slope = 1.f;
+  P.gate = nullptr; P.fm_other = nullptr; P.fm_coef = nullptr; P.gate_slope = 1.f; P.gate_dbias = nullptr;
 }
 inline void fill_epi(GemmP& P, const vbx_epilogue* e) {
   if (!e) return;
   P.bias = e->bias; P.res = e->res; P.mask = e->mask; P.slope = e->slope; P.beta = e->beta;
   P.gate = e->gate; P.gate_slope = e->gate_slope;
   P.fm_other = e->gate ? e->fm_other : nullptr; P.fm_coef = P.fm_other ? e->fm_coef : nullptr;
+  P.gate_dbias = e->gate ? e->gate_dbias : nullptr;
 }
 
 struct Plan { int tm; bool bk; int grid[3]; };

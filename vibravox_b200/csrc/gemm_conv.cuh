@@ -56,6 +56,7 @@ struct GemmP {
   const float* fm_other;  // optional, with gate: v += fm_coef[0]*sign(y - fm_other) - fm_coef[1]*sign(y) before the gate
   const float* fm_coef;
   float gate_slope;
+  float* gate_dbias;      // optional, with gate (host side only: conv_plan.h GateArgs runs the reduction after the kernel)
 };
 
 // the gate stage of vbx_epilogue on one value (exact products: sign() is -1/0/1, so the sum below rounds exactly like

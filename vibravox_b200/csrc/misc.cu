@@ -704,6 +704,12 @@ extern "C" int vbx_leaky_relu_fwd(const float* x, float* y, int64_t n, float slo
   leaky_relu_fwd_kernel<<<stream_blocks(n, 1024), 256, 0, ST>>>(x, y, n, slope);
   return launched("leaky_relu_fwd_kernel");
 }
+namespace vbx {
+int launch_lrelu_bwd_bias(const float* dy, const float* ref, float* dx, float* dbias, int B, int C, int T, float slope,
+                          void* stream) {
+  return vbx_leaky_relu_bwd(dy, ref, nullptr, dx, dbias, B, C, T, slope, 0.f, stream);
+}
+}  // namespace vbx
 extern "C" int vbx_leaky_relu_bwd(const float* dy, const float* ref, const uint8_t* mask, float* dx, float* dbias,
                                   int32_t B, int32_t C, int32_t T, float slope, float beta, void* stream) {
   VBX_REQUIRE(dy && (dx || dbias), VBX_BAD_POINTER, "leaky_relu_bwd: null tensor");

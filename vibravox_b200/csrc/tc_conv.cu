@@ -1221,7 +1221,7 @@ extern "C" int vbx_tc_conv1d_dgrad(const vbx_conv_desc* d, const float* dy, cons
   if (P.slab) rc = P.ps ? launch_pslab(P, (cudaStream_t)stream) : launch_slab(P, (cudaStream_t)stream);
   else if (P.merged) rc = launch_tc<FWD>(P, (cudaStream_t)stream);
   else rc = launch_tc<DGRAD>(P, (cudaStream_t)stream);
-  return gate.finish(rc, dx, (long long)d->B * d->Cin * d->Tin, stream);
+  return gate.finish(rc, dx, d->B, d->Cin, d->Tin, stream);
 }
 
 #include "tc_wslab.cuh"

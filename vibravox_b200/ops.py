@@ -67,14 +67,17 @@ class ConvGeom:
 
 
 def _epi(bias=None, res=None, mask=None, slope=1.0, beta=0.0, gate=None) -> Epilogue:
-    """`gate` = (y, gate_slope, fm_other, fm_coef): the producer-side LeakyReLU' (+ feature-matching gradient) stage of an
-    input-gradient epilogue (include/vbx.h: vbx_epilogue)."""
+    """`gate` = (y, gate_slope, fm_other, fm_coef[, gate_dbias]): the producer-side LeakyReLU' (+ feature-matching gradient,
+    + bias gradient) stage of an input-gradient epilogue (include/vbx.h: vbx_epilogue)."""
     if gate is None:
-        return Epilogue(_p(bias), _p(res), _p(mask, torch.uint8), float(slope), float(beta), None, None, None, 1.0)
-    y, gslope, other, coef = gate
+        return Epilogue(_p(bias), _p(res), _p(mask, torch.uint8), float(slope), float(beta), None, None, None, 1.0, None)
+    y, gslope, other, coef = gate[:4]
+    dbias = gate[4] if len(gate) > 4 else None           # bias gradient of the stage that produced y (accumulated)
     assert (other is None) == (coef is None)
+    if dbias is not None:
+        assert dbias.numel() == y.shape[1]
     return Epilogue(_p(bias), _p(res), _p(mask, torch.uint8), float(slope), float(beta), _p(y), _p(other), _p(coef),
-                    float(gslope))
+                    float(gslope), _p(dbias))
 
 
 # ------------------------------------------------------------------ conv family

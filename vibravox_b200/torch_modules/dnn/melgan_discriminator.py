@@ -39,15 +39,16 @@ def run_chain(stages, x: torch.Tensor) -> List[torch.Tensor]:
     it, so that its input-gradient kernel finishes that stage's LeakyReLU / feature-matching backward, and the outputs are
     tagged for the feature-matching loss."""
     chain = Flags.gated_chain and torch.is_grad_enabled()
-    embeddings, prev_slope = [x], 1.0
+    embeddings, prev_slope, prev_bias = [x], 1.0, None
     for stage in stages:
         conv, extra, slope = _parse_stage(stage)
         w, wt = effective_weight(conv)
-        y = ConvFn.apply(embeddings[-1], w, wt, conv.bias, conv_geom(conv, extra), slope, prev_slope if chain else 1.0)
+        y = ConvFn.apply(embeddings[-1], w, wt, conv.bias, conv_geom(conv, extra), slope, prev_slope if chain else 1.0,
+                         prev_bias if chain else None)
         if chain and slope != 1.0:
             y._vbx_chain = True
         embeddings.append(y)
-        prev_slope = slope
+        prev_slope, prev_bias = slope, conv.bias
     return embeddings
 
 
