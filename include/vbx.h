@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define VBX_ABI_VERSION 6
+#define VBX_ABI_VERSION 7
 #if defined(__GNUC__)
 #define VBX_API __attribute__((visibility("default")))
 #else
@@ -207,6 +207,11 @@ VBX_API int vbx_l1_pair_bwd(const float* a, const float* b, int64_t n, const dou
  * gradient and a single weight gradient - dx = dgrad(dz, wf) + g and dwf = wgrad(x, dz) - from which
  * vbx_unit_split_grads recovers  dw1 = w2^T dwf  and  dw2[co][m] = <dwf[co], w1[m]>  (either may be NULL; beta scales
  * what the outputs hold).  The intermediate activation h of the forward pass is not needed by the backward pass. */
+/* dx += the mirror terms of the input gradient of a k = 3, stride-1, groups-1 conv (C -> C) whose reflect halo equals its
+ * dilation: with them, the ZERO-halo input gradient (the fast slab-form kernels) becomes the reflect-halo one
+ * (eben_generator.py:295-312 padding_mode="reflect").  w is W[co][ci][3]; touches 2*dil positions per row. */
+VBX_API int vbx_reflect_fold_k3(const float* dy, const float* w, float* dx, int32_t B, int32_t C, int32_t T, int32_t dil,
+                        void* stream);
 VBX_API int vbx_unit_combine(const float* w1, const float* w2, int32_t C, int32_t K, float* wf, void* stream);
 VBX_API int vbx_unit_split_grads(const float* dwf, const float* w1, const float* w2, int32_t C, int32_t K, float* dw1,
                          float* dw2, float beta, void* stream);

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), s
     assert sorted(_lib.SIGNATURES) == syms
-    assert lib.vbx_abi_version() == _lib.ABI_VERSION == 6
+    assert lib.vbx_abi_version() == _lib.ABI_VERSION == 7
 
 
 def test_ops_refuse_cpu_tensors():

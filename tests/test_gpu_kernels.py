@@ -607,20 +607,21 @@ def test_residual_unit_composed_backward_matches_fp64_and_the_layerwise_backward
     y64 = x64 + F.leaky_relu(F.conv1d(h64, w264), 0.01)
     want = torch.autograd.grad(y64, (x64, w164, w264), go.double())
     res = {}
-    for composed in (True, False):
-        old, functional.UNIT_COMPOSED = functional.UNIT_COMPOSED, composed
+    for mode in ("composed", "layerwise", "zero_halo"):     # zero_halo: composed + slab-form zero-halo dgrad + mirror terms
+        old = functional.UNIT_COMPOSED, functional.UNIT_ZERO_HALO_DGRAD
+        functional.UNIT_COMPOSED, functional.UNIT_ZERO_HALO_DGRAD = mode != "layerwise", mode == "zero_halo"
         try:
             y = ResidualUnitFn.apply(x, w1, ops.transpose_weight(w1.detach(), 1), w2, ops.transpose_weight(w2.detach(), 1),
                                      g1, g2, 0.01)
-            res[composed] = torch.autograd.grad(y, (x, w1, w2), go)
+            res[mode] = torch.autograd.grad(y, (x, w1, w2), go)
         finally:
-            functional.UNIT_COMPOSED = old
+            functional.UNIT_COMPOSED, functional.UNIT_ZERO_HALO_DGRAD = old
         assert (y.double() - y64).abs().max() < 2e-4 * float(y64.abs().max())
-    for a, b, w in zip(res[True], res[False], want):
-        scale = float(w.abs().max())
-        assert (a.double() - w).abs().max() < 3e-4 * scale, (C, (a.double() - w).abs().max() / scale)
-        assert (b.double() - w).abs().max() < 3e-4 * scale
-        assert (a.double() - w).norm() / w.norm() < 1e-4
+    for mode, grads in res.items():
+        for a, w in zip(grads, want):
+            scale = float(w.abs().max())
+            assert (a.double() - w).abs().max() < 3e-4 * scale, (mode, C, (a.double() - w).abs().max() / scale)
+            assert (a.double() - w).norm() / w.norm() < 1e-4, mode
 
 
 WG_CASES = [  # B, C, T, dilation, K

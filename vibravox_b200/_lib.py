@@ -14,7 +14,7 @@ import torch  # noqa: F401  (must precede the CDLL load, see module docstring)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvbx_b200.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 c_int, c_i64, c_f, c_d, c_p = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double, ctypes.c_void_p
 
@@ -72,6 +72,7 @@ SIGNATURES = {
     "vbx_l1_pair_sums": [c_p, c_p, c_i64, c_p, c_p],
     "vbx_fm_finalize": [c_p, c_int, c_f, c_p, c_p],
     "vbx_l1_pair_bwd": [c_p, c_p, c_i64, c_p, c_p, c_f, c_p, c_p, c_p],
+    "vbx_reflect_fold_k3": [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p],
     "vbx_unit_combine": [c_p, c_p, c_int, c_int, c_p, c_p],
     "vbx_unit_split_grads": [c_p, c_p, c_p, c_int, c_int, c_p, c_p, c_f, c_p],
     "vbx_fm_coef": [c_p, c_int, c_p, c_f, c_p, c_p],

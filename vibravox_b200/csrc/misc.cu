@@ -415,6 +415,27 @@ __global__ void unit_split_grads_kernel(const float* __restrict__ dwf, const flo
     if (lane == 0) dw2[j] = beta != 0.f ? fmaf(beta, dw2[j], v) : v;
   }
 }
+// Mirror terms of a k = 3, stride-1 conv whose reflect halo equals its dilation d (the residual units' dilated conv):
+// the input gradient is the ZERO-halo input gradient plus, on the d positions next to each edge,
+//   dx[b, ci, u]         += sum_co w[co, ci, 0] * dy[b, co, d - u]              (u = 1 .. d)
+//   dx[b, ci, T - 1 - j] += sum_co w[co, ci, 2] * dy[b, co, T - 1 + j - d]      (j = 1 .. d)
+// (the other taps of a mirrored position fall outside the signal).  One thread per (b, ci, side, j).
+__global__ void reflect_fold_k3_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
+                                       int B, int C, int T, int d) {
+  const int n = B * C * 2 * d;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int j = i % d + 1, side = (i / d) & 1, ci = (i / (2 * d)) % C, b = i / (2 * d * C);
+    const int u = side == 0 ? j : T - 1 - j;
+    const int t = side == 0 ? d - j : T - 1 + j - d;
+    if (u < 0 || u >= T || t < 0 || t >= T) continue;
+    const int k = side == 0 ? 0 : 2;
+    const float* dyb = dy + (long long)b * C * T + t;
+    float v = 0.f;
+#pragma unroll 4
+    for (int co = 0; co < C; ++co) v = fmaf(w[((long long)co * C + ci) * 3 + k], dyb[(long long)co * T], v);
+    dx[((long long)b * C + ci) * T + u] += v;
+  }
+}
 // the two scalars of l1_pair_bwd_kernel per layer, for the conv epilogue's gate stage and fm_gate_bwd_kernel
 __global__ void fm_coef_kernel(const double* __restrict__ sums, int n, const float* __restrict__ go, float scale,
                                float* __restrict__ coef) {
@@ -792,6 +813,14 @@ extern "C" int vbx_l1_pair_bwd(const float* a, const float* b, int64_t n, const 
   VBX_REQUIRE(n > 0, VBX_BAD_SHAPE, "l1_pair_bwd: empty");
   l1_pair_bwd_kernel<<<stream_blocks(n, 1024), 256, 0, ST>>>(a, b, n, sums, go, scale, da, db);
   return launched("l1_pair_bwd_kernel");
+}
+extern "C" int vbx_reflect_fold_k3(const float* dy, const float* w, float* dx, int32_t B, int32_t C, int32_t T,
+                                   int32_t dil, void* stream) {
+  VBX_REQUIRE(dy && w && dx, VBX_BAD_POINTER, "reflect_fold_k3: null tensor");
+  VBX_REQUIRE(B > 0 && C > 0 && T > 1 && dil > 0 && dil <= T - 1 && (long long)B * C * 2 * dil < (1ll << 31), VBX_BAD_SHAPE,
+              "reflect_fold_k3: bad shape");
+  reflect_fold_k3_kernel<<<cdiv(B * C * 2 * dil, 128), 128, 0, ST>>>(dy, w, dx, B, C, T, dil);
+  return launched("reflect_fold_k3_kernel");
 }
 extern "C" int vbx_unit_combine(const float* w1, const float* w2, int32_t C, int32_t K, float* wf, void* stream) {
   VBX_REQUIRE(w1 && w2 && wf, VBX_BAD_POINTER, "unit_combine: null tensor");

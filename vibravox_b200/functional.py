@@ -20,6 +20,9 @@ Tensor = torch.Tensor
 
 
 UNIT_COMPOSED = __import__("os").environ.get("VBX_UNIT_COMPOSED", "1") != "0"
+# unit input gradient as the zero-halo gradient on the slab-form kernels + vbx_reflect_fold_k3 (mirror terms).  Off by
+# default: parity-green, but measured 36.5 vs 35.7 ms per step - at C <= 128 the gather-form reflect kernel is the faster one
+UNIT_ZERO_HALO_DGRAD = __import__("os").environ.get("VBX_UNIT_ZERO_HALO_DGRAD", "0") == "1"
 # bias gradient of a chain stage reduced inside the next stage's gate pass (vbx_epilogue.gate_dbias).  Off by default:
 # measured 36.6 vs 35.9 ms per step - the per-channel reduction lengthens a pass that the rest of the chain waits for,
 # while the separate read-only reduction runs beside the chain
@@ -294,7 +297,15 @@ class ResidualUnitFn(Function):
             if need_w1 or need_w2:
                 dwf = ops.unit_wgrad(x, dz, 3, g1.dil) if tma_wgrad else ops.conv_wgrad(x, dz, g1)
                 dw1, dw2 = ops.unit_split_grads(dwf, w1c, w2c, need_w1, need_w2)
-            dx = ops.conv_dgrad(dz, wf, None, g1, T, res=g) if ctx.needs_input_grad[0] else None
+            dx = None
+            if ctx.needs_input_grad[0]:
+                if UNIT_ZERO_HALO_DGRAD and ops.TC_ENABLED and T > 2 * g1.dil:
+                    # zero-halo input gradient on the slab-form kernels + the mirror terms of the 2*d edge positions
+                    gz = ConvGeom(g1.Cin, g1.Cout, g1.K, g1.stride, g1.dil, g1.pad, 0, g1.groups)
+                    dx = ops.conv_dgrad(dz, wf, None, gz, T, res=g)
+                    ops.reflect_fold_k3(dz, wf, dx, g1.dil)
+                else:
+                    dx = ops.conv_dgrad(dz, wf, None, g1, T, res=g)
             return dx, dw1, None, dw2, None, None, None, None
         if need_w2:
             dw2 = ops.unit_wgrad(h, dz, 1, 1) if tma_wgrad else ops.conv_wgrad(h, dz, g2)

@@ -406,6 +406,15 @@ def l1_pair_bwd(a: Tensor, b: Tensor, sums: Tensor, go: Tensor, scale: float, wa
     return da, db
 
 
+def reflect_fold_k3(dy: Tensor, w: Tensor, dx: Tensor, dil: int) -> Tensor:
+    """dx += mirror terms: turns the zero-halo input gradient of a k3 / stride-1 / reflect-halo = dilation conv into the
+    reflect-halo one (vbx_reflect_fold_k3)."""
+    B, C, T = dx.shape
+    assert dy.shape == dx.shape and tuple(w.shape) == (C, C, 3)
+    check(_lib.load().vbx_reflect_fold_k3(_p(dy), _p(w), _p(dx), B, C, T, dil, _stream()), "vbx_reflect_fold_k3")
+    return dx
+
+
 def unit_combine(w1: Tensor, w2: Tensor) -> Tensor:
     """wf (C, C, K) = w2 (C, C[, 1]) composed with w1 (C, C, K): the residual unit's two convs as one (vbx_unit_combine)."""
     C, _, K = w1.shape
