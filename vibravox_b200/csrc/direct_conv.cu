@@ -293,9 +293,11 @@ __global__ void __launch_bounds__(kDirThreads) direct_fwd4_kernel(const GemmP P,
       w[j] = p >= 0 ? xr[p] : 0.f;
     }
   }
-  const bool vec = (P.Tout & 3) == 0 && t0 + R <= P.Tout && !P.mask && !P.res && P.beta == 0.f &&
+  const bool vec = (P.Tout & 3) == 0 && t0 + R <= P.Tout && !P.mask && !P.res && P.beta == 0.f && !P.gate &&
                    (reinterpret_cast<uintptr_t>(P.Y) & 15) == 0;
-#pragma unroll
+  // (the channel loop stays ROLLED: fully unrolled, the 16 x 15 x 4 FMA body runs once per warp and the kernel is bound by
+  //  instruction fetch - ncu: top stall no_instruction at 7.9 cycles per issue)
+#pragma unroll 1
   for (int j = 0; j < CG; ++j) {
     if (j < Cg) {
       float wt[KP];
@@ -310,10 +312,12 @@ __global__ void __launch_bounds__(kDirThreads) direct_fwd4_kernel(const GemmP P,
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = fmaf(wt[k], w[k + r], acc[r]);
       const long long o = ((long long)b * P.Cout + j) * P.Tout + t0;
-      if (vec) {
+      if (vec) {                                         // bias + LeakyReLU only: nothing per element but the select
+        const float bv = P.bias ? __ldg(P.bias + j) : 0.f, sl = P.slope;
         float4 v;
-        v.x = dir_finish(P, acc[0], j, o); v.y = dir_finish(P, acc[1], j, o + 1);
-        v.z = dir_finish(P, acc[2], j, o + 2); v.w = dir_finish(P, acc[3], j, o + 3);
+        v.x = acc[0] + bv; v.y = acc[1] + bv; v.z = acc[2] + bv; v.w = acc[3] + bv;
+        v.x = v.x > 0.f ? v.x : v.x * sl; v.y = v.y > 0.f ? v.y : v.y * sl;
+        v.z = v.z > 0.f ? v.z : v.z * sl; v.w = v.w > 0.f ? v.w : v.w * sl;
         *reinterpret_cast<float4*>(P.Y + o) = v;
       } else {
 #pragma unroll
@@ -442,7 +446,7 @@ __global__ void __launch_bounds__(kDirThreads) skinny_fwd_kernel(const GemmP P, 
 #pragma unroll
     for (int k = 0; k < 3; ++k) p[k] = map_pos(t + k * P.dil - P.pad, P.Tin, P.refl);
     const float* __restrict__ xb = P.X + (long long)b * P.Cin * P.Tin;
-#pragma unroll 4
+#pragma unroll 8
     for (int c = c0; c < c1; ++c) {
       const float* __restrict__ xr = xb + (long long)c * P.Tin;
       float xv[3];
@@ -479,7 +483,7 @@ bool skinny_fwd_ok(const GemmP& P) {
 int skinny_fwd(const GemmP& P, cudaStream_t st) {
   // slices of the input channels per block: enough blocks to fill the machine on the short certainty maps
   int nslice = 1;
-  while (nslice < 8 && (long long)P.B * P.Tout * nslice < 148LL * 8 * kDirThreads && P.Cin / (2 * nslice) >= 8) nslice *= 2;
+  while (nslice < 16 && (long long)P.B * P.Tout * nslice < 148LL * 8 * kDirThreads && P.Cin / (2 * nslice) >= 8) nslice *= 2;
   const int ppb = kDirThreads / nslice;
   const int tiles = (P.Tout + ppb - 1) / ppb;
   const long long grid = (long long)P.B * tiles;
