@@ -124,6 +124,32 @@ def test_fused_discriminator_chain_backward_equals_the_separate_passes(golden_di
         assert results[True][2][k] == pytest.approx(v, rel=1e-5, abs=1e-6), k
 
 
+def test_chain_contract_violations_fail_loudly():
+    """functional.Flags: a feature-matching term that no conv stage applies is an error at the end of the backward pass (not
+    a silently missing gradient), and the fused feature-matching backward refuses gradients for the reference features."""
+    from vibravox_b200.functional import FeatureMatchingFn, Flags
+    with cpu_ops():
+        a = torch.randn(2, 3, 16, requires_grad=True)
+        b = torch.randn(2, 3, 16)
+        Flags.chain_reset()
+        loss = FeatureMatchingFn.apply(0.5, 1, True, a * 1.0, b)          # fused, but `a * 1.0` is not a ConvFn stage output
+        loss.backward()
+        with pytest.raises(RuntimeError, match="feature-matching gradient terms"):
+            Flags.chain_check()
+        assert not Flags.pending                                          # (chain_check leaves the tables clean)
+        b2 = torch.randn(2, 3, 16, requires_grad=True)
+        loss = FeatureMatchingFn.apply(0.5, 1, True, a * 1.0, b2 * 1.0)
+        with pytest.raises(NotImplementedError):
+            loss.backward()
+        Flags.chain_reset()
+        # the unfused form is the ordinary differentiable loss
+        a.grad = None
+        FeatureMatchingFn.apply(0.5, 1, False, a * 1.0, b).backward()
+        ref = a.detach().clone().requires_grad_(True)
+        (0.5 * (ref - b).abs().mean() / ref.abs().mean()).backward()
+        assert torch.allclose(a.grad, ref.grad, atol=1e-6)
+
+
 def test_flat_adam_state_dict_is_torch_adam_compatible():
     """FlatAdam.state_dict() is the layout torch.optim.Adam writes: a torch Adam loaded from it takes the same next
     step, and FlatAdam loaded from a torch Adam state continues that optimizer's trajectory."""

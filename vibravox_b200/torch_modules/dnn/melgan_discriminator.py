@@ -26,13 +26,6 @@ def _parse_stage(stage: nn.Module):
     return conv, extra, slope
 
 
-def run_stage(stage: nn.Module, x: torch.Tensor) -> torch.Tensor:
-    """One entry of a discriminator's ModuleList: [ReflectionPad1d] + wn-Conv1d [+ LeakyReLU]."""
-    conv, extra, slope = _parse_stage(stage)
-    w, wt = effective_weight(conv)
-    return ConvFn.apply(x, w, wt, conv.bias, conv_geom(conv, extra), slope)
-
-
 def run_chain(stages, x: torch.Tensor) -> List[torch.Tensor]:
     """[x, stage_1(x), stage_2(stage_1(x)), ...] - the embeddings list of the reference forwards.  Under
     functional.Flags.gated_chain (the training step's discriminator calls) every stage is told the slope of the stage before
