@@ -26,6 +26,8 @@ from ..torch_modules.utils import share_weight_norm
 _CHAIN_FUSION = __import__("os").environ.get("VBX_CHAIN_FUSION", "1") != "0"
 # discriminator-phase backward enqueued on a forked stream before the generator's backward (independent work)
 _PHASE_OVERLAP = __import__("os").environ.get("VBX_PHASE_OVERLAP", "1") != "0"
+# D(reference) forward started before the generator's forward (independent work)
+_EARLY_REFERENCE = __import__("os").environ.get("VBX_EARLY_REFERENCE", "1") != "0"
 
 
 class _SegmentedStep:
@@ -295,8 +297,18 @@ class EBENLightningModule(torch.nn.Module):
                 opt.materialize()
         d_params = [p for grp in d_opt.param_groups for p in grp["params"]]
         with share_weight_norm():
-            enhanced, enhanced_bands = G(corrupted_speech)
+            # D(reference) does not depend on the generator: on a GPU it is started first, on the discriminator's side
+            # streams, and the generator's forward - a serial chain of small kernels - runs underneath it
+            early = _EARLY_REFERENCE and hasattr(D, "forward_multi") and reference_speech.is_cuda
             reference_bands = G.pqmf.forward(reference_speech, "analysis")
+            reference_embeddings = None
+            if early:
+                Flags.gated_chain = _CHAIN_FUSION
+                try:
+                    (reference_embeddings,) = D.forward_multi([(reference_bands, reference_speech)], join=False)
+                finally:
+                    Flags.gated_chain = False
+            enhanced, enhanced_bands = G(corrupted_speech)
             enh = enhanced.detach().requires_grad_(True)
             bands = enhanced_bands.detach().requires_grad_(True)
             Flags.param_grads = False                      # generator phase: no D parameter gradients
@@ -309,7 +321,9 @@ class EBENLightningModule(torch.nn.Module):
                 # LeakyReLU / feature-matching backward of the stage before it
                 Flags.gated_chain = _CHAIN_FUSION
                 try:
-                    if hasattr(D, "forward_multi"):
+                    if early:
+                        (enhanced_embeddings,) = D.forward_multi([(bands, enh)])        # (joins the reference pass too)
+                    elif hasattr(D, "forward_multi"):
                         enhanced_embeddings, reference_embeddings = D.forward_multi(
                             [(bands, enh), (reference_bands, reference_speech)])
                     else:

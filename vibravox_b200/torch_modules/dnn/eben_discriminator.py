@@ -58,8 +58,11 @@ class DiscriminatorEBENMultiScales(nn.Module, PyTorchModelHubMixin):
     def forward(self, bands: torch.Tensor, audio: torch.Tensor) -> List[List[torch.Tensor]]:
         return self.forward_multi([(bands, audio)])[0]
 
-    def forward_multi(self, pairs) -> List[List[List[torch.Tensor]]]:
+    def forward_multi(self, pairs, join: bool = True) -> List[List[List[torch.Tensor]]]:
         """forward() for several independent (bands, audio) pairs at once (e.g. enhanced and reference).
+        `join=False` leaves the work running on the side streams (the caller's stream does NOT wait for it): the training
+        step starts the reference pass this way before the generator's forward, which does not depend on it, and joins
+        with the next call / `join_streams()`.
         The four sub-discriminators are independent chains of small / medium kernels: each runs on its own
         stream so that together they fill the 148 SMs; autograd replays each chain's backward on the stream
         its forward ran on and inserts the cross-stream waits itself."""
@@ -106,8 +109,9 @@ class DiscriminatorEBENMultiScales(nn.Module, PyTorchModelHubMixin):
                     for t in emb[1:]:
                         t.record_stream(cur)            # consumed by the losses on the caller's stream
                     out[j][i] = emb
-        for st in streams:
-            cur.wait_stream(st)
+        if join:
+            for st in streams:
+                cur.wait_stream(st)
         return out
 
     def join_streams(self) -> None:
